@@ -1,0 +1,524 @@
+// Persistent, warp-specialised bf16 GEMM for sm_100a: TMA -> shared memory (SWIZZLE_128B) ->
+// tcgen05.mma with the fp32 accumulator in TMEM -> tcgen05.ld epilogue with the LoRA / AdaLN fusions.
+//
+//   acc = A0 . B0^T  (+ A1 . B1^T)      both operands K-major (row-major with K contiguous)
+//
+// The second contraction segment is the LoRA up-projection: it lands in the SAME TMEM tile as the
+// frozen base GEMM, so the adapter costs one extra 64-wide k-block and no extra pass over the output
+// (reference: toolkit/network_mixins.py:304-342 runs it as ~8 separate full-size elementwise kernels).
+//
+// Roles (192 threads):  warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread MMA issuer,
+// warps 2..5 = epilogue (one TMEM sub-partition each).  Two TMEM accumulator stages let the epilogue
+// of tile i overlap the main loop of tile i+1.
+//
+// CG == 2 pairs two CTAs of a cluster on one 256 x BN tile (tcgen05.mma.cta_group::2): each CTA loads
+// its own 128 rows of A and HALF of the B tile, which halves the L2->SM traffic per flop.
+#include "common.cuh"
+#include "ctx.h"
+
+namespace b200 {
+
+struct GemmArgs {
+  int M, N;
+  int kb0, kb1;  // 64-wide k-blocks in segment 0 / 1
+  int splits;    // split-K factor (out_f32 only)
+  int group_m;   // rasterisation group (tile rows per group)
+  const bf16* bias;
+  const bf16* res;
+  int ldres;
+  const bf16* gate;
+  int ldgate;
+  int rows_per_sample;
+  const bf16* aux_in;
+  int ldaux_in;
+  bf16* aux_out;
+  int ldaux_out;
+  void* out;
+  int ldo;
+  int act;
+  int out_f32;
+};
+
+constexpr uint32_t kPeerMask = 0xFEFFFFFFu;  // clears the CTA-rank bit of a shared::cluster address (pair leader)
+
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx_cluster(uint32_t bar_addr, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cluster.b64 _, [%0], %1;" ::"r"(bar_addr), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_addr) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(bar_addr) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_cg2(uint32_t smem_dst, const CUtensorMap* tmap, uint32_t bar_addr, int c0,
+                                                int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], "
+      "[%2];" ::"r"(smem_dst),
+      "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar_addr), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void umma_bf16_ss_cg2(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                                 uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_cg2_mc(uint64_t* bar) {
+  const uint16_t mask = 3;
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::
+                   "r"(smem_u32(bar)),
+               "h"(mask)
+               : "memory");
+}
+template <int NCOLS>
+__device__ __forceinline__ void tmem_alloc_cg2(uint32_t* smem_result) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_result)),
+               "n"(NCOLS)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+template <int NCOLS>
+__device__ __forceinline__ void tmem_dealloc_cg2(uint32_t taddr) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(NCOLS) : "memory");
+}
+
+// tile index -> (split, m_blk, n_blk) with grouped rasterisation: tiles of `group_m` consecutive tile
+// rows are visited column by column so that one wave re-uses both operand panels out of L2.
+__device__ __forceinline__ void tile_coords(int t, int m_tiles, int n_tiles, int group_m, int& split, int& m_blk,
+                                            int& n_blk) {
+  const int per_split = m_tiles * n_tiles;
+  split = t / per_split;
+  int r = t - split * per_split;
+  const int group_size = group_m * n_tiles;
+  const int grp = r / group_size;
+  const int first_m = grp * group_m;
+  const int gm = min(group_m, m_tiles - first_m);
+  const int in_grp = r - grp * group_size;
+  m_blk = first_m + in_grp % gm;
+  n_blk = in_grp / gm;
+}
+
+__device__ __forceinline__ void load8_bf16(const bf16* p, float (&v)[8]) {
+  uint4 u = *reinterpret_cast<const uint4*>(p);
+  float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
+  v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y; v[4] = c.x; v[5] = c.y; v[6] = d.x; v[7] = d.y;
+}
+__device__ __forceinline__ void store8_bf16(bf16* p, const float (&v)[8]) {
+  uint4 u;
+  u.x = pack_bf16x2(v[0], v[1]);
+  u.y = pack_bf16x2(v[2], v[3]);
+  u.z = pack_bf16x2(v[4], v[5]);
+  u.w = pack_bf16x2(v[6], v[7]);
+  *reinterpret_cast<uint4*>(p) = u;
+}
+
+// Epilogue for 32 consecutive columns of one output row held in registers.
+__device__ __forceinline__ void epilogue_row32(const GemmArgs& g, int row, int n0, int split, const uint32_t (&r)[32]) {
+  if (row >= g.M) return;
+  if (g.out_f32) {
+    float* o = reinterpret_cast<float*>(g.out) + (static_cast<size_t>(split) * g.M + row) * g.ldo + n0;
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) {
+      if (n0 + j < g.N) {
+        float4 v = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
+                               __uint_as_float(r[j + 3]));
+        *reinterpret_cast<float4*>(o + j) = v;
+      }
+    }
+    return;
+  }
+  const int sample = (g.gate != nullptr) ? row / g.rows_per_sample : 0;
+#pragma unroll
+  for (int j = 0; j < 32; j += 8) {
+    const int n = n0 + j;
+    if (n >= g.N) break;
+    float v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[j + i]);
+    if (g.bias != nullptr) {
+      float b[8];
+      load8_bf16(g.bias + n, b);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] += b[i];
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = bf16_round(v[i]);
+    if (g.aux_out != nullptr) store8_bf16(g.aux_out + static_cast<size_t>(row) * g.ldaux_out + n, v);
+    if (g.act == B200_ACT_GELU_TANH) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = bf16_round(gelu_tanh(v[i]));
+    }
+    if (g.aux_in != nullptr) {
+      float a[8];
+      load8_bf16(g.aux_in + static_cast<size_t>(row) * g.ldaux_in + n, a);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = bf16_round(v[i] * gelu_tanh_grad(a[i]));
+    }
+    if (g.gate != nullptr) {
+      float gt[8];
+      load8_bf16(g.gate + static_cast<size_t>(sample) * g.ldgate + n, gt);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = bf16_round(v[i] * gt[i]);
+    }
+    if (g.res != nullptr) {
+      float rs[8];
+      load8_bf16(g.res + static_cast<size_t>(row) * g.ldres + n, rs);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = bf16_round(v[i] + rs[i]);
+    }
+    store8_bf16(reinterpret_cast<bf16*>(g.out) + static_cast<size_t>(row) * g.ldo + n, v);
+  }
+}
+
+template <int CG, int BN, int STAGES>
+struct GemmCfg {
+  static constexpr int BM = 128;
+  static constexpr int BK = 64;
+  static constexpr int BNL = BN / CG;  // rows of the B tile this CTA loads
+  static constexpr uint32_t A_BYTES = BM * BK * 2;
+  static constexpr uint32_t B_BYTES = BNL * BK * 2;
+  static constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int TMEM_COLS = 2 * BN;
+  static constexpr size_t SMEM_BYTES = 1024 + static_cast<size_t>(STAGES) * STAGE_BYTES + (2 * STAGES + 4) * 8 + 16;
+  static_assert(BN % 16 == 0 && BN >= 32 && BN <= 256, "invalid UMMA N");
+  static_assert(TMEM_COLS == 64 || TMEM_COLS == 128 || TMEM_COLS == 256 || TMEM_COLS == 512, "TMEM cols pow2");
+  static_assert(SMEM_BYTES <= 232448, "exceeds 227 KB of shared memory");
+};
+
+template <int CG, int BN, int STAGES>
+__global__ void __launch_bounds__(192, 1)
+gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmB0,
+                 const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmB1,
+                 const GemmArgs g) {
+  using C = GemmCfg<CG, BN, STAGES>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * C::STAGE_BYTES);
+  uint64_t* empty = full + STAGES;
+  uint64_t* tfull = empty + STAGES;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  uint32_t cta_rank = 0;
+  if (CG == 2) asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(cta_rank));
+  const bool leader = (cta_rank == 0);
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA0);
+    tma_prefetch_desc(&tmB0);
+    if (g.kb1 > 0) {
+      tma_prefetch_desc(&tmA1);
+      tma_prefetch_desc(&tmB1);
+    }
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int s = 0; s < STAGES; ++s) {
+        mbar_init(&full[s], CG);  // one arrive.expect_tx per producing CTA
+        mbar_init(&empty[s], 1);  // one tcgen05.commit
+      }
+      for (int a = 0; a < 2; ++a) {
+        mbar_init(&tfull[a], 1);
+        mbar_init(&tempty[a], 128 * CG);  // every epilogue thread of every CTA of the pair
+      }
+      fence_barrier_init();
+    }
+    __syncwarp();
+    if (CG == 2)
+      tmem_alloc_cg2<C::TMEM_COLS>(tmem_slot);
+    else
+      tmem_alloc<C::TMEM_COLS>(tmem_slot);
+  }
+  tc_fence_before();
+  if (CG == 2)
+    cluster_sync_all();
+  else
+    __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
+
+  const int m_tiles = (g.M + C::BM * CG - 1) / (C::BM * CG);
+  const int n_tiles = (g.N + BN - 1) / BN;
+  const int splits = g.splits > 1 ? g.splits : 1;
+  const int total_tiles = m_tiles * n_tiles * splits;
+  const int kb_total = g.kb0 + g.kb1;
+  const int kb_per_split = (kb_total + splits - 1) / splits;
+  const int worker = blockIdx.x / CG;
+  const int nworkers = gridDim.x / CG;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = worker; t < total_tiles; t += nworkers) {
+        int split, m_blk, n_blk;
+        tile_coords(t, m_tiles, n_tiles, g.group_m, split, m_blk, n_blk);
+        const int row_a = m_blk * C::BM * CG + static_cast<int>(cta_rank) * C::BM;
+        const int row_b = n_blk * BN + static_cast<int>(cta_rank) * C::BNL;
+        const int kb_begin = split * kb_per_split;
+        const int kb_end = min(kb_total, kb_begin + kb_per_split);
+        for (int kb = kb_begin; kb < kb_end; ++kb) {
+          mbar_wait(&empty[stage], phase ^ 1u, 1);
+          uint8_t* sa = smem + stage * C::STAGE_BYTES;
+          uint8_t* sb = sa + C::A_BYTES;
+          const bool seg1 = kb >= g.kb0;
+          const CUtensorMap* ma = seg1 ? &tmA1 : &tmA0;
+          const CUtensorMap* mb = seg1 ? &tmB1 : &tmB0;
+          const int kc = (seg1 ? kb - g.kb0 : kb) * C::BK;
+          if (CG == 2) {
+            const uint32_t bar = smem_u32(&full[stage]) & kPeerMask;  // the pair leader's barrier
+            mbar_arrive_expect_tx_cluster(bar, C::STAGE_BYTES);
+            tma_load_2d_cg2(smem_u32(sa), ma, bar, kc, row_a);
+            tma_load_2d_cg2(smem_u32(sb), mb, bar, kc, row_b);
+          } else {
+            mbar_arrive_expect_tx(&full[stage], C::STAGE_BYTES);
+            tma_load_2d(sa, ma, &full[stage], kc, row_a);
+            tma_load_2d(sb, mb, &full[stage], kc, row_b);
+          }
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer (one thread)
+    if (leader && lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(C::BM * CG, BN, 0, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int t = worker; t < total_tiles; t += nworkers) {
+        int split, m_blk, n_blk;
+        tile_coords(t, m_tiles, n_tiles, g.group_m, split, m_blk, n_blk);
+        const int kb_begin = split * kb_per_split;
+        const int kb_end = min(kb_total, kb_begin + kb_per_split);
+        mbar_wait(&tempty[acc], acc_phase ^ 1u, 2);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BN);
+        for (int kb = kb_begin; kb < kb_end; ++kb) {
+          mbar_wait(&full[stage], phase, 3);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * C::STAGE_BYTES);
+          const uint32_t sb = sa + C::A_BYTES;
+          const uint64_t da = umma_desc_sw128(sa, 1024, 16);
+          const uint64_t db = umma_desc_sw128(sb, 1024, 16);
+#pragma unroll
+          for (int k = 0; k < C::BK / 16; ++k) {
+            const uint32_t accum = (kb > kb_begin || k > 0) ? 1u : 0u;
+            // advancing K by 16 bf16 = 32 bytes inside the 128-byte swizzle row: +2 in the >>4 address field
+            if (CG == 2)
+              umma_bf16_ss_cg2(d_tmem, da + 2u * k, db + 2u * k, idesc, accum);
+            else
+              umma_bf16_ss(d_tmem, da + 2u * k, db + 2u * k, idesc, accum);
+          }
+          if (CG == 2)
+            umma_commit_cg2_mc(&empty[stage]);
+          else
+            umma_commit(&empty[stage]);
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+        if (CG == 2)
+          umma_commit_cg2_mc(&tfull[acc]);
+        else
+          umma_commit(&tfull[acc]);
+        if (++acc == 2) {
+          acc = 0;
+          acc_phase ^= 1u;
+        }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue (warps 2..5)
+    const int q = warp & 3;  // TMEM sub-partition this warp may read
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int t = worker; t < total_tiles; t += nworkers) {
+      int split, m_blk, n_blk;
+      tile_coords(t, m_tiles, n_tiles, g.group_m, split, m_blk, n_blk);
+      const int kb_begin = split * kb_per_split;
+      const int kb_end = min(kb_total, kb_begin + kb_per_split);
+      const int row = m_blk * C::BM * CG + static_cast<int>(cta_rank) * C::BM + q * 32 + lane;
+      const int n_base = n_blk * BN;
+      mbar_wait(&tfull[acc], acc_phase, 4);
+      tc_fence_after();
+      const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * BN);
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t r[32];
+        if (kb_end > kb_begin) {
+          tmem_ld_32x32(t_addr + static_cast<uint32_t>(c * 32), r);
+          tmem_ld_wait();
+        } else {  // empty split-K slice: its partial result is exactly zero
+#pragma unroll
+          for (int i = 0; i < 32; ++i) r[i] = 0u;
+        }
+        epilogue_row32(g, row, n_base + c * 32, split, r);
+      }
+      tc_fence_before();
+      if (CG == 2)
+        mbar_arrive_cluster(smem_u32(&tempty[acc]) & kPeerMask);
+      else
+        mbar_arrive(&tempty[acc]);
+      if (++acc == 2) {
+        acc = 0;
+        acc_phase ^= 1u;
+      }
+    }
+  }
+
+  // ------------------------------------------------------------------ teardown
+  tc_fence_before();
+  if (CG == 2)
+    cluster_sync_all();
+  else
+    __syncthreads();
+  tc_fence_after();
+  if (warp == 1) {
+    if (CG == 2)
+      tmem_dealloc_cg2<C::TMEM_COLS>(tmem_base);
+    else
+      tmem_dealloc<C::TMEM_COLS>(tmem_base);
+  }
+}
+
+template <int CG, int BN, int STAGES>
+static int launch_gemm(b200_ctx* ctx, const CUtensorMap& a0, const CUtensorMap& b0, const CUtensorMap& a1,
+                       const CUtensorMap& b1, const GemmArgs& args, cudaStream_t stream) {
+  using C = GemmCfg<CG, BN, STAGES>;
+  auto kern = gemm_bf16_kernel<CG, BN, STAGES>;
+  static bool configured = false;
+  if (!configured) {
+    B200_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES));
+    configured = true;
+  }
+  const int m_tiles = (args.M + C::BM * CG - 1) / (C::BM * CG);
+  const int n_tiles = (args.N + BN - 1) / BN;
+  const int splits = args.splits > 1 ? args.splits : 1;
+  const int total = m_tiles * n_tiles * splits;
+  int workers = ctx->sm_count / CG;
+  if (total < workers) workers = total;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(workers * CG, 1, 1);
+  cfg.blockDim = dim3(192, 1, 1);
+  cfg.dynamicSmemBytes = C::SMEM_BYTES;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CG;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = (CG == 2) ? 1 : 0;
+  B200_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, a0, b0, a1, b1, args));
+  ctx->launches.fetch_add(1);
+  return B200_OK;
+}
+
+}  // namespace b200
+
+extern "C" int b200_gemm_bf16(b200_ctx* ctx, const b200_gemm_desc* d, void* stream_v) {
+  using namespace b200;
+  int rc = check_ctx(ctx);
+  if (rc != B200_OK) return rc;
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_v);
+  B200_REQUIRE(d != nullptr, "b200_gemm_bf16: null descriptor");
+  B200_REQUIRE(d->M > 0 && d->N > 0 && d->K0 > 0 && d->K1 >= 0, "b200_gemm_bf16: bad shape M=%d N=%d K0=%d K1=%d", d->M,
+               d->N, d->K0, d->K1);
+  B200_REQUIRE(d->A0 && d->B0 && d->out, "b200_gemm_bf16: null operand");
+  B200_REQUIRE(d->N % 8 == 0 && d->ldo % 8 == 0, "b200_gemm_bf16: N (%d) and ldo (%d) must be multiples of 8", d->N,
+               d->ldo);
+  B200_REQUIRE(d->K0 % 8 == 0 && d->K1 % 8 == 0, "b200_gemm_bf16: K0/K1 must be multiples of 8");
+  if (d->K1 > 0) B200_REQUIRE(d->A1 && d->B1, "b200_gemm_bf16: K1 > 0 but A1/B1 null");
+  if (d->gate) B200_REQUIRE(d->rows_per_sample > 0 && d->ldgate % 8 == 0, "b200_gemm_bf16: gate needs rows_per_sample");
+  if (d->res) B200_REQUIRE(d->ldres % 8 == 0, "b200_gemm_bf16: ldres %% 8");
+  if (d->aux_in) B200_REQUIRE(d->ldaux_in % 8 == 0, "b200_gemm_bf16: ldaux_in %% 8");
+  if (d->aux_out) B200_REQUIRE(d->ldaux_out % 8 == 0, "b200_gemm_bf16: ldaux_out %% 8");
+  const int splits = d->splits > 1 ? d->splits : 1;
+  if (splits > 1) B200_REQUIRE(d->out_f32, "b200_gemm_bf16: split-K needs out_f32");
+  if (d->out_f32)
+    B200_REQUIRE(!d->bias && !d->res && !d->gate && !d->aux_in && !d->aux_out && d->act == 0 && d->ldo % 4 == 0,
+                 "b200_gemm_bf16: out_f32 excludes the fused epilogue");
+
+  int config = d->config;
+  if (config == B200_GEMM_AUTO) {
+    if (d->N <= 64)
+      config = B200_GEMM_1CTA_N64;
+    else if (d->N <= 128)
+      config = B200_GEMM_1CTA_N128;
+    else {
+      static int def = -1;
+      if (def < 0) {
+        const char* e = getenv("B200_GEMM_CG");
+        def = (e && e[0] == '1') ? B200_GEMM_1CTA_N256 : B200_GEMM_2CTA_N256;
+      }
+      config = def;
+    }
+  }
+
+  GemmArgs a;
+  a.M = d->M;
+  a.N = d->N;
+  a.kb0 = (d->K0 + 63) / 64;
+  a.kb1 = (d->K1 + 63) / 64;
+  a.splits = splits;
+  a.group_m = 8;
+  a.bias = reinterpret_cast<const bf16*>(d->bias);
+  a.res = reinterpret_cast<const bf16*>(d->res);
+  a.ldres = d->ldres;
+  a.gate = reinterpret_cast<const bf16*>(d->gate);
+  a.ldgate = d->ldgate;
+  a.rows_per_sample = d->rows_per_sample > 0 ? d->rows_per_sample : 1;
+  a.aux_in = reinterpret_cast<const bf16*>(d->aux_in);
+  a.ldaux_in = d->ldaux_in;
+  a.aux_out = reinterpret_cast<bf16*>(d->aux_out);
+  a.ldaux_out = d->ldaux_out;
+  a.out = d->out;
+  a.ldo = d->ldo;
+  a.act = d->act;
+  a.out_f32 = d->out_f32;
+
+  uint32_t box_b;
+  switch (config) {
+    case B200_GEMM_1CTA_N256: box_b = 256; break;
+    case B200_GEMM_2CTA_N256: box_b = 128; a.group_m = 4; break;
+    case B200_GEMM_1CTA_N128: box_b = 128; break;
+    case B200_GEMM_1CTA_N64: box_b = 64; break;
+    default: set_error("b200_gemm_bf16: unknown config %d", config); return B200_ERR_INVALID;
+  }
+  CUtensorMap tA0, tB0, tA1, tB1;
+  rc = make_tmap_bf16_2d(ctx, &tA0, d->A0, d->M, d->K0, d->lda0, 64, 128);
+  if (rc) return rc;
+  rc = make_tmap_bf16_2d(ctx, &tB0, d->B0, d->N, d->K0, d->ldb0, 64, box_b);
+  if (rc) return rc;
+  if (d->K1 > 0) {
+    rc = make_tmap_bf16_2d(ctx, &tA1, d->A1, d->M, d->K1, d->lda1, 64, 128);
+    if (rc) return rc;
+    rc = make_tmap_bf16_2d(ctx, &tB1, d->B1, d->N, d->K1, d->ldb1, 64, box_b);
+    if (rc) return rc;
+  } else {
+    tA1 = tA0;
+    tB1 = tB0;
+  }
+  switch (config) {
+    case B200_GEMM_1CTA_N256: return launch_gemm<1, 256, 4>(ctx, tA0, tB0, tA1, tB1, a, stream);
+    case B200_GEMM_2CTA_N256: return launch_gemm<2, 256, 6>(ctx, tA0, tB0, tA1, tB1, a, stream);
+    case B200_GEMM_1CTA_N128: return launch_gemm<1, 128, 6>(ctx, tA0, tB0, tA1, tB1, a, stream);
+    case B200_GEMM_1CTA_N64: return launch_gemm<1, 64, 8>(ctx, tA0, tB0, tA1, tB1, a, stream);
+  }
+  return B200_ERR_INVALID;
+}
