@@ -51,7 +51,7 @@ __device__ __forceinline__ uint32_t mbar_try_wait(uint64_t* bar, uint32_t parity
       : "memory");
   return ok;
 }
-__device__ __noinline__ void mbar_timeout_trap(int tag) {
+static __device__ __noinline__ void mbar_timeout_trap(int tag) {
   printf("[b200] mbarrier watchdog: block %d thread %d tag %d\n", blockIdx.x, threadIdx.x, tag);
   __trap();
 }

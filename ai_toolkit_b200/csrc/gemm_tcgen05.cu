@@ -36,7 +36,11 @@ struct GemmArgs {
   void* out;
   int ldo;
   int act;
-  int out_f32;
+  int f32_mode;   // 0 = bf16 epilogue, 1 = fp32 partial store (split-K), 2 = fp32 atomic accumulate
+  int f32_trans;  // f32_mode 2: write out[n * ldo + m] instead of out[m * ldo + n]
+  int n_store;    // f32 modes: only columns [0, n_store) are written
+  float alpha;    // accumulator scale applied before the epilogue
+  const float* row_alpha;  // optional per-sample scale [ceil(M / rows_per_sample)]
 };
 
 constexpr uint32_t kPeerMask = 0xFEFFFFFFu;  // clears the CTA-rank bit of a shared::cluster address (pair leader)
@@ -121,26 +125,39 @@ __device__ __forceinline__ void store8_bf16(bf16* p, const float (&v)[8]) {
 // Epilogue for 32 consecutive columns of one output row held in registers.
 __device__ __forceinline__ void epilogue_row32(const GemmArgs& g, int row, int n0, int split, const uint32_t (&r)[32]) {
   if (row >= g.M) return;
-  if (g.out_f32) {
+  const int sample = (g.gate != nullptr || g.row_alpha != nullptr) ? row / g.rows_per_sample : 0;
+  const float alpha = g.alpha * (g.row_alpha != nullptr ? g.row_alpha[sample] : 1.0f);
+  if (g.f32_mode == 1) {
     float* o = reinterpret_cast<float*>(g.out) + (static_cast<size_t>(split) * g.M + row) * g.ldo + n0;
 #pragma unroll
     for (int j = 0; j < 32; j += 4) {
-      if (n0 + j < g.N) {
-        float4 v = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
-                               __uint_as_float(r[j + 3]));
+      if (n0 + j < g.n_store) {
+        float4 v = make_float4(alpha * __uint_as_float(r[j]), alpha * __uint_as_float(r[j + 1]),
+                               alpha * __uint_as_float(r[j + 2]), alpha * __uint_as_float(r[j + 3]));
         *reinterpret_cast<float4*>(o + j) = v;
       }
     }
     return;
   }
-  const int sample = (g.gate != nullptr) ? row / g.rows_per_sample : 0;
+  if (g.f32_mode == 2) {
+    float* o = reinterpret_cast<float*>(g.out);
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      const int n = n0 + j;
+      if (n < g.n_store) {
+        const size_t idx = g.f32_trans ? static_cast<size_t>(n) * g.ldo + row : static_cast<size_t>(row) * g.ldo + n;
+        atomicAdd(o + idx, alpha * __uint_as_float(r[j]));
+      }
+    }
+    return;
+  }
 #pragma unroll
   for (int j = 0; j < 32; j += 8) {
     const int n = n0 + j;
     if (n >= g.N) break;
     float v[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[j + i]);
+    for (int i = 0; i < 8; ++i) v[i] = alpha * __uint_as_float(r[j + i]);
     if (g.bias != nullptr) {
       float b[8];
       load8_bf16(g.bias + n, b);
@@ -176,7 +193,7 @@ __device__ __forceinline__ void epilogue_row32(const GemmArgs& g, int row, int n
   }
 }
 
-template <int CG, int BN, int STAGES>
+template <int CG, int BN, int STAGES, int A_MN, int B_MN>
 struct GemmCfg {
   static constexpr int BM = 128;
   static constexpr int BK = 64;
@@ -191,12 +208,12 @@ struct GemmCfg {
   static_assert(SMEM_BYTES <= 232448, "exceeds 227 KB of shared memory");
 };
 
-template <int CG, int BN, int STAGES>
+template <int CG, int BN, int STAGES, int A_MN, int B_MN>
 __global__ void __launch_bounds__(192, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmB0,
                  const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmB1,
                  const GemmArgs g) {
-  using C = GemmCfg<CG, BN, STAGES>;
+  using C = GemmCfg<CG, BN, STAGES, A_MN, B_MN>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * C::STAGE_BYTES);
@@ -274,15 +291,37 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
           const CUtensorMap* ma = seg1 ? &tmA1 : &tmA0;
           const CUtensorMap* mb = seg1 ? &tmB1 : &tmB0;
           const int kc = (seg1 ? kb - g.kb0 : kb) * C::BK;
+          // K-major operand: one box {64 k, rows}.  MN-major operand (stored [k][mn], mn contiguous):
+          // boxes of {64 mn, 64 k}, 8 KB each, one per 64 rows of the tile (descriptor LBO = 8192).
           if (CG == 2) {
             const uint32_t bar = smem_u32(&full[stage]) & kPeerMask;  // the pair leader's barrier
             mbar_arrive_expect_tx_cluster(bar, C::STAGE_BYTES);
-            tma_load_2d_cg2(smem_u32(sa), ma, bar, kc, row_a);
-            tma_load_2d_cg2(smem_u32(sb), mb, bar, kc, row_b);
+            if (A_MN) {
+#pragma unroll
+              for (int i = 0; i < C::BM / 64; ++i) tma_load_2d_cg2(smem_u32(sa) + i * 8192, ma, bar, row_a + 64 * i, kc);
+            } else {
+              tma_load_2d_cg2(smem_u32(sa), ma, bar, kc, row_a);
+            }
+            if (B_MN) {
+#pragma unroll
+              for (int i = 0; i < C::BNL / 64; ++i) tma_load_2d_cg2(smem_u32(sb) + i * 8192, mb, bar, row_b + 64 * i, kc);
+            } else {
+              tma_load_2d_cg2(smem_u32(sb), mb, bar, kc, row_b);
+            }
           } else {
             mbar_arrive_expect_tx(&full[stage], C::STAGE_BYTES);
-            tma_load_2d(sa, ma, &full[stage], kc, row_a);
-            tma_load_2d(sb, mb, &full[stage], kc, row_b);
+            if (A_MN) {
+#pragma unroll
+              for (int i = 0; i < C::BM / 64; ++i) tma_load_2d(sa + i * 8192, ma, &full[stage], row_a + 64 * i, kc);
+            } else {
+              tma_load_2d(sa, ma, &full[stage], kc, row_a);
+            }
+            if (B_MN) {
+#pragma unroll
+              for (int i = 0; i < C::BNL / 64; ++i) tma_load_2d(sb + i * 8192, mb, &full[stage], row_b + 64 * i, kc);
+            } else {
+              tma_load_2d(sb, mb, &full[stage], kc, row_b);
+            }
           }
           if (++stage == STAGES) {
             stage = 0;
@@ -294,7 +333,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer (one thread)
     if (leader && lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(C::BM * CG, BN, 0, 0);
+      constexpr uint32_t idesc = umma_idesc_bf16(C::BM * CG, BN, A_MN, B_MN);
+      // k-step of 16: +32 B inside the swizzle row (K-major) or +16 rows * 128 B (MN-major), in 16-byte units
+      constexpr uint32_t a_kstep = A_MN ? 128u : 2u;
+      constexpr uint32_t b_kstep = B_MN ? 128u : 2u;
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -312,16 +354,15 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * C::STAGE_BYTES);
           const uint32_t sb = sa + C::A_BYTES;
-          const uint64_t da = umma_desc_sw128(sa, 1024, 16);
-          const uint64_t db = umma_desc_sw128(sb, 1024, 16);
+          const uint64_t da = umma_desc_sw128(sa, 1024, A_MN ? 8192 : 16);
+          const uint64_t db = umma_desc_sw128(sb, 1024, B_MN ? 8192 : 16);
 #pragma unroll
           for (int k = 0; k < C::BK / 16; ++k) {
             const uint32_t accum = (kb > kb_begin || k > 0) ? 1u : 0u;
-            // advancing K by 16 bf16 = 32 bytes inside the 128-byte swizzle row: +2 in the >>4 address field
             if (CG == 2)
-              umma_bf16_ss_cg2(d_tmem, da + 2u * k, db + 2u * k, idesc, accum);
+              umma_bf16_ss_cg2(d_tmem, da + a_kstep * k, db + b_kstep * k, idesc, accum);
             else
-              umma_bf16_ss(d_tmem, da + 2u * k, db + 2u * k, idesc, accum);
+              umma_bf16_ss(d_tmem, da + a_kstep * k, db + b_kstep * k, idesc, accum);
           }
           if (CG == 2)
             umma_commit_cg2_mc(&empty[stage]);
@@ -357,8 +398,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       mbar_wait(&tfull[acc], acc_phase, 4);
       tc_fence_after();
       const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * BN);
+      const int n_limit = g.f32_mode ? g.n_store : g.N;
 #pragma unroll 1
       for (int c = 0; c < BN / 32; ++c) {
+        if (n_base + c * 32 >= n_limit) break;
         uint32_t r[32];
         if (kb_end > kb_begin) {
           tmem_ld_32x32(t_addr + static_cast<uint32_t>(c * 32), r);
@@ -396,11 +439,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
   }
 }
 
-template <int CG, int BN, int STAGES>
+template <int CG, int BN, int STAGES, int A_MN, int B_MN>
 static int launch_gemm(b200_ctx* ctx, const CUtensorMap& a0, const CUtensorMap& b0, const CUtensorMap& a1,
                        const CUtensorMap& b1, const GemmArgs& args, cudaStream_t stream) {
-  using C = GemmCfg<CG, BN, STAGES>;
-  auto kern = gemm_bf16_kernel<CG, BN, STAGES>;
+  using C = GemmCfg<CG, BN, STAGES, A_MN, B_MN>;
+  auto kern = gemm_bf16_kernel<CG, BN, STAGES, A_MN, B_MN>;
   static bool configured = false;
   if (!configured) {
     B200_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES));
@@ -440,19 +483,25 @@ extern "C" int b200_gemm_bf16(b200_ctx* ctx, const b200_gemm_desc* d, void* stre
   B200_REQUIRE(d->M > 0 && d->N > 0 && d->K0 > 0 && d->K1 >= 0, "b200_gemm_bf16: bad shape M=%d N=%d K0=%d K1=%d", d->M,
                d->N, d->K0, d->K1);
   B200_REQUIRE(d->A0 && d->B0 && d->out, "b200_gemm_bf16: null operand");
-  B200_REQUIRE(d->N % 8 == 0 && d->ldo % 8 == 0, "b200_gemm_bf16: N (%d) and ldo (%d) must be multiples of 8", d->N,
-               d->ldo);
-  B200_REQUIRE(d->K0 % 8 == 0 && d->K1 % 8 == 0, "b200_gemm_bf16: K0/K1 must be multiples of 8");
+  const bool f32 = d->f32_mode != 0;
+  B200_REQUIRE(d->f32_mode >= 0 && d->f32_mode <= 2, "b200_gemm_bf16: f32_mode %d", d->f32_mode);
+  if (!f32) B200_REQUIRE(d->N % 8 == 0 && d->ldo % 8 == 0, "b200_gemm_bf16: N (%d) and ldo (%d) must be multiples of 8",
+                         d->N, d->ldo);
+  if (!d->trans_a) B200_REQUIRE(d->K0 % 8 == 0 && d->K1 % 8 == 0, "b200_gemm_bf16: K0/K1 must be multiples of 8");
+  if (d->trans_a) B200_REQUIRE(d->M % 8 == 0, "b200_gemm_bf16: trans_a needs M %% 8 == 0");
+  if (d->trans_b) B200_REQUIRE(d->N % 8 == 0, "b200_gemm_bf16: trans_b needs N %% 8 == 0");
   if (d->K1 > 0) B200_REQUIRE(d->A1 && d->B1, "b200_gemm_bf16: K1 > 0 but A1/B1 null");
   if (d->gate) B200_REQUIRE(d->rows_per_sample > 0 && d->ldgate % 8 == 0, "b200_gemm_bf16: gate needs rows_per_sample");
+  if (d->row_alpha) B200_REQUIRE(d->rows_per_sample > 0, "b200_gemm_bf16: row_alpha needs rows_per_sample");
   if (d->res) B200_REQUIRE(d->ldres % 8 == 0, "b200_gemm_bf16: ldres %% 8");
   if (d->aux_in) B200_REQUIRE(d->ldaux_in % 8 == 0, "b200_gemm_bf16: ldaux_in %% 8");
   if (d->aux_out) B200_REQUIRE(d->ldaux_out % 8 == 0, "b200_gemm_bf16: ldaux_out %% 8");
   const int splits = d->splits > 1 ? d->splits : 1;
-  if (splits > 1) B200_REQUIRE(d->out_f32, "b200_gemm_bf16: split-K needs out_f32");
-  if (d->out_f32)
-    B200_REQUIRE(!d->bias && !d->res && !d->gate && !d->aux_in && !d->aux_out && d->act == 0 && d->ldo % 4 == 0,
-                 "b200_gemm_bf16: out_f32 excludes the fused epilogue");
+  if (splits > 1) B200_REQUIRE(f32, "b200_gemm_bf16: split-K needs an fp32 output mode");
+  if (f32)
+    B200_REQUIRE(!d->bias && !d->res && !d->gate && !d->aux_in && !d->aux_out && d->act == 0,
+                 "b200_gemm_bf16: fp32 output excludes the fused epilogue");
+  if (d->f32_mode == 1) B200_REQUIRE(d->ldo % 4 == 0 && !d->f32_trans, "b200_gemm_bf16: f32 partial store needs ldo %% 4");
 
   int config = d->config;
   if (config == B200_GEMM_AUTO) {
@@ -490,35 +539,56 @@ extern "C" int b200_gemm_bf16(b200_ctx* ctx, const b200_gemm_desc* d, void* stre
   a.out = d->out;
   a.ldo = d->ldo;
   a.act = d->act;
-  a.out_f32 = d->out_f32;
+  a.f32_mode = d->f32_mode;
+  a.f32_trans = d->f32_trans;
+  a.n_store = (d->n_store > 0 && d->n_store < d->N) ? d->n_store : d->N;
+  a.alpha = d->alpha;
+  a.row_alpha = reinterpret_cast<const float*>(d->row_alpha);
 
-  uint32_t box_b;
+  int cg = 1, bn = 256;
   switch (config) {
-    case B200_GEMM_1CTA_N256: box_b = 256; break;
-    case B200_GEMM_2CTA_N256: box_b = 128; a.group_m = 4; break;
-    case B200_GEMM_1CTA_N128: box_b = 128; break;
-    case B200_GEMM_1CTA_N64: box_b = 64; break;
+    case B200_GEMM_1CTA_N256: cg = 1; bn = 256; break;
+    case B200_GEMM_2CTA_N256: cg = 2; bn = 256; a.group_m = 4; break;
+    case B200_GEMM_1CTA_N128: cg = 1; bn = 128; break;
+    case B200_GEMM_1CTA_N64: cg = 1; bn = 64; break;
     default: set_error("b200_gemm_bf16: unknown config %d", config); return B200_ERR_INVALID;
   }
+  const int ta = d->trans_a ? 1 : 0, tb = d->trans_b ? 1 : 0;
+  const uint32_t box_b_rows = static_cast<uint32_t>(bn / cg);
+  // K-major operand [rows = M|N, cols = K]: box {64 k, tile rows}.  MN-major operand [rows = K, cols = M|N]: box {64, 64}.
+  auto map_a = [&](CUtensorMap* t, const void* p, int K, int ld) {
+    return ta ? make_tmap_bf16_2d(ctx, t, p, K, d->M, ld, 64, 64) : make_tmap_bf16_2d(ctx, t, p, d->M, K, ld, 64, 128);
+  };
+  auto map_b = [&](CUtensorMap* t, const void* p, int K, int ld) {
+    return tb ? make_tmap_bf16_2d(ctx, t, p, K, d->N, ld, 64, 64)
+              : make_tmap_bf16_2d(ctx, t, p, d->N, K, ld, 64, box_b_rows);
+  };
   CUtensorMap tA0, tB0, tA1, tB1;
-  rc = make_tmap_bf16_2d(ctx, &tA0, d->A0, d->M, d->K0, d->lda0, 64, 128);
+  rc = map_a(&tA0, d->A0, d->K0, d->lda0);
   if (rc) return rc;
-  rc = make_tmap_bf16_2d(ctx, &tB0, d->B0, d->N, d->K0, d->ldb0, 64, box_b);
+  rc = map_b(&tB0, d->B0, d->K0, d->ldb0);
   if (rc) return rc;
   if (d->K1 > 0) {
-    rc = make_tmap_bf16_2d(ctx, &tA1, d->A1, d->M, d->K1, d->lda1, 64, 128);
+    rc = map_a(&tA1, d->A1, d->K1, d->lda1);
     if (rc) return rc;
-    rc = make_tmap_bf16_2d(ctx, &tB1, d->B1, d->N, d->K1, d->ldb1, 64, box_b);
+    rc = map_b(&tB1, d->B1, d->K1, d->ldb1);
     if (rc) return rc;
   } else {
     tA1 = tA0;
     tB1 = tB0;
   }
-  switch (config) {
-    case B200_GEMM_1CTA_N256: return launch_gemm<1, 256, 4>(ctx, tA0, tB0, tA1, tB1, a, stream);
-    case B200_GEMM_2CTA_N256: return launch_gemm<2, 256, 6>(ctx, tA0, tB0, tA1, tB1, a, stream);
-    case B200_GEMM_1CTA_N128: return launch_gemm<1, 128, 6>(ctx, tA0, tB0, tA1, tB1, a, stream);
-    case B200_GEMM_1CTA_N64: return launch_gemm<1, 64, 8>(ctx, tA0, tB0, tA1, tB1, a, stream);
-  }
+#define B200_LAUNCH(CG_, BN_, ST_, TA_, TB_) \
+  if (cg == CG_ && bn == BN_ && ta == TA_ && tb == TB_) return launch_gemm<CG_, BN_, ST_, TA_, TB_>(ctx, tA0, tB0, tA1, tB1, a, stream)
+  B200_LAUNCH(2, 256, 6, 0, 0);   // forward:  Y = X W^T
+  B200_LAUNCH(2, 256, 6, 0, 1);   // dgrad:    dX = dY W
+  B200_LAUNCH(1, 256, 4, 0, 0);
+  B200_LAUNCH(1, 256, 4, 0, 1);
+  B200_LAUNCH(1, 128, 6, 0, 0);
+  B200_LAUNCH(1, 128, 6, 0, 1);
+  B200_LAUNCH(1, 64, 8, 0, 0);    // rank-side: Z = X A^T
+  B200_LAUNCH(1, 64, 8, 0, 1);    // rank-side: T = dY B
+  B200_LAUNCH(1, 64, 8, 1, 1);    // wgrad:     dB = dY^T Z, dA^T = X^T T
+#undef B200_LAUNCH
+  set_error("b200_gemm_bf16: no kernel for config %d trans_a %d trans_b %d", config, ta, tb);
   return B200_ERR_INVALID;
 }

@@ -1,0 +1,152 @@
+"""Tensor-level wrappers over the C ABI (``include/b200_lora.h``).
+
+PyTorch tensors are used as device-memory handles only; every function here launches hand-written
+sm_100a kernels through ``ai_toolkit_b200.cabi`` on torch's current stream and raises ``B200Error``
+when the library or the device is missing.  There is no eager / CPU fallback.
+"""
+from __future__ import annotations
+
+from ctypes import c_void_p
+
+import torch
+
+from . import cabi
+from .cabi import ACT_GELU_TANH, ACT_NONE, gemm_bf16  # noqa: F401
+
+RANK_PAD = 64  # rank-side operands are padded to one 64-wide k-block
+
+
+def _p(t):
+    return None if t is None else c_void_p(t.data_ptr())
+
+
+def _ld(t):
+    return 0 if t is None else int(t.stride(-2))
+
+
+def _dev(t):
+    return t.device.index
+
+
+def ln_modulate_fwd(x, shift, scale, rows_per_sample, out=None, save_stats=True, eps=1e-6):
+    """x [M, D] bf16; shift/scale [S, D] bf16 views (row stride = stride(0)) or None."""
+    M, D = x.shape
+    out = torch.empty((M, D), device=x.device, dtype=torch.bfloat16) if out is None else out
+    mean = torch.empty(M, device=x.device, dtype=torch.float32) if save_stats else None
+    rstd = torch.empty(M, device=x.device, dtype=torch.float32) if save_stats else None
+    ldmod = int(scale.stride(0)) if scale is not None else (int(shift.stride(0)) if shift is not None else 8)
+    cabi.call("b200_ln_modulate_fwd", _p(x), _ld(x), _p(shift), _p(scale), ldmod, int(rows_per_sample), _p(out), _ld(out),
+              _p(mean), _p(rstd), M, D, float(eps), device=_dev(x))
+    return out, mean, rstd
+
+
+def ln_modulate_bwd(dy, x, mean, rstd, scale, rows_per_sample, dres=None, out=None):
+    M, D = x.shape
+    out = torch.empty((M, D), device=x.device, dtype=torch.bfloat16) if out is None else out
+    ldmod = int(scale.stride(0)) if scale is not None else 8
+    cabi.call("b200_ln_modulate_bwd", _p(dy), _ld(dy), _p(x), _ld(x), _p(mean), _p(rstd), _p(scale), ldmod,
+              int(rows_per_sample), _p(dres), _ld(dres), _p(out), _ld(out), M, D, device=_dev(x))
+    return out
+
+
+def col_reduce(a, rows_per_sample, b=None, mean=None, rstd=None, g=None, mul_out=None, sum_a=None, sum_ab=None):
+    """sum_a / sum_ab are fp32 views [S, D] (row stride = stride(0)) that are ACCUMULATED into."""
+    M, D = a.shape
+    ref = sum_a if sum_a is not None else sum_ab
+    ldsum = int(ref.stride(0)) if ref is not None else D
+    if sum_a is not None and sum_ab is not None:
+        assert sum_a.stride(0) == sum_ab.stride(0)
+    ldg = int(g.stride(0)) if g is not None else 0
+    cabi.call("b200_col_reduce", _p(a), _ld(a), _p(b), _ld(b), _p(mean), _p(rstd), _p(g), ldg, _p(mul_out), _ld(mul_out),
+              _p(sum_a), _p(sum_ab), ldsum, int(rows_per_sample), M, D, device=_dev(a))
+
+
+def qk_norm_rope_fwd(q, k, v, wq, wk, cos, sin, Q, K, V, B, Lseg, seq_off, eps=1e-6):
+    """q/k/v: [B*Lseg, H*128] bf16 views sharing one row stride; Q/K/V: [B, H, Ltot, 128] bf16."""
+    H, Ltot = Q.shape[1], Q.shape[2]
+    assert q.stride(0) == k.stride(0) == v.stride(0)
+    cabi.call("b200_qk_norm_rope_fwd", _p(q), _p(k), _p(v), int(q.stride(0)), _p(wq), _p(wk), _p(cos), _p(sin), _p(Q),
+              _p(K), _p(V), int(B), int(Lseg), int(seq_off), int(Ltot), int(H), 128, float(eps), device=_dev(q))
+
+
+def qk_norm_rope_bwd(dQ, dK, dV, q, k, wq, wk, cos, sin, dq, dk, dv, B, Lseg, seq_off, eps=1e-6):
+    H, Ltot = dQ.shape[1], dQ.shape[2]
+    assert q.stride(0) == k.stride(0) and dq.stride(0) == dk.stride(0) == dv.stride(0)
+    cabi.call("b200_qk_norm_rope_bwd", _p(dQ), _p(dK), _p(dV), _p(q), _p(k), int(q.stride(0)), _p(wq), _p(wk), _p(cos),
+              _p(sin), _p(dq), _p(dk), _p(dv), int(dq.stride(0)), int(B), int(Lseg), int(seq_off), int(Ltot), int(H), 128,
+              float(eps), device=_dev(q))
+
+
+def silu(x, out=None):
+    out = torch.empty_like(x) if out is None else out
+    cabi.call("b200_silu", _p(x), _p(out), x.numel(), device=_dev(x))
+    return out
+
+
+def timestep_embed(t01, dim=256, mult=1000.0, max_period=10000.0):
+    B = t01.shape[0]
+    out = torch.empty((B, dim), device=t01.device, dtype=torch.bfloat16)
+    cabi.call("b200_timestep_embed", _p(t01), _p(out), B, dim, float(max_period), float(mult), device=_dev(t01))
+    return out
+
+
+def add_bf16(a, b, c=None, out=None):
+    out = torch.empty_like(a) if out is None else out
+    cabi.call("b200_add_bf16", _p(a), _p(b), _p(c), _p(out), a.numel(), device=_dev(a))
+    return out
+
+
+def lora_gemv_fwd(x, W, bias, A=None, Bw=None, c=1.0, out=None):
+    """x [Bm, K] bf16, W [N, K] bf16, A [r, K] fp32, Bw [N, r] fp32 -> (y [Bm, N] bf16, z [Bm, r] fp32 | None)."""
+    Bm, K = x.shape
+    N = W.shape[0]
+    r = 0 if A is None else int(A.shape[0])
+    y = torch.empty((Bm, N), device=x.device, dtype=torch.bfloat16) if out is None else out
+    z = torch.empty((Bm, r), device=x.device, dtype=torch.float32) if r > 0 else None
+    cabi.call("b200_lora_gemv_fwd", _p(x), _ld(x), _p(W), _ld(W), _p(bias), _p(A), _p(Bw), r, float(c), _p(y), _ld(y),
+              _p(z), Bm, N, K, device=_dev(x))
+    return y, z
+
+
+def lora_gemv_bwd(dy, x, z, A, Bw, c, dA, dBw, t_ws=None):
+    """dy fp32 [Bm, N] (row stride = stride(0)); accumulates into dA [r, K], dBw [N, r] (fp32)."""
+    Bm, K = x.shape
+    N, r = Bw.shape
+    t_ws = torch.empty(Bm * r, device=x.device, dtype=torch.float32) if t_ws is None else t_ws
+    cabi.call("b200_lora_gemv_bwd", _p(dy), int(dy.stride(0)), _p(x), _ld(x), _p(z), _p(A), _p(Bw), r, float(c), _p(dA),
+              _p(dBw), _p(t_ws), Bm, N, K, device=_dev(x))
+
+
+def flow_add_noise(latents, noise, t, pack=True, out=None):
+    B, C, H, W = latents.shape
+    if out is None:
+        shape = (B, (H // 2) * (W // 2), C * 4) if pack else (B, C, H, W)
+        out = torch.empty(shape, device=latents.device, dtype=torch.bfloat16)
+    cabi.call("b200_flow_add_noise", _p(latents), _p(noise), _p(t), _p(out), B, C, H, W, int(pack), device=_dev(latents))
+    return out
+
+
+def flow_loss(pred, latents, noise, pack=True, gscale=1.0, dpred=None, want_grad=True, loss_ws=None):
+    """-> (loss_total [1] fp32, loss_per_sample [B] fp32, dpred like pred)."""
+    B, C, H, W = latents.shape
+    if want_grad and dpred is None:
+        dpred = torch.empty_like(pred)
+    if loss_ws is None:
+        loss_ws = torch.empty(B + 1, device=pred.device, dtype=torch.float32)
+    per, tot = loss_ws[:B], loss_ws[B:B + 1]
+    cabi.call("b200_flow_loss", _p(pred), _p(latents), _p(noise), _p(dpred if want_grad else None), _p(per), _p(tot), B, C,
+              H, W, int(pack), float(gscale), device=_dev(pred))
+    return tot, per, dpred
+
+
+def grad_sumsq(g, out_f64):
+    cabi.call("b200_grad_sumsq", _p(g), g.numel(), _p(out_f64), device=_dev(g))
+
+
+def clip_adamw(p, g, m, v, sumsq_f64, hyper, state, ema=None, norm_out=None):
+    cabi.call("b200_clip_adamw", _p(p), _p(g), _p(m), _p(v), _p(ema), _p(sumsq_f64), _p(hyper), _p(state), p.numel(),
+              _p(norm_out), device=_dev(p))
+
+
+def repack_lora(flat, pack, table_dev, n_entries):
+    cabi.call("b200_repack_lora", _p(flat), _p(pack), _p(table_dev), int(n_entries), device=_dev(flat))

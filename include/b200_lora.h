@@ -52,7 +52,7 @@ int64_t b200_ctx_launch_count(const b200_ctx* ctx);
 /*
  * Tensor-core GEMM with a two-segment contraction and a fused epilogue (tcgen05 / TMEM / TMA):
  *
- *   acc[M,N] = A0[M,K0] . B0[N,K0]^T  +  A1[M,K1] . B1[N,K1]^T          (fp32 accumulate in TMEM)
+ *   acc[M,N] = alpha * row_alpha[m / rows_per_sample] * ( op(A0)[M,K0] . op(B0)[N,K0]^T + op(A1)[M,K1] . op(B1)[N,K1]^T )
  *   y   = bf16(acc + bias[n])
  *   aux_out[m,n] = y                         (optional: pre-activation kept for backward)
  *   y   = bf16(gelu_tanh(y))                 (act == B200_ACT_GELU_TANH)
@@ -60,13 +60,25 @@ int64_t b200_ctx_launch_count(const b200_ctx* ctx);
  *   y   = bf16(y * gate[m / rows_per_sample, n])   (optional AdaLN-Zero gate)
  *   out[m,n] = bf16(res[m,n] + y)            (optional residual; res may alias out)
  *
+ * Operand storage (row-major, ld in elements):
+ *   trans_a == 0: A is [M, K] (K contiguous, "K-major");  trans_a != 0: A is stored [K, M] (M contiguous)
+ *   trans_b == 0: B is [N, K] (K contiguous);             trans_b != 0: B is stored [K, N] (N contiguous)
+ * so  forward  Y  = X W^T        is (trans_a 0, trans_b 0) with B0 = W[out,in]
+ *     dgrad    dX = dY W         is (trans_a 0, trans_b 1) with B0 = W[out,in] as stored (no transposed copy)
+ *     wgrad    dB = dY^T Z       is (trans_a 1, trans_b 1) with A0 = dY[tokens,out], B0 = Z[tokens,r]
+ * Both segments share the same trans flags.
+ *
  * The second segment is how the LoRA up-projection rides in the same TMEM tile as the frozen base
  * GEMM:  A1 = bf16(m_b * s * (x A^T)) padded to 64 columns, B1 = lora_up weight padded to 64 columns.
  * Replaces, per wrapped Linear, `org_forward(x) + (lora_up(lora_down(x.float())) * scale * multiplier).to(bf16)`
- * (toolkit/network_mixins.py:304-342) and the dX half of its autograd backward.
+ * (toolkit/network_mixins.py:304-342) and, with trans_b, the dX half of its autograd backward; the
+ * trans_a/trans_b form computes dA / dB (rank-r sides) without ever forming dW.
  *
- * out_f32 != 0: write the raw fp32 accumulator instead (no epilogue), `splits` partial results of a
- * split-K contraction go to out + split*M*ldo (used by the rank-side GEMMs).
+ * f32_mode 1: write the fp32 accumulator (no epilogue); `splits` partial results of a split-K
+ *             contraction go to out + split*M*ldo.
+ * f32_mode 2: atomically ADD alpha*acc (fp32) into out[m*ldo+n] (or out[n*ldo+m] when f32_trans), for the
+ *             columns n < n_store only; with `splits` > 1 the K range is split across CTAs (gradient
+ *             accumulation semantics: the caller zeroes `out` once per optimizer step).
  */
 typedef struct b200_gemm_desc {
   int32_t M, N, K0, K1;
@@ -74,20 +86,115 @@ typedef struct b200_gemm_desc {
   const void* B0; int32_t ldb0;
   const void* A1; int32_t lda1;
   const void* B1; int32_t ldb1;
+  int32_t trans_a, trans_b;
+  float alpha;                            /* accumulator scale (set 1.0f for none) */
+  const void* row_alpha;                  /* fp32 [ceil(M/rows_per_sample)] per-sample scale or NULL */
   const void* bias;                       /* bf16 [N] or NULL */
   const void* res; int32_t ldres;         /* bf16 [M,N] or NULL */
   const void* gate; int32_t ldgate;       /* bf16 [ceil(M/rows_per_sample), N] or NULL */
-  int32_t rows_per_sample;                /* >0 when gate is given */
+  int32_t rows_per_sample;                /* >0 when gate / row_alpha is given */
   const void* aux_in; int32_t ldaux_in;   /* bf16 [M,N] or NULL */
   void* aux_out; int32_t ldaux_out;       /* bf16 [M,N] or NULL */
-  void* out; int32_t ldo;                 /* bf16 [M,N] (or fp32 [splits,M,N] when out_f32) */
+  void* out; int32_t ldo;                 /* bf16 [M,N]; fp32 per f32_mode */
   int32_t act;
-  int32_t out_f32;
-  int32_t splits;                         /* split-K factor, only with out_f32 (0/1 = none) */
+  int32_t f32_mode;
+  int32_t f32_trans;
+  int32_t n_store;                        /* fp32 modes: columns written (0 = N) */
+  int32_t splits;                         /* split-K factor, fp32 modes only (0/1 = none) */
   int32_t config;                         /* B200_GEMM_* */
 } b200_gemm_desc;
 
 int b200_gemm_bf16(b200_ctx* ctx, const b200_gemm_desc* d, void* stream);
+
+
+/* -------------------------------------------------------------------------------------------------
+ * AdaLN-Zero modulation around LayerNorm (no affine):
+ *   out[m,:] = bf16( bf16( bf16(LN(x[m,:])) * bf16(1 + scale[s,:]) ) + shift[s,:] ),  s = m / rows_per_sample
+ * with the bf16 rounding points of the eager model (diffusers AdaLayerNormZero / the in-tree
+ * extensions_built_in/diffusion_models/chroma/src/layers.py:471-560).  shift/scale may be NULL (plain LN).
+ * mean/rstd [M] fp32 are saved for the backward.  D % 256 == 0.  Algorithmic bytes: 4 per element.
+ */
+int b200_ln_modulate_fwd(b200_ctx* ctx, const void* x, int ldx, const void* shift, const void* scale, int ldmod,
+                         int rows_per_sample, void* out, int ldo, void* mean, void* rstd, int M, int D, float eps,
+                         void* stream);
+/* out = dres + dLN/dx(dy * (1 + scale));  dres may be NULL.  Algorithmic bytes: 8 per element (6 without dres). */
+int b200_ln_modulate_bwd(b200_ctx* ctx, const void* dy, int lddy, const void* x, int ldx, const void* mean,
+                         const void* rstd, const void* scale, int ldmod, int rows_per_sample, const void* dres,
+                         int lddres, void* out, int ldo, int M, int D, void* stream);
+/*
+ * Per-sample column reductions for the gradients of the modulation vector (shift / scale / gate), fp32
+ * atomics into [samples, ldsum]:  sum_a += sum_rows a;  sum_ab += sum_rows a * f(b) with
+ * f(b) = (b - mean[m]) * rstd[m] when mean/rstd are given, else b;  optional mul_out = bf16(a * g[s,:]).
+ */
+int b200_col_reduce(b200_ctx* ctx, const void* a, int lda, const void* b, int ldb, const void* mean, const void* rstd,
+                    const void* g, int ldg, void* mul_out, int ldmul, void* sum_a, void* sum_ab, int ldsum,
+                    int rows_per_sample, int M, int D, void* stream);
+/*
+ * Per-head RMSNorm of q and k (weights wq/wk bf16 [128]), rotary embedding from fp32 cos/sin tables
+ * [Ltot,128] (pairs interleaved), and re-layout of q/k/v rows [B*Lseg, ld] into head-major Q/K/V
+ * [B, H, Ltot, 128] at sequence offset seq_off (text tokens first, then image tokens).
+ * Reference arithmetic: chroma/src/layers.py:72-91 (QKNorm), chroma/src/math.py:33-51 (apply_rope).
+ */
+int b200_qk_norm_rope_fwd(b200_ctx* ctx, const void* q, const void* k, const void* v, int ld, const void* wq,
+                          const void* wk, const void* cos_t, const void* sin_t, void* Q, void* K, void* V, int B, int Lseg,
+                          int seq_off, int Ltot, int H, int head_dim, float eps, void* stream);
+int b200_qk_norm_rope_bwd(b200_ctx* ctx, const void* dQ, const void* dK, const void* dV, const void* q, const void* k,
+                          int ld, const void* wq, const void* wk, const void* cos_t, const void* sin_t, void* dq, void* dk,
+                          void* dv, int ldd, int B, int Lseg, int seq_off, int Ltot, int H, int head_dim, float eps,
+                          void* stream);
+int b200_silu(b200_ctx* ctx, const void* x, void* y, int64_t n, void* stream);
+/* out[b,:] = bf16([cos(t f_i) | sin(t f_i)]), t = bf16(bf16(t01[b]) * mult)  (chroma/src/layers.py:30-53) */
+int b200_timestep_embed(b200_ctx* ctx, const void* t01, void* out, int B, int dim, float max_period, float mult,
+                        void* stream);
+int b200_add_bf16(b200_ctx* ctx, const void* a, const void* b, const void* c, void* y, int64_t n, void* stream);
+
+/* -------------------------------------------------------------------------------------------------
+ * LoRA-wrapped Linear for Bm <= 8 rows (the AdaLN modulation projections): weight streaming at the
+ * HBM roofline, fp32 master A [r,K] / B [N,r] used directly.
+ *   y = bf16( bf16(x W^T + bias) + bf16( (c x A^T) B^T ) );  z = c x A^T [Bm,r] fp32 is saved.
+ * r == 0: plain frozen Linear.  Replaces toolkit/network_mixins.py:304-342 for these modules.
+ */
+int b200_lora_gemv_fwd(b200_ctx* ctx, const void* x, int ldx, const void* W, int ldw, const void* bias, const void* A,
+                       const void* Bw, int r, float c, void* y, int ldy, void* z, int Bm, int N, int K, void* stream);
+/* dA += (c dy B)^T x,  dB += dy^T z   with dy fp32 [Bm, lddy];  t_ws: fp32 [Bm*r] scratch. */
+int b200_lora_gemv_bwd(b200_ctx* ctx, const void* dy, int lddy, const void* x, int ldx, const void* z, const void* A,
+                       const void* Bw, int r, float c, void* dA, void* dBw, void* t_ws, int Bm, int N, int K,
+                       void* stream);
+
+/* -------------------------------------------------------------------------------------------------
+ * Flow-matching batch preparation and loss.
+ * b200_flow_add_noise: out = bf16((1 - t/1000) x0 + (t/1000) noise), optionally written in FLUX's packed
+ *   "b c (h 2) (w 2) -> b (h w) (c 4)" layout (toolkit/samplers/custom_flowmatch_sampler.py:91-102,
+ *   toolkit/stable_diffusion_model.py:2166-2172).  t fp32 [B] in [0,1000].  8 bytes per latent element
+ *   together with b200_flow_loss's reads.
+ * b200_flow_loss: target = bf16(noise - x0); loss_per_sample[b] = mean((pred - target)^2);
+ *   loss_total = mean_b; dpred = bf16(2 (pred - target) gscale / (C H W B)) in pred's layout
+ *   (extensions_built_in/sd_trainer/SDTrainer.py:644-646, 916, 987-990, 1013).
+ */
+int b200_flow_add_noise(b200_ctx* ctx, const void* latents, const void* noise, const void* t, void* out, int B, int C,
+                        int H, int W, int pack, void* stream);
+int b200_flow_loss(b200_ctx* ctx, const void* pred, const void* latents, const void* noise, void* dpred,
+                   void* loss_per_sample, void* loss_total, int B, int C, int H, int W, int pack, float gscale,
+                   void* stream);
+
+/* -------------------------------------------------------------------------------------------------
+ * Optimizer over the flat fp32 LoRA parameter buffer.
+ * b200_grad_sumsq: *sumsq_f64 = sum g^2.
+ * b200_clip_adamw: total_norm = sqrt(sumsq) * hyper[7]; g *= min(1, max_norm / (total_norm + 1e-6))
+ *   (accelerator.clip_grad_norm_, SDTrainer.py:2278-2283); torch.optim.AdamW update with decoupled weight
+ *   decay (toolkit/optimizer.py:78-79); optional EMA shadow -= (1 - decay_t)(shadow - p) with
+ *   decay_t = min(decay, (1 + n) / (10 + n)) (toolkit/ema.py:100-152).
+ *   hyper fp32[8] (device): lr, beta1, beta2, eps, weight_decay, max_norm, ema_decay, grad_prescale.
+ *   state (device, 64 bytes, zero-initialised): int64 step counter + per-step derived scalars.
+ *   28 bytes per parameter (36 with EMA).
+ * b200_repack_lora: bf16 padded operand copies of the fp32 masters; table = n_entries x
+ *   {int64 src_off, int64 dst_off, int32 rows, cols, dst_ld, pad}.
+ */
+int b200_grad_sumsq(b200_ctx* ctx, const void* g, int64_t n, void* sumsq_f64, void* stream);
+int b200_clip_adamw(b200_ctx* ctx, void* p, void* g, void* m, void* v, void* ema, const void* sumsq_f64,
+                    const void* hyper, void* state, int64_t n, void* norm_out, void* stream);
+int b200_repack_lora(b200_ctx* ctx, const void* flat_f32, void* pack_bf16, const void* table, int n_entries,
+                     void* stream);
 
 #ifdef __cplusplus
 }
