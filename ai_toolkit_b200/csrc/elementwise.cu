@@ -315,12 +315,13 @@ __global__ void silu_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, lo
   }
 }
 
-// out[b, :] = bf16([cos(t*f) | sin(t*f)]), f_i = exp(-ln(max_period) * i / half), t = bf16(bf16(t01) * 1000)
-__global__ void timestep_embed_kernel(const float* __restrict__ t01, bf16* __restrict__ out, int B, int dim, float max_period,
-                                      float mult) {
+// out[b, :] = bf16([cos(t*f) | sin(t*f)]), f_i = exp(-ln(max_period) * i / half), t = bf16(bf16(t_in / div) * mult)
+// (the trainer passes timestep / 1000 in fp32, the bf16 model multiplies by 1000 in bf16)
+__global__ void timestep_embed_kernel(const float* __restrict__ t_in, bf16* __restrict__ out, int B, int dim, float max_period,
+                                      float div, float mult) {
   const int b = blockIdx.x;
   const int half = dim / 2;
-  const float t = bf16_round(bf16_round(t01[b]) * mult);
+  const float t = bf16_round(bf16_round(t_in[b] / div) * mult);
   for (int i = threadIdx.x; i < half; i += blockDim.x) {
     const float f = expf(-logf(max_period) * static_cast<float>(i) / static_cast<float>(half));
     const float ang = t * f;
@@ -466,13 +467,13 @@ extern "C" int b200_silu(b200_ctx* ctx, const void* x, void* y, int64_t n, void*
   return B200_OK;
 }
 
-extern "C" int b200_timestep_embed(b200_ctx* ctx, const void* t01, void* out, int B, int dim, float max_period, float mult,
-                                   void* stream) {
+extern "C" int b200_timestep_embed(b200_ctx* ctx, const void* t01, void* out, int B, int dim, float max_period, float div,
+                                   float mult, void* stream) {
   int rc = check_ctx(ctx);
   if (rc) return rc;
-  B200_REQUIRE(t01 && out && B > 0 && dim > 0 && dim % 2 == 0, "b200_timestep_embed: bad args");
+  B200_REQUIRE(t01 && out && B > 0 && dim > 0 && dim % 2 == 0 && div != 0.f, "b200_timestep_embed: bad args");
   timestep_embed_kernel<<<B, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>((const float*)t01, (bf16*)out, B, dim,
-                                                                               max_period, mult);
+                                                                               max_period, div, mult);
   B200_CUDA_CHECK(cudaGetLastError());
   ctx->launches.fetch_add(1);
   return B200_OK;

@@ -1,0 +1,99 @@
+"""Forward / backward of ONE LoRA-wrapped Linear as launches of the C-ABI kernels.
+
+Shared by the per-module autograd path (`autograd.lora_linear`, the drop-in for
+`ToolkitModuleMixin.forward`, toolkit/network_mixins.py:274-348) and by the fused FLUX engine
+(`flux_engine`).  With c = multiplier * scale (per sample when the multiplier is a list):
+
+  forward    Zc = bf16(c * X A^T)                        rank-side GEMM, N = 64 (rank padded)
+             Y  = epilogue(X W^T + Zc B^T + bias)        ONE tcgen05 tile: base + adapter
+  backward   T  = bf16(c * dY B)                         rank-side GEMM (B consumed MN-major)
+             dX = epilogue(dY W + T A)                   W and A consumed MN-major: no transposed copies
+             dB += dY^T Zc ,  dA += T^T X                token-contraction GEMMs, fp32 atomics into the flat
+                                                         gradient buffer; dW [out, in] is never formed
+"""
+from __future__ import annotations
+
+import torch
+
+from . import cabi, ops
+from .cabi import gemm_bf16
+
+RANK_PAD = 64
+GEMV_MAX_ROWS = 8
+
+
+def wgrad_splits(tokens: int, features: int, sm_count: int = 148) -> int:
+    """Split the token contraction so that (features/128) * splits CTAs fill the GPU."""
+    tiles = max(1, (features + 127) // 128)
+    kb = max(1, (tokens + 63) // 64)
+    s = max(1, min(kb, (sm_count + tiles - 1) // tiles))
+    return s
+
+
+def lora_coeff(lora, n_rows: int):
+    """-> (alpha scalar, row_alpha tensor | None, rows_per_sample) for this call (no device sync for scalars)."""
+    net = lora.network_ref()
+    m = net._multiplier
+    if isinstance(m, (int, float)):
+        return float(m) * lora.scale, None, 0
+    if isinstance(m, list) and len(m) == 1 and isinstance(m[0], (int, float)):
+        return float(m[0]) * lora.scale, None, 0
+    tm = net.torch_multiplier
+    if tm.numel() == 1:
+        return float(tm.item()) * lora.scale, None, 0
+    nb = tm.numel()
+    if n_rows % nb != 0:
+        raise ValueError(f"{lora.lora_name}: {n_rows} rows cannot be split over {nb} per-sample multipliers")
+    return lora.scale, tm.to(torch.float32).contiguous(), n_rows // nb
+
+
+def linear_fwd(lin, x2, out, *, lora=None, zc_out=None, **epi):
+    """out = epilogue(x2 @ W^T [+ adapter] + bias).  Returns Zc (saved for backward) or None."""
+    W = lin.weight if lin.weight.dim() == 2 else lin.weight.view(lin.weight.shape[0], -1)
+    if lora is None:
+        gemm_bf16(x2, W, out, bias=lin.bias, **epi)
+        return None
+    alpha, row_alpha, rps = lora_coeff(lora, x2.shape[0])
+    zc = zc_out if zc_out is not None else torch.empty((x2.shape[0], RANK_PAD), device=x2.device, dtype=torch.bfloat16)
+    gemm_bf16(x2, lora.a_pack, zc, alpha=alpha, row_alpha=row_alpha, rows_per_sample=rps, config=cabi.GEMM_1CTA_N64)
+    gemm_bf16(x2, W, out, a1=zc, b1=lora.b_pack, bias=lin.bias, **epi)
+    return zc
+
+
+def linear_bwd(lin, dy, x2, zc, dx_out, *, lora=None, n_slices=None, **epi):
+    """dX (into dx_out, may be None) and, with an adapter, accumulation of dA / dB into their `.grad` views.
+
+    n_slices: optional list of (col0, col1, epi_kwargs) to produce dX in column ranges with different epilogues
+    (the single-stream block applies gelu' only to the MLP part of the concatenated operand)."""
+    W = lin.weight if lin.weight.dim() == 2 else lin.weight.view(lin.weight.shape[0], -1)
+    t = None
+    if lora is not None:
+        alpha, row_alpha, rps = lora_coeff(lora, dy.shape[0])
+        t = torch.empty((dy.shape[0], RANK_PAD), device=dy.device, dtype=torch.bfloat16)
+        gemm_bf16(dy, lora.b_pack, t, trans_b=True, alpha=alpha, row_alpha=row_alpha, rows_per_sample=rps,
+                  config=cabi.GEMM_1CTA_N64)
+    if dx_out is not None:
+        slices = n_slices if n_slices is not None else [(0, W.shape[1], epi)]
+        for c0, c1, e in slices:
+            a1 = t if lora is not None else None
+            b1 = lora.a_pack[:, c0:c1] if lora is not None else None
+            gemm_bf16(dy, W[:, c0:c1], dx_out[:, c0:c1], a1=a1, b1=b1, trans_b=True, N=c1 - c0, **e)
+    if lora is not None:
+        r = lora.lora_dim
+        tokens = dy.shape[0]
+        g_up = lora.lora_up.weight.grad.view(lora.out_dim, r)
+        g_down = lora.lora_down.weight.grad.view(r, lora.in_dim)
+        gemm_bf16(dy, zc, g_up, trans_a=True, trans_b=True, f32_mode=2, n_store=r,
+                  splits=wgrad_splits(tokens, lora.out_dim), config=cabi.GEMM_1CTA_N64)
+        gemm_bf16(x2, t, g_down, trans_a=True, trans_b=True, f32_mode=2, f32_trans=True, n_store=r,
+                  splits=wgrad_splits(tokens, lora.in_dim), config=cabi.GEMM_1CTA_N64)
+    return t
+
+
+def live_lora(lin):
+    """The active adapter of a Linear, or None (inactive network, merged in, multiplier 0, or not wrapped)."""
+    ref = getattr(lin, "_b200_lora", None)
+    lora = ref() if ref is not None else None
+    if lora is None or not lora.is_live():
+        return None
+    return lora

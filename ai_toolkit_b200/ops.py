@@ -83,10 +83,11 @@ def silu(x, out=None):
     return out
 
 
-def timestep_embed(t01, dim=256, mult=1000.0, max_period=10000.0):
-    B = t01.shape[0]
-    out = torch.empty((B, dim), device=t01.device, dtype=torch.bfloat16)
-    cabi.call("b200_timestep_embed", _p(t01), _p(out), B, dim, float(max_period), float(mult), device=_dev(t01))
+def timestep_embed(t, dim=256, div=1.0, mult=1000.0, max_period=10000.0):
+    """t fp32 [B]; the embedded value is bf16(bf16(t / div) * mult)."""
+    B = t.shape[0]
+    out = torch.empty((B, dim), device=t.device, dtype=torch.bfloat16)
+    cabi.call("b200_timestep_embed", _p(t), _p(out), B, dim, float(max_period), float(div), float(mult), device=_dev(t))
     return out
 
 

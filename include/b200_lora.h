@@ -143,9 +143,9 @@ int b200_qk_norm_rope_bwd(b200_ctx* ctx, const void* dQ, const void* dK, const v
                           void* dv, int ldd, int B, int Lseg, int seq_off, int Ltot, int H, int head_dim, float eps,
                           void* stream);
 int b200_silu(b200_ctx* ctx, const void* x, void* y, int64_t n, void* stream);
-/* out[b,:] = bf16([cos(t f_i) | sin(t f_i)]), t = bf16(bf16(t01[b]) * mult)  (chroma/src/layers.py:30-53) */
-int b200_timestep_embed(b200_ctx* ctx, const void* t01, void* out, int B, int dim, float max_period, float mult,
-                        void* stream);
+/* out[b,:] = bf16([cos(t f_i) | sin(t f_i)]), t = bf16(bf16(t_in[b] / div) * mult)  (chroma/src/layers.py:30-53) */
+int b200_timestep_embed(b200_ctx* ctx, const void* t_in, void* out, int B, int dim, float max_period, float div,
+                        float mult, void* stream);
 int b200_add_bf16(b200_ctx* ctx, const void* a, const void* b, const void* c, void* y, int64_t n, void* stream);
 
 /* -------------------------------------------------------------------------------------------------

@@ -1,0 +1,151 @@
+"""The fused FLUX engine (forward, loss, backward, optimizer) against the oracle (eager restatement of the
+diffusers blocks + the reference's LoRA forward) on identical weights / latents / timesteps / embeddings.
+
+Metric: the oracle in fp32 is the reference value; the bf16 eager oracle's own distance to
+it is the bf16 noise floor.  The B200 path must be within max(1e-3, 1.5 x that floor) relative error on the loss
+and on the fp32 LoRA gradients (they are bf16-rounding limited), and bit-exact on index ops (pack / ids)."""
+import copy
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _rel(a, b):
+    a, b = a.float(), b.float()
+    return ((a - b).norm() / (b.norm() + 1e-30)).item()
+
+
+def _setup(layers, single, heads, B, hl, wl, Lt, rank, seed=0):
+    from oracle import flux_ref, lora_ref
+    from ai_toolkit_b200 import LoRASpecialNetwork
+    from ai_toolkit_b200.flux import FluxConfig, FluxTransformer2DModel
+    torch.manual_seed(seed)
+    cfgd = dict(num_layers=layers, num_single_layers=single, num_attention_heads=heads, joint_attention_dim=64,
+                pooled_projection_dim=32)
+    ocfg = flux_ref.FluxConfig(**cfgd)
+    omodel = flux_ref.init_synthetic_(flux_ref.FluxTransformer2DModel(ocfg), seed=seed, std=0.05)
+    omodel.requires_grad_(False)
+    model = FluxTransformer2DModel(FluxConfig(**cfgd), device=DEV)
+    missing = model.load_state_dict(omodel.state_dict(), strict=True)
+    net = LoRASpecialNetwork(text_encoder=None, unet=model, lora_dim=rank, alpha=rank, train_unet=True,
+                             train_text_encoder=False, is_flux=True, transformer_only=True)
+    net.force_to(DEV, torch.float32)
+    net._update_torch_multiplier()
+    net.apply_to(None, model, False, True)
+    # oracle networks (bf16 eager and fp32 eager) with the same adapter values, lora_up made non-zero
+    g = torch.Generator().manual_seed(seed + 1)
+    onets = {}
+    for name, dt in (("bf16", torch.bfloat16), ("fp32", torch.float32)):
+        om = copy.deepcopy(omodel).to(DEV, dt)
+        on = lora_ref.LoRANetworkRef(om, lora_dim=rank)
+        on.to(DEV, torch.float32)
+        onets[name] = (om, on)
+    with torch.no_grad():
+        for i, lora in enumerate(net.get_all_modules()):
+            up = torch.randn(lora.lora_up.weight.shape, generator=g) * 0.05
+            lora.lora_up.weight.copy_(up)
+            for om, on in onets.values():
+                ol = on.loras[i]
+                assert ol.lora_name == lora.lora_name
+                ol.lora_down.weight.copy_(lora.lora_down.weight)
+                ol.lora_up.weight.copy_(up)
+    net.mark_params_changed()
+    lat = torch.randn(B, 16, hl, wl, generator=g).bfloat16().to(DEV)
+    noise = torch.randn(B, 16, hl, wl, generator=g).bfloat16().to(DEV)
+    t = torch.tensor([317.0, 850.0, 42.0][:B], device=DEV)
+    text = (torch.randn(B, Lt, 64, generator=g) * 0.5).bfloat16().to(DEV)
+    pooled = torch.randn(B, 32, generator=g).bfloat16().to(DEV)
+    return model, net, onets, (lat, noise, t, text, pooled)
+
+
+def _oracle_step(om, on, batch, dtype):
+    from oracle import flux_ref, lora_ref
+    lat, noise, t, text, pooled = batch
+    noisy = lora_ref.add_noise_flowmatch(lat, noise, t).to(torch.bfloat16).to(dtype)
+    on.zero_grad(set_to_none=True)
+    with on:
+        pred = lora_ref.flux_predict(om, noisy, t, text.to(dtype), pooled.to(dtype), 1.0, flux_ref.pack_latents,
+                                     flux_ref.unpack_latents, flux_ref.make_img_ids)
+        loss = lora_ref.flow_loss(pred, lat, noise)
+        loss.backward()
+    grads = torch.cat([p.grad.reshape(-1) for lora in on.loras for p in (lora.lora_down.weight, lora.lora_up.weight)])
+    return loss.item(), pred.detach(), grads
+
+
+@pytest.mark.parametrize("layers,single,heads,B,hl,wl,Lt,rank", [(1, 1, 2, 1, 16, 16, 24, 4), (2, 2, 2, 2, 16, 24, 40, 16)])
+def test_engine_step_matches_oracle(layers, single, heads, B, hl, wl, Lt, rank):
+    from oracle import flux_ref
+    from ai_toolkit_b200 import ops
+    from ai_toolkit_b200.train_step import make_img_ids
+    model, net, onets, batch = _setup(layers, single, heads, B, hl, wl, Lt, rank)
+    lat, noise, t, text, pooled = batch
+    loss32, pred32, g32 = _oracle_step(*onets["fp32"], batch, torch.float32)
+    loss16, pred16, g16 = _oracle_step(*onets["bf16"], batch, torch.bfloat16)
+    # index ops: bit-exact
+    assert torch.equal(make_img_ids(hl, wl, DEV), flux_ref.make_img_ids(hl, wl, DEV))
+    packed = ops.flow_add_noise(lat, noise, t, pack=True)
+    eng = model.engine
+    net.flat_grads.zero_()
+    img_ids, txt_ids = make_img_ids(hl, wl, DEV), torch.zeros(Lt, 3, device=DEV)
+    guidance = torch.ones(B, device=DEV)
+    with net:
+        pred = eng.forward(packed, t, text, pooled, guidance, txt_ids, img_ids, save=True, t_div=1000.0)
+        tot, per, dpred = ops.flow_loss(pred.view(B, -1, 64), lat, noise, pack=True)
+        eng.backward(dpred.view(-1, 64))
+    torch.cuda.synchronize()
+    pred_unp = flux_ref.unpack_latents(pred.view(B, -1, 64), hl, wl)
+    floor_pred, floor_g = _rel(pred16, pred32), _rel(g16, g32)
+    floor_loss = abs(loss16 - loss32) / abs(loss32)
+    e_pred, e_g = _rel(pred_unp, pred32), _rel(net.flat_grads[:g32.numel()], g32)
+    e_loss = abs(tot.item() - loss32) / abs(loss32)
+    print(f"pred rel err {e_pred:.3e} (bf16 eager floor {floor_pred:.3e}); grads {e_g:.3e} (floor {floor_g:.3e}); "
+          f"loss {e_loss:.3e} (floor {floor_loss:.3e})")
+    assert e_pred < max(1e-3, 1.5 * floor_pred)
+    assert e_g < max(1e-3, 1.5 * floor_g)
+    assert e_loss < max(1e-3, 1.5 * floor_loss)
+
+
+def test_lora_module_autograd_dropin():
+    """The per-module seam (LoRAModule.forward inside an eager model) against the oracle's adapter forward."""
+    from oracle import lora_ref
+    from ai_toolkit_b200 import LoRASpecialNetwork
+    torch.manual_seed(0)
+
+    class Toy(torch.nn.Module):  # class name the reference targets for generic transformers
+        def __init__(self):
+            super().__init__()
+            self.transformer_blocks = torch.nn.ModuleList([torch.nn.Linear(256, 512), torch.nn.Linear(512, 256)])
+
+        def forward(self, x):
+            return self.transformer_blocks[1](torch.nn.functional.gelu(self.transformer_blocks[0](x), approximate="tanh"))
+
+    Toy.__name__ = "FluxTransformer2DModel"
+    m = Toy().to(DEV, torch.bfloat16).requires_grad_(False)
+    m2 = copy.deepcopy(m)
+    net = LoRASpecialNetwork(None, m, lora_dim=8, alpha=8, train_text_encoder=False, is_flux=True, transformer_only=True)
+    net.force_to(DEV, torch.float32)
+    net._update_torch_multiplier()
+    net.apply_to(None, m, False, True)
+    ref = lora_ref.LoRANetworkRef(m2, lora_dim=8).to(DEV)
+    with torch.no_grad():
+        for a, b in zip(net.get_all_modules(), ref.loras):
+            a.lora_up.weight.normal_(0, 0.05)
+            b.lora_down.weight.copy_(a.lora_down.weight)
+            b.lora_up.weight.copy_(a.lora_up.weight)
+    net.mark_params_changed()
+    x = torch.randn(3, 200, 256, device=DEV).bfloat16()
+    with net:
+        y = m(x)
+        (y.float() ** 2).mean().backward()
+    with ref:
+        y2 = m2(x)
+        (y2.float() ** 2).mean().backward()
+    assert _rel(y, y2) < 1e-2
+    for a, b in zip(net.get_all_modules(), ref.loras):
+        assert _rel(a.lora_down.weight.grad, b.lora_down.weight.grad) < 2e-2
+        assert _rel(a.lora_up.weight.grad, b.lora_up.weight.grad) < 2e-2
+    # inactive network = frozen model, untouched
+    assert torch.equal(m(x), m2(x))
