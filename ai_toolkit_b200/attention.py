@@ -75,11 +75,12 @@ def bwd(Q, K, V, o0, o1, do0, do1, lse, split):
     dK = torch.empty_like(K)
     dV = torch.empty_like(V)
     delta = torch.empty((B, H, L), device=Q.device, dtype=torch.float32)
+    dOh = torch.empty_like(Q)
     ld0 = int(o0.stride(0)) if o0 is not None else 0
     ld1 = int(o1.stride(0))
     ldd0 = int(do0.stride(0)) if do0 is not None else 0
     ldd1 = int(do1.stride(0))
     cabi.call("b200_attn_bwd", _p(Q), _p(K), _p(V), _p(o0), ld0, _p(o1), ld1, _p(do0), ldd0, _p(do1), ldd1, _p(lse),
-              _p(delta), _p(dQ), _p(dK), _p(dV), int(B), int(H), int(L), int(split), float(1.0 / math.sqrt(Dh)),
+              _p(delta), _p(dOh), _p(dQ), _p(dK), _p(dV), int(B), int(H), int(L), int(split), float(1.0 / math.sqrt(Dh)),
               device=Q.device.index)
     return dQ, dK, dV

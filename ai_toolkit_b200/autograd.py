@@ -12,7 +12,7 @@ from .linear import GEMV_MAX_ROWS, RANK_PAD, linear_bwd, linear_fwd, lora_coeff
 
 class _LoraLinearFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x2, lora):
+    def forward(ctx, x2, a_weight, b_weight, lora):  # a/b only tell autograd that the output depends on them
         lin = lora.org_module[0]
         out = torch.empty((x2.shape[0], lora.out_dim), device=x2.device, dtype=torch.bfloat16)
         zc = linear_fwd(lin, x2, out, lora=lora)
@@ -28,14 +28,14 @@ class _LoraLinearFn(torch.autograd.Function):
         dy = dy.contiguous()
         dx = torch.empty_like(x2) if ctx.needs_input_grad[0] else None
         linear_bwd(lin, dy, x2, zc, dx, lora=lora)
-        return dx, None
+        return dx, None, None, None
 
 
 class _LoraGemvFn(torch.autograd.Function):
     """M <= 8 rows (conditioning vectors): fp32 master weights, weight-streaming kernels."""
 
     @staticmethod
-    def forward(ctx, x2, lora):
+    def forward(ctx, x2, a_weight, b_weight, lora):
         lin = lora.org_module[0]
         alpha, row_alpha, _ = lora_coeff(lora, x2.shape[0])
         if row_alpha is not None:
@@ -62,7 +62,7 @@ class _LoraGemvFn(torch.autograd.Function):
             t = torch.empty((dyb.shape[0], RANK_PAD), device=dy.device, dtype=torch.bfloat16)
             cabi.gemm_bf16(dyb, lora.b_pack, t, trans_b=True, alpha=ctx.alpha, config=cabi.GEMM_1CTA_N64)
             cabi.gemm_bf16(dyb, lin.weight, dx, a1=t, b1=lora.a_pack, trans_b=True)
-        return dx, None
+        return dx, None, None, None
 
 
 def lora_linear(lora, x):
@@ -82,5 +82,5 @@ def lora_linear(lora, x):
     if not x2.is_contiguous():
         x2 = x2.contiguous()
     fn = _LoraGemvFn if x2.shape[0] <= GEMV_MAX_ROWS else _LoraLinearFn
-    y = fn.apply(x2, lora)
+    y = fn.apply(x2, lora.lora_down.weight, lora.lora_up.weight, lora)
     return y.view(*shape[:-1], lora.out_dim)

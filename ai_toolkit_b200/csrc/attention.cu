@@ -1,0 +1,664 @@
+// Flash attention for the DiT blocks on tcgen05 / TMEM / TMA (head_dim 128, non-causal, joint text||image
+// sequence), forward and backward.  Operands are head-major [B, H, L, 128] bf16 (written by
+// b200_qk_norm_rope_fwd); the forward writes O token-major straight into the operand buffers of the
+// following projection GEMMs.
+//
+// Forward (one CTA per 128-row Q tile of one (b, h); 192 threads = TMA warp, MMA warp, 4 softmax warps):
+//   S = Q K_j^T        tcgen05.mma, both operands K-major from SWIZZLE_128B tiles, accumulator in TMEM (2 buffers)
+//   P = exp2(S c - m)  one thread per row reads its row with tcgen05.ld (no shuffles), lazy rescaling of O
+//                      (only when the running max grows by more than 2^8), P written bf16 to swizzled smem
+//   O += P V_j         tcgen05.mma, V consumed MN-major exactly as it lies in HBM ([kv, d], d contiguous)
+// Backward = three kernels: delta/dO re-layout, dK/dV (kv-stationary) and dQ (q-stationary); the two
+// tensor-core kernels are one template: the stationary 128-row operands stay in smem, 64-row tiles of the
+// other side stream through a 3-stage TMA ring, S and dP go to double-buffered TMEM, P / dS are written
+// bf16 to smem once and consumed both K-major and MN-major (same bytes, two descriptors).
+//
+// Reference semantics: torch SDPA as called by diffusers' FLUX attention processor (in-tree equivalent
+// extensions_built_in/diffusion_models/chroma/src/math.py:13-30); backward = its autograd.
+#include "common.cuh"
+#include "ctx.h"
+
+namespace b200 {
+
+__device__ __forceinline__ float ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+      "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]),
+      "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]),
+      "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+      : "memory");
+}
+// 16-byte store of 8 bf16 into a [rows x 128 B] SWIZZLE_128B tile (row r, 16-byte chunk c of 8)
+__device__ __forceinline__ void st_sw128(uint8_t* tile, int r, int c, uint4 v) {
+  *reinterpret_cast<uint4*>(tile + r * 128 + ((c ^ (r & 7)) << 4)) = v;
+}
+
+constexpr float kLog2e = 1.4426950408889634f;
+constexpr float kLn2 = 0.6931471805599453f;
+
+// =================================================================================================
+// forward
+// =================================================================================================
+struct AttnFwdArgs {
+  bf16* o0;
+  int ld0;
+  bf16* o1;
+  int ld1;
+  float* lse;
+  int B, H, L, split;
+  float scale;
+};
+
+constexpr int kFwdSmem = 1024 + 32768 + 2 * 32768 + 2 * 32768 + 32768 + 16 * 8 + 16;
+
+__global__ void __launch_bounds__(192, 1)
+attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                const __grid_constant__ CUtensorMap tmV, const AttnFwdArgs g) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;
+  uint8_t* sK = sQ + 32768;
+  uint8_t* sV = sK + 2 * 32768;
+  uint8_t* sP = sV + 2 * 32768;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 32768);
+  uint64_t* q_full = bars;
+  uint64_t* k_full = bars + 1;
+  uint64_t* k_empty = bars + 3;
+  uint64_t* v_full = bars + 5;
+  uint64_t* v_empty = bars + 7;
+  uint64_t* s_full = bars + 9;
+  uint64_t* s_empty = bars + 11;
+  uint64_t* p_full = bars + 13;
+  uint64_t* pv_done = bars + 14;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 15);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int bh = blockIdx.y;
+  const int q0 = blockIdx.x * 128;
+  const int n_kv = (g.L + 127) / 128;
+  const long long row_base = static_cast<long long>(bh) * g.L;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmV);
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      mbar_init(q_full, 1);
+      for (int s = 0; s < 2; ++s) {
+        mbar_init(&k_full[s], 1);
+        mbar_init(&k_empty[s], 1);
+        mbar_init(&v_full[s], 1);
+        mbar_init(&v_empty[s], 1);
+        mbar_init(&s_full[s], 1);
+        mbar_init(&s_empty[s], 128);
+      }
+      mbar_init(p_full, 128);
+      mbar_init(pv_done, 1);
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc<512>(tmem_slot);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
+  const uint32_t tS[2] = {tmem_base, tmem_base + 128u};
+  const uint32_t tO = tmem_base + 256u;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      const int qrow = static_cast<int>(row_base + q0);
+      mbar_arrive_expect_tx(q_full, 32768);
+      tma_load_2d(sQ, &tmQ, q_full, 0, qrow);
+      tma_load_2d(sQ + 16384, &tmQ, q_full, 64, qrow);
+      for (int j = 0; j < n_kv; ++j) {
+        const int s = j & 1;
+        const uint32_t ph = (j >> 1) & 1;
+        const int kvrow = static_cast<int>(row_base + j * 128);
+        mbar_wait(&k_empty[s], ph ^ 1u, 10);
+        mbar_arrive_expect_tx(&k_full[s], 32768);
+        tma_load_2d(sK + s * 32768, &tmK, &k_full[s], 0, kvrow);
+        tma_load_2d(sK + s * 32768 + 16384, &tmK, &k_full[s], 64, kvrow);
+        mbar_wait(&v_empty[s], ph ^ 1u, 11);
+        mbar_arrive_expect_tx(&v_full[s], 32768);
+#pragma unroll
+        for (int jc = 0; jc < 2; ++jc)
+#pragma unroll
+          for (int ih = 0; ih < 2; ++ih)
+            tma_load_2d(sV + s * 32768 + (jc * 2 + ih) * 8192, &tmV, &v_full[s], jc * 64, kvrow + ih * 64);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idS = umma_idesc_bf16(128, 128, 0, 0);
+      constexpr uint32_t idPV = umma_idesc_bf16(128, 128, 0, 1);
+      mbar_wait(q_full, 0, 12);
+      auto issue_S = [&](int j) {
+        const int s = j & 1;
+        const uint32_t ph = (j >> 1) & 1;
+        mbar_wait(&k_full[s], ph, 13);
+        mbar_wait(&s_empty[s], ph ^ 1u, 14);
+        tc_fence_after();
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk) {
+          const uint64_t da = umma_desc_sw128(smem_u32(sQ + (kk >> 2) * 16384), 1024, 16) + 2u * (kk & 3);
+          const uint64_t db = umma_desc_sw128(smem_u32(sK + s * 32768 + (kk >> 2) * 16384), 1024, 16) + 2u * (kk & 3);
+          umma_bf16_ss(tS[s], da, db, idS, kk > 0 ? 1u : 0u);
+        }
+        umma_commit(&k_empty[s]);
+        umma_commit(&s_full[s]);
+      };
+      auto issue_PV = [&](int j) {
+        const int s = j & 1;
+        const uint32_t ph = (j >> 1) & 1;
+        mbar_wait(&v_full[s], ph, 15);
+        mbar_wait(p_full, j & 1, 16);
+        tc_fence_after();
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk) {
+          const uint64_t da = umma_desc_sw128(smem_u32(sP + (kk >> 2) * 16384), 1024, 16) + 2u * (kk & 3);
+          const uint64_t db =
+              umma_desc_sw128(smem_u32(sV + s * 32768 + (kk >> 2) * 8192 + (kk & 3) * 2048), 1024, 16384);
+          umma_bf16_ss(tO, da, db, idPV, (j > 0 || kk > 0) ? 1u : 0u);
+        }
+        umma_commit(&v_empty[s]);
+        umma_commit(pv_done);
+      };
+      issue_S(0);
+      for (int j = 0; j < n_kv; ++j) {
+        if (j + 1 < n_kv) issue_S(j + 1);
+        issue_PV(j);
+      }
+    }
+  } else {
+    // ---------------------------------------------------------------- softmax / epilogue: one thread per row
+    const int q = warp & 3;
+    const int r = q * 32 + lane;
+    const int qi = q0 + r;
+    const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
+    const float c2 = g.scale * kLog2e;
+    float m_used = -INFINITY, l_sum = 0.f;
+    for (int j = 0; j < n_kv; ++j) {
+      const int s = j & 1;
+      const uint32_t ph = (j >> 1) & 1;
+      mbar_wait(&s_full[s], ph, 17);
+      tc_fence_after();
+      const int kv0 = j * 128;
+      // pass 1: row max
+      float mx = -INFINITY;
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t v[32];
+        tmem_ld_32x32(tS[s] + lane_off + c * 32, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const float x = (kv0 + c * 32 + i < g.L) ? __uint_as_float(v[i]) * c2 : -INFINITY;
+          mx = fmaxf(mx, x);
+        }
+      }
+      const float m_new = fmaxf(m_used, mx);
+      const bool need = (m_new > m_used + 8.0f);  // also true for the first tile (m_used = -inf)
+      const bool any_need = __any_sync(0xffffffffu, need);
+      if (j > 0) {
+        mbar_wait(pv_done, (j - 1) & 1, 18);  // P buffer free, O stable
+        tc_fence_after();
+      }
+      if (any_need) {
+        const float f = need ? ex2(m_used - m_new) : 1.0f;  // first tile: ex2(-inf) = 0
+        if (need) {
+          m_used = m_new;
+          l_sum *= f;
+        }
+        if (j > 0) {
+#pragma unroll 1
+          for (int c = 0; c < 4; ++c) {
+            uint32_t v[32];
+            tmem_ld_32x32(tO + lane_off + c * 32, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * f);
+            tmem_st_32x32(tO + lane_off + c * 32, v);
+          }
+          tmem_st_wait();
+        }
+      }
+      // pass 2: P = exp2(S c - m_used), row sum, bf16 -> swizzled smem (two [128 x 64] K-major blocks)
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t v[32];
+        tmem_ld_32x32(tS[s] + lane_off + c * 32, v);
+        tmem_ld_wait();
+        float p[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const float x = (kv0 + c * 32 + i < g.L) ? ex2(__uint_as_float(v[i]) * c2 - m_used) : 0.f;
+          p[i] = x;
+          l_sum += x;
+        }
+        uint8_t* blk = sP + (c >> 1) * 16384;
+#pragma unroll
+        for (int k8 = 0; k8 < 4; ++k8) {
+          uint4 u;
+          u.x = pack_bf16x2(p[k8 * 8 + 0], p[k8 * 8 + 1]);
+          u.y = pack_bf16x2(p[k8 * 8 + 2], p[k8 * 8 + 3]);
+          u.z = pack_bf16x2(p[k8 * 8 + 4], p[k8 * 8 + 5]);
+          u.w = pack_bf16x2(p[k8 * 8 + 6], p[k8 * 8 + 7]);
+          st_sw128(blk, r, (c & 1) * 4 + k8, u);
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&s_empty[s]);
+      fence_proxy_async_smem();
+      mbar_arrive(p_full);
+    }
+    mbar_wait(pv_done, (n_kv - 1) & 1, 19);
+    tc_fence_after();
+    const float inv = 1.0f / l_sum;
+    const bool live = qi < g.L;
+    bf16* orow = nullptr;
+    if (live) {
+      const int b = bh / g.H, h = bh % g.H;
+      if (qi < g.split)
+        orow = g.o0 + (static_cast<size_t>(b) * g.split + qi) * g.ld0 + h * 128;
+      else
+        orow = g.o1 + (static_cast<size_t>(b) * (g.L - g.split) + (qi - g.split)) * g.ld1 + h * 128;
+      g.lse[row_base + qi] = (m_used + log2f(l_sum)) * kLn2;
+    }
+#pragma unroll 1
+    for (int c = 0; c < 4; ++c) {  // tcgen05.ld is warp-collective: every lane loads, only live rows store
+      uint32_t v[32];
+      tmem_ld_32x32(tO + lane_off + c * 32, v);
+      tmem_ld_wait();
+      if (live) {
+#pragma unroll
+        for (int k8 = 0; k8 < 4; ++k8) {
+          uint4 u;
+          u.x = pack_bf16x2(__uint_as_float(v[k8 * 8 + 0]) * inv, __uint_as_float(v[k8 * 8 + 1]) * inv);
+          u.y = pack_bf16x2(__uint_as_float(v[k8 * 8 + 2]) * inv, __uint_as_float(v[k8 * 8 + 3]) * inv);
+          u.z = pack_bf16x2(__uint_as_float(v[k8 * 8 + 4]) * inv, __uint_as_float(v[k8 * 8 + 5]) * inv);
+          u.w = pack_bf16x2(__uint_as_float(v[k8 * 8 + 6]) * inv, __uint_as_float(v[k8 * 8 + 7]) * inv);
+          *reinterpret_cast<uint4*>(orow + c * 32 + k8 * 8) = u;
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (warp == 1) tmem_dealloc<512>(tmem_base);
+}
+
+// =================================================================================================
+// backward
+// =================================================================================================
+// delta[b,h,l] = sum_d dO * O ;  dOh = dO re-laid head-major.  One warp per (b, l, h).
+__global__ void __launch_bounds__(256) attn_delta_kernel(const bf16* __restrict__ o0, int ld0, const bf16* __restrict__ o1, int ld1,
+                                                         const bf16* __restrict__ do0, int ldd0,
+                                                         const bf16* __restrict__ do1, int ldd1, float* __restrict__ delta,
+                                                         bf16* __restrict__ dOh, int B, int H, int L, int split) {
+  const long long w = static_cast<long long>(blockIdx.x) * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (w >= static_cast<long long>(B) * L * H) return;
+  const int h = static_cast<int>(w % H);
+  const long long tok = w / H;
+  const int l = static_cast<int>(tok % L);
+  const int b = static_cast<int>(tok / L);
+  const bf16 *po, *pd;
+  if (l < split) {
+    po = o0 + (static_cast<size_t>(b) * split + l) * ld0 + h * 128 + lane * 4;
+    pd = do0 + (static_cast<size_t>(b) * split + l) * ldd0 + h * 128 + lane * 4;
+  } else {
+    po = o1 + (static_cast<size_t>(b) * (L - split) + (l - split)) * ld1 + h * 128 + lane * 4;
+    pd = do1 + (static_cast<size_t>(b) * (L - split) + (l - split)) * ldd1 + h * 128 + lane * 4;
+  }
+  const uint2 uo = *reinterpret_cast<const uint2*>(po);
+  const uint2 ud = *reinterpret_cast<const uint2*>(pd);
+  const float2 a0 = unpack_bf16x2(uo.x), a1 = unpack_bf16x2(uo.y), d0 = unpack_bf16x2(ud.x), d1 = unpack_bf16x2(ud.y);
+  float s = a0.x * d0.x + a0.y * d0.y + a1.x * d1.x + a1.y * d1.y;
+  s = warp_sum(s);
+  const size_t hm = ((static_cast<size_t>(b) * H + h) * L + l);
+  if (lane == 0) delta[hm] = s;
+  *reinterpret_cast<uint2*>(dOh + hm * 128 + lane * 4) = ud;
+}
+
+struct AttnBwdArgs {
+  const float* lse;
+  const float* delta;
+  bf16* out0;  // MODE_KV: dV ; MODE_Q: dQ
+  bf16* out1;  // MODE_KV: dK
+  int L;
+  float scale;
+};
+
+constexpr int kBwdStages = 3;
+constexpr int kBwdSmem = 1024 + 2 * 32768 + kBwdStages * 32768 + 2 * 16384 + 16 * 8 + 16;
+
+// MODE_KV = 1: stationary (R0, R1) = (K_j, V_j), streamed (T0, T1) = (Q_i, dO_i); outputs dV (acc0), dK (acc1)
+// MODE_KV = 0: stationary (R0, R1) = (Q_i, dO_i), streamed (T0, T1) = (K_j, V_j); output  dQ (acc0)
+template <int MODE_KV>
+__global__ void __launch_bounds__(192, 1)
+attn_bwd_kernel(const __grid_constant__ CUtensorMap tmR0, const __grid_constant__ CUtensorMap tmR1,
+                const __grid_constant__ CUtensorMap tmT0, const __grid_constant__ CUtensorMap tmT1, const AttnBwdArgs g) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sR0 = smem;
+  uint8_t* sR1 = sR0 + 32768;
+  uint8_t* sT = sR1 + 32768;  // stage st: T0 at sT + st*32768, T1 at +16384
+  uint8_t* sPB0 = sT + kBwdStages * 32768;
+  uint8_t* sPB1 = sPB0 + 16384;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sPB1 + 16384);
+  uint64_t* r_full = bars;
+  uint64_t* t_full = bars + 1;
+  uint64_t* t_empty = bars + 4;
+  uint64_t* x_full = bars + 7;
+  uint64_t* x_empty = bars + 9;
+  uint64_t* pb_full = bars + 11;
+  uint64_t* pb_empty = bars + 12;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int bh = blockIdx.y;
+  const int r0 = blockIdx.x * 128;
+  const int n_t = (g.L + 63) / 64;
+  const long long row_base = static_cast<long long>(bh) * g.L;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmR0);
+    tma_prefetch_desc(&tmR1);
+    tma_prefetch_desc(&tmT0);
+    tma_prefetch_desc(&tmT1);
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      mbar_init(r_full, 1);
+      for (int s = 0; s < kBwdStages; ++s) {
+        mbar_init(&t_full[s], 1);
+        mbar_init(&t_empty[s], 1);
+      }
+      for (int s = 0; s < 2; ++s) {
+        mbar_init(&x_full[s], 1);
+        mbar_init(&x_empty[s], 128);
+      }
+      mbar_init(pb_full, 128);
+      mbar_init(pb_empty, 1);
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc<512>(tmem_slot);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
+  const uint32_t tX0[2] = {tmem_base, tmem_base + 64u};
+  const uint32_t tX1[2] = {tmem_base + 128u, tmem_base + 192u};
+  const uint32_t tA0 = tmem_base + 256u, tA1 = tmem_base + 384u;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      const int rrow = static_cast<int>(row_base + r0);
+      mbar_arrive_expect_tx(r_full, 65536);
+      tma_load_2d(sR0, &tmR0, r_full, 0, rrow);
+      tma_load_2d(sR0 + 16384, &tmR0, r_full, 64, rrow);
+      tma_load_2d(sR1, &tmR1, r_full, 0, rrow);
+      tma_load_2d(sR1 + 16384, &tmR1, r_full, 64, rrow);
+      for (int i = 0; i < n_t; ++i) {
+        const int st = i % kBwdStages;
+        const uint32_t ph = (i / kBwdStages) & 1;
+        const int trow = static_cast<int>(row_base + i * 64);
+        mbar_wait(&t_empty[st], ph ^ 1u, 20);
+        mbar_arrive_expect_tx(&t_full[st], 32768);
+        uint8_t* d = sT + st * 32768;
+        tma_load_2d(d, &tmT0, &t_full[st], 0, trow);
+        tma_load_2d(d + 8192, &tmT0, &t_full[st], 64, trow);
+        tma_load_2d(d + 16384, &tmT1, &t_full[st], 0, trow);
+        tma_load_2d(d + 16384 + 8192, &tmT1, &t_full[st], 64, trow);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idA = umma_idesc_bf16(128, 64, 0, 0);
+      constexpr uint32_t idB = umma_idesc_bf16(128, 128, 0, 1);
+      mbar_wait(r_full, 0, 21);
+      auto issue_A = [&](int i) {
+        const int st = i % kBwdStages;
+        const uint32_t ph = (i / kBwdStages) & 1;
+        const int xb = i & 1;
+        const uint32_t xph = (i >> 1) & 1;
+        mbar_wait(&t_full[st], ph, 22);
+        mbar_wait(&x_empty[xb], xph ^ 1u, 23);
+        tc_fence_after();
+        const uint8_t* t0 = sT + st * 32768;
+        const uint8_t* t1 = t0 + 16384;
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk) {
+          const uint64_t da = umma_desc_sw128(smem_u32(sR0 + (kk >> 2) * 16384), 1024, 16) + 2u * (kk & 3);
+          const uint64_t db = umma_desc_sw128(smem_u32(t0 + (kk >> 2) * 8192), 1024, 16) + 2u * (kk & 3);
+          umma_bf16_ss(tX0[xb], da, db, idA, kk > 0 ? 1u : 0u);
+        }
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk) {
+          const uint64_t da = umma_desc_sw128(smem_u32(sR1 + (kk >> 2) * 16384), 1024, 16) + 2u * (kk & 3);
+          const uint64_t db = umma_desc_sw128(smem_u32(t1 + (kk >> 2) * 8192), 1024, 16) + 2u * (kk & 3);
+          umma_bf16_ss(tX1[xb], da, db, idA, kk > 0 ? 1u : 0u);
+        }
+        umma_commit(&x_full[xb]);
+      };
+      auto issue_B = [&](int i) {
+        const int st = i % kBwdStages;
+        mbar_wait(pb_full, i & 1, 24);
+        tc_fence_after();
+        const uint8_t* t0 = sT + st * 32768;
+        const uint8_t* t1 = t0 + 16384;
+        const uint32_t acc = i > 0 ? 1u : 0u;
+        if (MODE_KV) {
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) {  // dV += P^T dO_i
+            const uint64_t da = umma_desc_sw128(smem_u32(sPB0), 1024, 16) + 2u * kk;
+            const uint64_t db = umma_desc_sw128(smem_u32(t1 + kk * 2048), 1024, 8192);
+            umma_bf16_ss(tA0, da, db, idB, (kk > 0) ? 1u : acc);
+          }
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) {  // dK += dS^T Q_i
+            const uint64_t da = umma_desc_sw128(smem_u32(sPB1), 1024, 16) + 2u * kk;
+            const uint64_t db = umma_desc_sw128(smem_u32(t0 + kk * 2048), 1024, 8192);
+            umma_bf16_ss(tA1, da, db, idB, (kk > 0) ? 1u : acc);
+          }
+        } else {
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) {  // dQ += dS K_j
+            const uint64_t da = umma_desc_sw128(smem_u32(sPB1), 1024, 16) + 2u * kk;
+            const uint64_t db = umma_desc_sw128(smem_u32(t0 + kk * 2048), 1024, 8192);
+            umma_bf16_ss(tA0, da, db, idB, (kk > 0) ? 1u : acc);
+          }
+        }
+        umma_commit(&t_empty[st]);
+        umma_commit(pb_empty);
+      };
+      issue_A(0);
+      for (int i = 0; i < n_t; ++i) {
+        if (i + 1 < n_t) issue_A(i + 1);
+        issue_B(i);
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    const int r = q * 32 + lane;
+    const int ri = r0 + r;  // kv index (MODE_KV) or q index
+    const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
+    const float c2 = g.scale * kLog2e;
+    const float* lse_bh = g.lse + row_base;
+    const float* delta_bh = g.delta + row_base;
+    float my_lse2 = 0.f, my_delta = 0.f;
+    if (!MODE_KV && ri < g.L) {
+      my_lse2 = lse_bh[ri] * kLog2e;
+      my_delta = delta_bh[ri];
+    }
+    for (int i = 0; i < n_t; ++i) {
+      const int xb = i & 1;
+      const uint32_t xph = (i >> 1) & 1;
+      mbar_wait(&x_full[xb], xph, 25);
+      tc_fence_after();
+      const int c0 = i * 64;
+      uint32_t pp[32], dd[32];  // packed bf16 pairs: P and dS rows (64 values each)
+#pragma unroll
+      for (int hlf = 0; hlf < 2; ++hlf) {
+        uint32_t sv[32], dv[32];
+        tmem_ld_32x32(tX0[xb] + lane_off + hlf * 32, sv);
+        tmem_ld_32x32(tX1[xb] + lane_off + hlf * 32, dv);
+        tmem_ld_wait();
+#pragma unroll
+        for (int k = 0; k < 32; k += 2) {
+          float p2[2], d2[2];
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const int cc = c0 + hlf * 32 + k + e;  // q index (MODE_KV) or kv index
+            const bool valid = (cc < g.L) && (ri < g.L);
+            float lse2, dl;
+            if (MODE_KV) {
+              const int cq = cc < g.L ? cc : 0;
+              lse2 = __ldg(lse_bh + cq) * kLog2e;
+              dl = __ldg(delta_bh + cq);
+            } else {
+              lse2 = my_lse2;
+              dl = my_delta;
+            }
+            const float p = valid ? ex2(__uint_as_float(sv[k + e]) * c2 - lse2) : 0.f;
+            p2[e] = p;
+            d2[e] = p * (__uint_as_float(dv[k + e]) - dl) * g.scale;
+          }
+          pp[hlf * 16 + k / 2] = pack_bf16x2(p2[0], p2[1]);
+          dd[hlf * 16 + k / 2] = pack_bf16x2(d2[0], d2[1]);
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&x_empty[xb]);
+      if (i > 0) mbar_wait(pb_empty, (i - 1) & 1, 26);
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        if (MODE_KV) st_sw128(sPB0, r, c, make_uint4(pp[c * 4], pp[c * 4 + 1], pp[c * 4 + 2], pp[c * 4 + 3]));
+        st_sw128(sPB1, r, c, make_uint4(dd[c * 4], dd[c * 4 + 1], dd[c * 4 + 2], dd[c * 4 + 3]));
+      }
+      fence_proxy_async_smem();
+      mbar_arrive(pb_full);
+    }
+    mbar_wait(pb_empty, (n_t - 1) & 1, 27);
+    tc_fence_after();
+#pragma unroll 1
+    for (int which = 0; which < (MODE_KV ? 2 : 1); ++which) {
+      const uint32_t ta = which == 0 ? tA0 : tA1;
+      bf16* out = which == 0 ? g.out0 : g.out1;
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t v[32];
+        tmem_ld_32x32(ta + lane_off + c * 32, v);
+        tmem_ld_wait();
+        if (ri < g.L) {
+          bf16* orow = out + (row_base + ri) * 128 + c * 32;
+#pragma unroll
+          for (int k8 = 0; k8 < 4; ++k8) {
+            uint4 u;
+            u.x = pack_bf16x2(__uint_as_float(v[k8 * 8 + 0]), __uint_as_float(v[k8 * 8 + 1]));
+            u.y = pack_bf16x2(__uint_as_float(v[k8 * 8 + 2]), __uint_as_float(v[k8 * 8 + 3]));
+            u.z = pack_bf16x2(__uint_as_float(v[k8 * 8 + 4]), __uint_as_float(v[k8 * 8 + 5]));
+            u.w = pack_bf16x2(__uint_as_float(v[k8 * 8 + 6]), __uint_as_float(v[k8 * 8 + 7]));
+            *reinterpret_cast<uint4*>(orow + k8 * 8) = u;
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (warp == 1) tmem_dealloc<512>(tmem_base);
+}
+
+}  // namespace b200
+
+using namespace b200;
+
+static int attn_maps(b200_ctx* ctx, const void* p, uint64_t rows, uint32_t box_rows, CUtensorMap* out) {
+  return make_tmap_bf16_2d(ctx, out, p, rows, 128, 128, 64, box_rows);
+}
+
+extern "C" int b200_attn_fwd(b200_ctx* ctx, const void* Q, const void* K, const void* V, void* o0, int ld0, void* o1, int ld1,
+                             void* lse, int B, int H, int L, int split, float scale, void* stream) {
+  int rc = check_ctx(ctx);
+  if (rc) return rc;
+  B200_REQUIRE(Q && K && V && o1 && lse && B > 0 && H > 0 && L > 0, "b200_attn_fwd: bad args");
+  B200_REQUIRE(split >= 0 && split <= L && (split == 0 || o0 != nullptr), "b200_attn_fwd: bad split %d", split);
+  B200_REQUIRE(ld1 % 8 == 0 && (split == 0 || ld0 % 8 == 0), "b200_attn_fwd: output leading dims must be multiples of 8");
+  const uint64_t rows = static_cast<uint64_t>(B) * H * L;
+  B200_REQUIRE(rows < (1ull << 31), "b200_attn_fwd: too many rows");
+  CUtensorMap tq, tk, tv;
+  if ((rc = attn_maps(ctx, Q, rows, 128, &tq))) return rc;
+  if ((rc = attn_maps(ctx, K, rows, 128, &tk))) return rc;
+  if ((rc = attn_maps(ctx, V, rows, 64, &tv))) return rc;
+  static bool configured = false;
+  if (!configured) {
+    B200_CUDA_CHECK(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwdSmem));
+    configured = true;
+  }
+  AttnFwdArgs a{(bf16*)o0, ld0, (bf16*)o1, ld1, (float*)lse, B, H, L, split, scale};
+  dim3 grid((L + 127) / 128, B * H);
+  attn_fwd_kernel<<<grid, 192, kFwdSmem, reinterpret_cast<cudaStream_t>(stream)>>>(tq, tk, tv, a);
+  B200_CUDA_CHECK(cudaGetLastError());
+  ctx->launches.fetch_add(1);
+  return B200_OK;
+}
+
+extern "C" int b200_attn_bwd(b200_ctx* ctx, const void* Q, const void* K, const void* V, const void* o0, int ld0,
+                             const void* o1, int ld1, const void* do0, int ldd0, const void* do1, int ldd1, const void* lse,
+                             void* delta, void* dOh, void* dQ, void* dK, void* dV, int B, int H, int L, int split,
+                             float scale, void* stream) {
+  int rc = check_ctx(ctx);
+  if (rc) return rc;
+  B200_REQUIRE(Q && K && V && o1 && do1 && lse && delta && dOh && dQ && dK && dV, "b200_attn_bwd: null argument");
+  B200_REQUIRE(B > 0 && H > 0 && L > 0 && split >= 0 && split <= L && (split == 0 || (o0 && do0)), "b200_attn_bwd: bad shape");
+  B200_REQUIRE(ld1 % 4 == 0 && ldd1 % 4 == 0 && ld0 % 4 == 0 && ldd0 % 4 == 0, "b200_attn_bwd: leading dims %% 4");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const uint64_t rows = static_cast<uint64_t>(B) * H * L;
+  B200_REQUIRE(rows < (1ull << 31), "b200_attn_bwd: too many rows");
+  const long long warps = static_cast<long long>(B) * L * H;
+  attn_delta_kernel<<<static_cast<unsigned>((warps + 7) / 8), 256, 0, st>>>((const bf16*)o0, ld0, (const bf16*)o1, ld1,
+                                                                            (const bf16*)do0, ldd0, (const bf16*)do1, ldd1,
+                                                                            (float*)delta, (bf16*)dOh, B, H, L, split);
+  B200_CUDA_CHECK(cudaGetLastError());
+  CUtensorMap q128, k128, v128, d128, q64, k64, v64, d64;
+  if ((rc = attn_maps(ctx, Q, rows, 128, &q128))) return rc;
+  if ((rc = attn_maps(ctx, K, rows, 128, &k128))) return rc;
+  if ((rc = attn_maps(ctx, V, rows, 128, &v128))) return rc;
+  if ((rc = attn_maps(ctx, dOh, rows, 128, &d128))) return rc;
+  if ((rc = attn_maps(ctx, Q, rows, 64, &q64))) return rc;
+  if ((rc = attn_maps(ctx, K, rows, 64, &k64))) return rc;
+  if ((rc = attn_maps(ctx, V, rows, 64, &v64))) return rc;
+  if ((rc = attn_maps(ctx, dOh, rows, 64, &d64))) return rc;
+  static bool configured = false;
+  if (!configured) {
+    B200_CUDA_CHECK(cudaFuncSetAttribute(attn_bwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdSmem));
+    B200_CUDA_CHECK(cudaFuncSetAttribute(attn_bwd_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdSmem));
+    configured = true;
+  }
+  dim3 grid((L + 127) / 128, B * H);
+  AttnBwdArgs akv{(const float*)lse, (const float*)delta, (bf16*)dV, (bf16*)dK, L, scale};
+  attn_bwd_kernel<1><<<grid, 192, kBwdSmem, st>>>(k128, v128, q64, d64, akv);
+  B200_CUDA_CHECK(cudaGetLastError());
+  AttnBwdArgs aq{(const float*)lse, (const float*)delta, (bf16*)dQ, nullptr, L, scale};
+  attn_bwd_kernel<0><<<grid, 192, kBwdSmem, st>>>(q128, d128, k64, v64, aq);
+  B200_CUDA_CHECK(cudaGetLastError());
+  ctx->launches.fetch_add(3);
+  return B200_OK;
+}

@@ -530,6 +530,8 @@ class LoRASpecialNetwork(nn.Module):
 
     def force_to(self, device, dtype):
         self.to(device, dtype)
+        for lora in self.get_all_modules():  # not registered as sub-modules before apply_to (network_mixins.py:855-863)
+            lora.to(device, dtype)
 
     def reset_weights(self):
         for m in self.get_all_modules():

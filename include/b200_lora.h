@@ -149,6 +149,22 @@ int b200_timestep_embed(b200_ctx* ctx, const void* t_in, void* out, int B, int d
 int b200_add_bf16(b200_ctx* ctx, const void* a, const void* b, const void* c, void* y, int64_t n, void* stream);
 
 /* -------------------------------------------------------------------------------------------------
+ * Joint attention of the DiT blocks (head_dim 128, non-causal): Q/K/V head-major [B,H,L,128] bf16.
+ * Forward writes O token-major: tokens l < split to o0[(b*split + l)*ld0 + h*128 ..], the rest to
+ * o1[(b*(L-split) + l-split)*ld1 + h*128 ..] (text / image streams of a double block; split = 0 for a
+ * single-stream block writing into its concat buffer), and lse [B,H,L] fp32 (natural log).
+ * Backward: delta [B,H,L] fp32 and dOh [B,H,L,128] bf16 are caller-provided scratch; dQ/dK/dV head-major.
+ * Replaces torch SDPA inside diffusers' FLUX attention processor (toolkit/stable_diffusion_model.py:2192-2205
+ * call path; in-tree equivalent chroma/src/math.py:13-30) and its autograd backward.
+ * Algorithmic FLOPs: forward 4 B H L^2 128, backward 2.5x that.
+ */
+int b200_attn_fwd(b200_ctx* ctx, const void* Q, const void* K, const void* V, void* o0, int ld0, void* o1, int ld1,
+                  void* lse, int B, int H, int L, int split, float scale, void* stream);
+int b200_attn_bwd(b200_ctx* ctx, const void* Q, const void* K, const void* V, const void* o0, int ld0, const void* o1,
+                  int ld1, const void* do0, int ldd0, const void* do1, int ldd1, const void* lse, void* delta, void* dOh,
+                  void* dQ, void* dK, void* dV, int B, int H, int L, int split, float scale, void* stream);
+
+/* -------------------------------------------------------------------------------------------------
  * LoRA-wrapped Linear for Bm <= 8 rows (the AdaLN modulation projections): weight streaming at the
  * HBM roofline, fp32 master A [r,K] / B [N,r] used directly.
  *   y = bf16( bf16(x W^T + bias) + bf16( (c x A^T) B^T ) );  z = c x A^T [Bm,r] fp32 is saved.

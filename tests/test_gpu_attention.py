@@ -1,0 +1,84 @@
+"""tcgen05 flash attention (b200_attn_fwd / b200_attn_bwd) vs an fp32 PyTorch reference of the same op.
+Tolerances: outputs are bf16 (one rounding, ulp 2^-8) of fp32-accumulated products of bf16 P: 1e-2 relative
+Frobenius error on O and on dQ/dK/dV (the eager bf16 SDPA reference sits at the same distance from fp32)."""
+import math
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _rel(a, b):
+    a, b = a.float(), b.float()
+    return ((a - b).norm() / (b.norm() + 1e-30)).item()
+
+
+def _ref(Q, K, V, dO):
+    q, k, v = (t.float().requires_grad_(True) for t in (Q, K, V))
+    s = (q @ k.transpose(-1, -2)) / math.sqrt(Q.shape[-1])
+    lse = torch.logsumexp(s, -1)
+    o = torch.softmax(s, -1) @ v
+    o.backward(dO.float())
+    return o.detach(), lse.detach(), q.grad, k.grad, v.grad
+
+
+@pytest.mark.parametrize("B,H,L,split,scale_q", [(1, 2, 88, 24, 1.0), (2, 3, 320, 64, 1.0), (1, 2, 128, 0, 3.0),
+                                                  (1, 1, 1000, 0, 6.0), (1, 4, 4608, 512, 1.0)])
+def test_attention_fwd_bwd(B, H, L, split, scale_q):
+    from ai_toolkit_b200 import attention
+    torch.manual_seed(L)
+    Q = (torch.randn(B, H, L, 128, device=DEV) * scale_q).bfloat16()
+    K = torch.randn(B, H, L, 128, device=DEV).bfloat16()
+    V = torch.randn(B, H, L, 128, device=DEV).bfloat16()
+    D = H * 128
+    pad = 64  # outputs live inside wider buffers (the single-stream concat buffer)
+    o0 = torch.full((B * split, D), float("nan"), device=DEV, dtype=torch.bfloat16) if split else None
+    o1 = torch.full((B * (L - split), D + pad), float("nan"), device=DEV, dtype=torch.bfloat16)
+    lse = attention.fwd(Q, K, V, o0, o1[:, :D], split)
+    torch.cuda.synchronize()
+    dO = torch.randn(B, L, D, device=DEV).bfloat16()
+    o_ref, lse_ref, dq_ref, dk_ref, dv_ref = _ref(Q, K, V, dO.view(B, L, H, 128).transpose(1, 2))
+    o_tok = o_ref.transpose(1, 2).reshape(B, L, D)
+    got = torch.cat(([o0.view(B, split, D)] if split else []) + [o1[:, :D].reshape(B, L - split, D)], 1)
+    assert not torch.isnan(got.float()).any()
+    assert torch.isnan(o1[:, D:].float()).all()  # nothing written outside the head columns
+    assert _rel(got, o_tok) < 1e-2
+    assert (lse - lse_ref).abs().max().item() < 2e-2
+    do0 = dO[:, :split].reshape(B * split, D).contiguous() if split else None
+    do1 = dO[:, split:].reshape(B * (L - split), D).contiguous()
+    dQ, dK, dV = attention.bwd(Q, K, V, o0, o1[:, :D], do0, do1, lse, split)
+    torch.cuda.synchronize()
+    for name, g, r in (("dQ", dQ, dq_ref), ("dK", dK, dk_ref), ("dV", dV, dv_ref)):
+        assert not torch.isnan(g.float()).any(), name
+        assert _rel(g, r) < 1.5e-2, (name, _rel(g, r))
+
+
+def test_attention_flux_shape_timing():
+    """FLUX.1-dev joint attention (24 heads, L = 4608): report achieved TFLOP/s (informational)."""
+    from ai_toolkit_b200 import attention
+    B, H, L, split = 1, 24, 4608, 512
+    Q, K, V = (torch.randn(B, H, L, 128, device=DEV).bfloat16() for _ in range(3))
+    D = H * 128
+    o0 = torch.empty(B * split, D, device=DEV, dtype=torch.bfloat16)
+    o1 = torch.empty(B * (L - split), D, device=DEV, dtype=torch.bfloat16)
+    do0, do1 = torch.randn_like(o0), torch.randn_like(o1)
+    lse = attention.fwd(Q, K, V, o0, o1, split)
+    attention.bwd(Q, K, V, o0, o1, do0, do1, lse, split)
+    torch.cuda.synchronize()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+    ev[0].record()
+    for _ in range(5):
+        lse = attention.fwd(Q, K, V, o0, o1, split)
+    ev[1].record()
+    for _ in range(5):
+        attention.bwd(Q, K, V, o0, o1, do0, do1, lse, split)
+    ev[2].record()
+    torch.cuda.synchronize()
+    f = 4.0 * B * H * L * L * 128
+    tf, tb = ev[0].elapsed_time(ev[1]) / 5, ev[1].elapsed_time(ev[2]) / 5
+    print(f"attention fwd {tf*1e3:.0f} us = {f/tf/1e9:.0f} TFLOP/s; bwd {tb*1e3:.0f} us = {2.5*f/tb/1e9:.0f} TFLOP/s (algorithmic)")
+    ref = torch.nn.functional.scaled_dot_product_attention(Q, K, V).transpose(1, 2).reshape(B, L, D)
+    got = torch.cat([o0.view(B, split, D), o1.view(B, L - split, D)], 1)
+    assert _rel(got, ref) < 1e-2
