@@ -134,6 +134,16 @@ class FluxTransformer2DModel(nn.Module):
         self.cfg = cfg
         d, hd = cfg.inner_dim, cfg.attention_head_dim
         inner = int(d * cfg.mlp_ratio)
+        prev = torch.get_default_dtype()
+        torch.set_default_dtype(dtype)  # build the 12 B parameters directly in bf16 (no fp32 staging copy)
+        try:
+            self._build(cfg, d, hd, inner, device)
+        finally:
+            torch.set_default_dtype(prev)
+        self.requires_grad_(False)  # frozen base (BaseSDTrainProcess.py:1900)
+        self._engine = None
+
+    def _build(self, cfg, d, hd, inner, device):
         with torch.device(device if device is not None else "cpu"):
             self.time_text_embed = _CombinedEmbeddings(d, cfg.pooled_projection_dim, cfg.guidance_embeds)
             self.context_embedder = nn.Linear(cfg.joint_attention_dim, d)
@@ -143,9 +153,6 @@ class FluxTransformer2DModel(nn.Module):
                 [FluxSingleTransformerBlock(d, hd, inner) for _ in range(cfg.num_single_layers)])
             self.norm_out = _AdaNorm(d, 2)
             self.proj_out = nn.Linear(d, cfg.in_channels)
-        self.to(dtype)
-        self.requires_grad_(False)  # frozen base (BaseSDTrainProcess.py:1900)
-        self._engine = None
 
     @property
     def dtype(self):

@@ -1,0 +1,335 @@
+#!/usr/bin/env python
+"""bench.py — train-steps/sec of FLUX.1-dev LoRA (r=16, bs=1/GPU, 1024^2) on the B200-native path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+
+One "step" = SDTrainer.hook_train_loop: add_noise + pack -> forward through the
+LoRA-wrapped frozen DiT -> flow-matching MSE -> backward (dX through 11.9 B frozen weights, dA/dB for 494 adapters)
+-> [N GPUs: all-reduce of the flat LoRA gradient over NCCL] -> clip_grad_norm_(1.0) -> AdamW(eps 1e-6) -> EMA.
+Synthetic latents / embeddings / weights of the true shapes (no network for checkpoints).  Prints ONE JSON line.
+
+  value     steps/s of the whole job with the batch resident in HBM (CUDA events, max over ranks)
+  e2e       the same through FluxLoRATrainStep.hook_train_loop with pinned HOST batches: H2D copies and the D2H
+            read of the loss inside the timed region
+  roofline  the dominant kernel (fused LoRA-Linear tcgen05 GEMM) timed live, against MEASURED_PEAKS.json
+  cpu_baseline  the oracle (eager PyTorch restatement of the reference path) on the host cores, bounded sample
+
+`--impl reference` times the reference's CPU implementation of the path: ostris/ai-toolkit is not pip-installable
+(no setup.py / pyproject) and its model code is diffusers (absent), so this is the oracle port on the host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+RANK = 16
+LATENT = (16, 128, 128)  # 1024^2 image -> 16 x 128 x 128 latent -> 4096 packed tokens
+TEXT_LEN = 512
+
+
+def flux_flops(B=1, r=RANK, I=4096, T=512, D=3072, M=12288, n_double=19, n_single=38):
+    """Algorithmic FLOPs of one step: F = 2 F_lin + 3.5 F_attn + 3 F_lora."""
+    L = I + T
+    f_lin = n_double * (2 * B * (I + T) * (4 * D * D + 2 * D * M) + 2 * B * 2 * 6 * D * D) \
+        + n_single * (2 * B * L * (3 * D * D + D * M + (D + M) * D) + 2 * B * 3 * D * D)
+    f_attn = (n_double + n_single) * 4 * B * 24 * L * L * 128
+    lora = 0
+    for toks, i, o, cnt in ((I, D, D, 4 * n_double), (T, D, D, 4 * n_double), (I, D, M, n_double), (I, M, D, n_double),
+                            (T, D, M, n_double), (T, M, D, n_double), (1, D, 6 * D, 2 * n_double),
+                            (L, D, D, 3 * n_single), (L, D, M, n_single), (L, D + M, D, n_single), (1, D, 3 * D, n_single)):
+        lora += cnt * 2 * B * toks * r * (i + o)
+    return 2 * f_lin + 3.5 * f_attn + 3 * lora, f_lin, f_attn, lora
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d, "measured"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.rows = []
+        self.stop_flag = False
+
+    def run(self):
+        q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unsampled"]}
+        sm = sorted(float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit())
+        reasons = set()
+        for r in self.rows:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": float(self.rows[0][1]) if self.rows else None,
+                "power_w_max": max(float(r[2]) for r in self.rows), "reasons": sorted(reasons)}
+
+
+# ---------------------------------------------------------------------------------------------------
+# CPU baseline / reference arm: the oracle port on the host cores
+# ---------------------------------------------------------------------------------------------------
+def cpu_reference_sample(n_double=1, n_single=1, steps=1, warmup=0, tokens_img=1024, tokens_txt=128):
+    """Eager oracle (oracle/flux_ref.py + oracle/lora_ref.py) on the host CPU, FLUX width (D = 3072, 24 heads,
+    MLP 12288) but a bounded number of blocks / tokens; returns (seconds per sample-step, F_sample, description)."""
+    import torch
+
+    from oracle import flux_ref, lora_ref
+
+    torch.set_num_threads(os.cpu_count() or 1)
+    torch.manual_seed(0)
+    cfg = flux_ref.FluxConfig(num_layers=n_double, num_single_layers=n_single)
+    model = flux_ref.FluxTransformer2DModel(cfg).to(torch.bfloat16).requires_grad_(False)
+    net = lora_ref.LoRANetworkRef(model, lora_dim=RANK)
+    params = [p for l in net.loras for p in (l.lora_down.weight, l.lora_up.weight)]
+    opt = torch.optim.AdamW(params, lr=1e-4, eps=1e-6)
+    side = int(round((tokens_img * 4) ** 0.5))
+    lat = torch.randn(1, 16, side, side).bfloat16()
+    noise = torch.randn_like(lat)
+    t = torch.tensor([500.0])
+    text = (torch.randn(1, tokens_txt, 4096) * 0.1).bfloat16()
+    pooled = torch.randn(1, 768).bfloat16()
+    times = []
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        opt.zero_grad(set_to_none=True)
+        noisy = lora_ref.add_noise_flowmatch(lat, noise, t).to(torch.bfloat16)
+        with net:
+            pred = lora_ref.flux_predict(model, noisy, t, text, pooled, 1.0, flux_ref.pack_latents, flux_ref.unpack_latents,
+                                         flux_ref.make_img_ids)
+            loss = lora_ref.flow_loss(pred, lat, noise)
+            loss.backward()
+        torch.nn.utils.clip_grad_norm_(params, 1.0)
+        opt.step()
+        float(loss)
+        if it >= warmup:
+            times.append(time.perf_counter() - t0)
+    I = (side // 2) ** 2
+    f_sample = flux_flops(1, RANK, I, tokens_txt, n_double=n_double, n_single=n_single)[0]
+    desc = (f"oracle port (eager PyTorch bf16) on {os.cpu_count()} host cores: FLUX-width blocks {n_double} double + {n_single} "
+            f"single, {I}+{tokens_txt} tokens, r={RANK}; steps/s extrapolated linearly in F_step "
+            f"({f_sample / 1e12:.2f} of {flux_flops()[0] / 1e12:.1f} TFLOP)")
+    return sum(times) / len(times), f_sample, desc
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sec, f_sample, desc = cpu_reference_sample(steps=max(1, min(args.steps, 3)), warmup=min(args.warmup, 1))
+    f_step = flux_flops()[0]
+    value = 1.0 / (sec * f_step / f_sample)
+    out = {"metric": "train-steps/sec FLUX.1-dev LoRA r=16 bs=1 1024^2", "value": value, "unit": "steps/s", "n_gpus": args.gpus,
+           "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 / value, "higher_is_better": True, "scaling": "weak",
+           "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "impl": "reference",
+           "config": {"workload": "FLUX.1-dev LoRA r=16 bs=1 1024^2 (configs[2]), CPU sample extrapolated"},
+           "cpu_baseline": {"value": value, "unit": "steps/s", "cores": os.cpu_count(), "kind": "port", "sample": desc},
+           "e2e": {"value": value, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(out), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------
+# B200 arm
+# ---------------------------------------------------------------------------------------------------
+def run_b200(args):
+    import torch
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=dev)
+    from ai_toolkit_b200 import LoRASpecialNetwork, cabi
+    from ai_toolkit_b200.flux import FluxTransformer2DModel, flux_dev_config
+    from ai_toolkit_b200.optimizer import B200AdamW
+    from ai_toolkit_b200.train_step import FluxLoRATrainStep
+
+    ctx = cabi.Context.get(local)
+    cfg = flux_dev_config()
+    if args.layers:
+        cfg.num_layers, cfg.num_single_layers = args.layers
+    t_setup = time.time()
+    model = FluxTransformer2DModel(cfg, device=dev).init_synthetic_(seed=0)
+    net = LoRASpecialNetwork(text_encoder=None, unet=model, lora_dim=RANK, alpha=RANK, train_unet=True,
+                             train_text_encoder=False, is_flux=True, transformer_only=True)
+    net.force_to(dev, torch.float32)
+    net._update_torch_multiplier()
+    net.apply_to(None, model, False, True)
+    g = torch.Generator(device=dev).manual_seed(1234)
+    with torch.no_grad():  # non-zero lora_up so that every gradient path carries signal (same on every rank)
+        for m in net.get_all_modules():
+            m.lora_up.weight.copy_(torch.randn(m.lora_up.weight.shape, generator=g, device=dev) * 0.02)
+    net.mark_params_changed()
+    opt = B200AdamW(net, lr=1e-4, betas=(0.9, 0.999), eps=1e-6, weight_decay=1e-2, max_grad_norm=1.0, ema_decay=0.99,
+                    grad_prescale=1.0 / world)
+    step = FluxLoRATrainStep(model, net, opt, batch_size=1, latent_shape=LATENT, text_len=TEXT_LEN, guidance_scale=1.0,
+                             use_cuda_graph=not args.no_graph)
+    # synthetic batch: host (pinned) copies for the e2e leg, seeded per rank
+    hg = torch.Generator().manual_seed(1234 + rank)
+    host = {
+        "latents": torch.randn(1, *LATENT, generator=hg).bfloat16().pin_memory(),
+        "noise": torch.randn(1, *LATENT, generator=hg).bfloat16().pin_memory(),
+        "timesteps": torch.linspace(1000, 1, 1000)[torch.randint(0, 999, (1,), generator=hg)].float().pin_memory(),
+        "text_embeds": (torch.randn(1, TEXT_LEN, 4096, generator=hg) * 0.1).bfloat16().pin_memory(),
+        "pooled_embeds": torch.randn(1, 768, generator=hg).bfloat16().pin_memory(),
+    }
+    h2d = sum(v.numel() * v.element_size() for v in host.values())
+    step.load_batch(**{k: host[k] for k in ("latents", "noise", "timesteps")}, text_embeds=host["text_embeds"],
+                    pooled_embeds=host["pooled_embeds"])
+    torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    # launches of OUR kernels per step, counted on an eager step (graph replays do not pass through the C ABI)
+    n0 = ctx.launch_count()
+    step.run()
+    torch.cuda.synchronize()
+    launches_per_step = ctx.launch_count() - n0
+    losses = []
+    for _ in range(max(3, args.warmup)):  # includes the CUDA-graph capture
+        losses.append(step.run())
+    barrier()
+    setup_s = time.time() - t_setup
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for _ in range(args.steps):
+        loss_dev = step.run()
+    ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1) / args.steps
+    # e2e: host batches in, loss out, every step
+    barrier()
+    t0 = time.perf_counter()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    last = None
+    for _ in range(args.steps):
+        last = step.hook_train_loop(host)
+    e1.record()
+    barrier()
+    ms_e2e = max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3) / args.steps
+    sampler.stop_flag = True
+    t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
+    if world > 1:
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+    ms, ms_e2e = float(t[0]), float(t[1])
+
+    # dominant kernel, timed live: the fused LoRA-Linear GEMM at the FLUX MLP-up shape
+    peaks, peak_kind = measured_peaks()
+    roof = None
+    if rank == 0:
+        M_, N_, K_ = 4608, 12288, 3072
+        x = (torch.randn(M_, K_, device=dev) * 0.5).bfloat16()
+        w = (torch.randn(N_, K_, device=dev) * 0.02).bfloat16()
+        zc = (torch.randn(M_, 64, device=dev) * 0.1).bfloat16()
+        bp = (torch.randn(N_, 64, device=dev) * 0.02).bfloat16()
+        bias = torch.zeros(N_, device=dev, dtype=torch.bfloat16)
+        y = torch.empty(M_, N_, device=dev, dtype=torch.bfloat16)
+        flush = torch.empty(256 * 1024 * 1024, device=dev, dtype=torch.uint8)
+        for _ in range(3):
+            cabi.gemm_bf16(x, w, y, a1=zc, b1=bp, bias=bias)
+        tt = []
+        for _ in range(10):
+            flush.zero_()  # L2 flush between timed launches (buffer > 126 MB L2)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            cabi.gemm_bf16(x, w, y, a1=zc, b1=bp, bias=bias)
+            b.record()
+            torch.cuda.synchronize()
+            tt.append(a.elapsed_time(b))
+        kms = sum(tt) / len(tt)
+        fl = 2.0 * M_ * N_ * K_ + 2.0 * M_ * RANK * N_  # base GEMM + rank-r up-projection riding in the same tile
+        ach = fl / kms / 1e9
+        roof = {"bound": "tensor", "kernel": "gemm_bf16_kernel<2,256,6,0,0> fused LoRA-Linear M=4608 N=12288 K=3072 r=16",
+                "achieved": ach, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": ach / peaks["bf16_tflops"],
+                "peak_kind": f"{peak_kind} burst (kernel timed alone)", "traffic": None, "us_per_launch": kms * 1e3}
+    if rank != 0:
+        return
+    f_step, f_lin, f_attn, f_lora = flux_flops(1, RANK, n_double=cfg.num_layers, n_single=cfg.num_single_layers)
+    value = world * 1e3 / ms
+    out = {
+        "metric": "train-steps/sec FLUX.1-dev LoRA r=16 bs=1 1024^2", "value": value, "unit": "steps/s", "n_gpus": world,
+        "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": "FLUX.1-dev LoRA r=16 bs=1/GPU 1024^2 (BASELINE.json configs[2])", "global_batch": world,
+                   "tokens": 4608, "lora_modules": len(net.get_all_modules()), "lora_params": int(net.n_params),
+                   "blocks": [cfg.num_layers, cfg.num_single_layers], "parallelism": f"dp{world}", "ema": True,
+                   "cuda_graph": not args.no_graph,
+                   "l2": "per-step working set (23.8 GB weights + activations) >> 126 MB L2; no explicit flush"},
+        "impl": "b200",
+        "step_roofline": {"bound": "tensor", "f_step_tflop": f_step / 1e12, "achieved": f_step / (ms * 1e-3) / 1e12,
+                          "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
+                          "frac": f_step / (ms * 1e-3) / 1e12 / peaks["bf16_tflops_sustained"], "peak_kind": f"{peak_kind} sustained"},
+        "roofline": roof,
+        "e2e": {"value": world * 1e3 / ms_e2e, "unit": "steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+                "ms_per_step": ms_e2e},
+        "gpu_launches": int(launches_per_step) * args.steps,
+        "launches_per_step": int(launches_per_step),
+        "clocks": sampler.summary(),
+        "loss_last": last["loss"] if last else None,
+        "setup_s": setup_s,
+    }
+    if not args.skip_cpu_baseline:
+        sec, f_sample, desc = cpu_reference_sample(steps=1, warmup=0)
+        v = 1.0 / (sec * f_step / f_sample)
+        out["cpu_baseline"] = {"value": v, "unit": "steps/s", "cores": os.cpu_count(), "kind": "port", "sample": desc}
+    print(json.dumps(out), flush=True)
+    if world > 1:
+        torch.distributed.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--skip-cpu-baseline", action="store_true")
+    ap.add_argument("--layers", type=int, nargs=2, default=None, help="debug: override (double, single) block counts")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()
