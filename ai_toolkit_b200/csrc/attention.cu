@@ -57,9 +57,10 @@ struct AttnFwdArgs {
   float scale;
 };
 
-constexpr int kFwdSmem = 1024 + 32768 + 2 * 32768 + 2 * 32768 + 32768 + 16 * 8 + 16;
+constexpr int kFwdSmem = 1024 + 32768 + 2 * 32768 + 2 * 32768 + 32768 + 16 * 8 + 16 + 2 * 2 * 128 * 4;
+constexpr int kAttnThreads = 320;  // TMA warp, MMA warp, 8 softmax warps (two per TMEM sub-partition)
 
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(kAttnThreads, 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                 const __grid_constant__ CUtensorMap tmV, const AttnFwdArgs g) {
   extern __shared__ uint8_t smem_raw[];
@@ -79,6 +80,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   uint64_t* p_full = bars + 13;
   uint64_t* pv_done = bars + 14;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 15);
+  float* xch = reinterpret_cast<float*>(bars + 16);  // [2 parity][2 halves][128 rows] row-max / row-sum exchange
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int bh = blockIdx.y;
@@ -100,9 +102,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         mbar_init(&v_full[s], 1);
         mbar_init(&v_empty[s], 1);
         mbar_init(&s_full[s], 1);
-        mbar_init(&s_empty[s], 128);
+        mbar_init(&s_empty[s], 256);
       }
-      mbar_init(p_full, 128);
+      mbar_init(p_full, 256);
       mbar_init(pv_done, 1);
       fence_barrier_init();
     }
@@ -182,8 +184,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       }
     }
   } else {
-    // ---------------------------------------------------------------- softmax / epilogue: one thread per row
+    // ---------------------------------------------------------------- softmax / epilogue
+    // two threads per row: thread (r, h) owns columns [64 h, 64 h + 64) of the S / P / O row r
     const int q = warp & 3;
+    const int h = (warp - 2) >> 2;
     const int r = q * 32 + lane;
     const int qi = q0 + r;
     const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
@@ -194,21 +198,34 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       const uint32_t ph = (j >> 1) & 1;
       mbar_wait(&s_full[s], ph, 17);
       tc_fence_after();
-      const int kv0 = j * 128;
-      // pass 1: row max
+      uint32_t v0[32], v1[32];
+      tmem_ld_32x32(tS[s] + lane_off + h * 64, v0);
+      tmem_ld_32x32(tS[s] + lane_off + h * 64 + 32, v1);
+      tmem_ld_wait();
+      tc_fence_before();
+      mbar_arrive(&s_empty[s]);  // S is in registers: the tensor core may overwrite this buffer
+      const int nvalid = g.L - (j * 128 + h * 64);  // columns of my half that exist
+      float x[64];
       float mx = -INFINITY;
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        uint32_t v[32];
-        tmem_ld_32x32(tS[s] + lane_off + c * 32, v);
-        tmem_ld_wait();
+      if (nvalid >= 64) {
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
-          const float x = (kv0 + c * 32 + i < g.L) ? __uint_as_float(v[i]) * c2 : -INFINITY;
-          mx = fmaxf(mx, x);
+          x[i] = __uint_as_float(v0[i]) * c2;
+          x[32 + i] = __uint_as_float(v1[i]) * c2;
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          x[i] = i < nvalid ? __uint_as_float(v0[i]) * c2 : -INFINITY;
+          x[32 + i] = 32 + i < nvalid ? __uint_as_float(v1[i]) * c2 : -INFINITY;
         }
       }
-      const float m_new = fmaxf(m_used, mx);
+#pragma unroll
+      for (int i = 0; i < 64; ++i) mx = fmaxf(mx, x[i]);
+      float* xm = xch + (j & 1) * 256;
+      xm[h * 128 + r] = mx;
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      const float m_new = fmaxf(m_used, fmaxf(mx, xm[(h ^ 1) * 128 + r]));
       const bool need = (m_new > m_used + 8.0f);  // also true for the first tile (m_used = -inf)
       const bool any_need = __any_sync(0xffffffffu, need);
       if (j > 0) {
@@ -223,63 +240,60 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         }
         if (j > 0) {
 #pragma unroll 1
-          for (int c = 0; c < 4; ++c) {
+          for (int c = 0; c < 2; ++c) {
             uint32_t v[32];
-            tmem_ld_32x32(tO + lane_off + c * 32, v);
+            tmem_ld_32x32(tO + lane_off + h * 64 + c * 32, v);
             tmem_ld_wait();
 #pragma unroll
             for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * f);
-            tmem_st_32x32(tO + lane_off + c * 32, v);
+            tmem_st_32x32(tO + lane_off + h * 64 + c * 32, v);
           }
           tmem_st_wait();
         }
       }
-      // pass 2: P = exp2(S c - m_used), row sum, bf16 -> swizzled smem (two [128 x 64] K-major blocks)
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        uint32_t v[32];
-        tmem_ld_32x32(tS[s] + lane_off + c * 32, v);
-        tmem_ld_wait();
-        float p[32];
+      // P = exp2(S c - m_used) -> bf16 -> swizzled smem block h ([128 rows x 64 kv] K-major)
+      uint8_t* blk = sP + h * 16384;
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const float x = (kv0 + c * 32 + i < g.L) ? ex2(__uint_as_float(v[i]) * c2 - m_used) : 0.f;
-          p[i] = x;
-          l_sum += x;
-        }
-        uint8_t* blk = sP + (c >> 1) * 16384;
+      for (int k8 = 0; k8 < 8; ++k8) {
+        float p[8];
 #pragma unroll
-        for (int k8 = 0; k8 < 4; ++k8) {
-          uint4 u;
-          u.x = pack_bf16x2(p[k8 * 8 + 0], p[k8 * 8 + 1]);
-          u.y = pack_bf16x2(p[k8 * 8 + 2], p[k8 * 8 + 3]);
-          u.z = pack_bf16x2(p[k8 * 8 + 4], p[k8 * 8 + 5]);
-          u.w = pack_bf16x2(p[k8 * 8 + 6], p[k8 * 8 + 7]);
-          st_sw128(blk, r, (c & 1) * 4 + k8, u);
+        for (int e = 0; e < 8; ++e) {
+          p[e] = ex2(x[k8 * 8 + e] - m_used);
+          l_sum += p[e];
         }
+        uint4 u;
+        u.x = pack_bf16x2(p[0], p[1]);
+        u.y = pack_bf16x2(p[2], p[3]);
+        u.z = pack_bf16x2(p[4], p[5]);
+        u.w = pack_bf16x2(p[6], p[7]);
+        st_sw128(blk, r, k8, u);
       }
       tc_fence_before();
-      mbar_arrive(&s_empty[s]);
       fence_proxy_async_smem();
       mbar_arrive(p_full);
     }
+    // combine the two half-row sums
+    float* xl = xch + (n_kv & 1) * 256;
+    xl[h * 128 + r] = l_sum;
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    l_sum += xl[(h ^ 1) * 128 + r];
     mbar_wait(pv_done, (n_kv - 1) & 1, 19);
     tc_fence_after();
     const float inv = 1.0f / l_sum;
     const bool live = qi < g.L;
     bf16* orow = nullptr;
     if (live) {
-      const int b = bh / g.H, h = bh % g.H;
+      const int b = bh / g.H, hh = bh % g.H;
       if (qi < g.split)
-        orow = g.o0 + (static_cast<size_t>(b) * g.split + qi) * g.ld0 + h * 128;
+        orow = g.o0 + (static_cast<size_t>(b) * g.split + qi) * g.ld0 + hh * 128 + h * 64;
       else
-        orow = g.o1 + (static_cast<size_t>(b) * (g.L - g.split) + (qi - g.split)) * g.ld1 + h * 128;
-      g.lse[row_base + qi] = (m_used + log2f(l_sum)) * kLn2;
+        orow = g.o1 + (static_cast<size_t>(b) * (g.L - g.split) + (qi - g.split)) * g.ld1 + hh * 128 + h * 64;
+      if (h == 0) g.lse[row_base + qi] = (m_used + log2f(l_sum)) * kLn2;
     }
 #pragma unroll 1
-    for (int c = 0; c < 4; ++c) {  // tcgen05.ld is warp-collective: every lane loads, only live rows store
+    for (int c = 0; c < 2; ++c) {  // tcgen05.ld is warp-collective: every lane loads, only live rows store
       uint32_t v[32];
-      tmem_ld_32x32(tO + lane_off + c * 32, v);
+      tmem_ld_32x32(tO + lane_off + h * 64 + c * 32, v);
       tmem_ld_wait();
       if (live) {
 #pragma unroll
@@ -343,12 +357,12 @@ struct AttnBwdArgs {
 };
 
 constexpr int kBwdStages = 3;
-constexpr int kBwdSmem = 1024 + 2 * 32768 + kBwdStages * 32768 + 2 * 16384 + 16 * 8 + 16;
+constexpr int kBwdSmem = 1024 + 2 * 32768 + kBwdStages * 32768 + 2 * 16384 + 16 * 8 + 16 + 8 * 64 * 4;
 
 // MODE_KV = 1: stationary (R0, R1) = (K_j, V_j), streamed (T0, T1) = (Q_i, dO_i); outputs dV (acc0), dK (acc1)
 // MODE_KV = 0: stationary (R0, R1) = (Q_i, dO_i), streamed (T0, T1) = (K_j, V_j); output  dQ (acc0)
 template <int MODE_KV>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(kAttnThreads, 1)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tmR0, const __grid_constant__ CUtensorMap tmR1,
                 const __grid_constant__ CUtensorMap tmT0, const __grid_constant__ CUtensorMap tmT1, const AttnBwdArgs g) {
   extern __shared__ uint8_t smem_raw[];
@@ -367,6 +381,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmR0, const __grid_constant_
   uint64_t* pb_full = bars + 11;
   uint64_t* pb_empty = bars + 12;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
+  float* colws = reinterpret_cast<float*>(bars + 14);  // per softmax warp: 32 x (lse2, delta*scale) of its columns
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int bh = blockIdx.y;
@@ -389,9 +404,9 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmR0, const __grid_constant_
       }
       for (int s = 0; s < 2; ++s) {
         mbar_init(&x_full[s], 1);
-        mbar_init(&x_empty[s], 128);
+        mbar_init(&x_empty[s], 256);
       }
-      mbar_init(pb_full, 128);
+      mbar_init(pb_full, 256);
       mbar_init(pb_empty, 1);
       fence_barrier_init();
     }
@@ -494,62 +509,73 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmR0, const __grid_constant_
       }
     }
   } else {
+    // two threads per row: thread (r, h) owns columns [32 h, 32 h + 32) of each 64-column S / dP tile
     const int q = warp & 3;
+    const int h = (warp - 2) >> 2;
     const int r = q * 32 + lane;
     const int ri = r0 + r;  // kv index (MODE_KV) or q index
     const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
     const float c2 = g.scale * kLog2e;
     const float* lse_bh = g.lse + row_base;
     const float* delta_bh = g.delta + row_base;
-    float my_lse2 = 0.f, my_delta = 0.f;
+    float* myws = colws + (warp - 2) * 64;
+    float my_lse2 = 0.f, my_dls = 0.f;
     if (!MODE_KV && ri < g.L) {
       my_lse2 = lse_bh[ri] * kLog2e;
-      my_delta = delta_bh[ri];
+      my_dls = delta_bh[ri] * g.scale;
     }
     for (int i = 0; i < n_t; ++i) {
       const int xb = i & 1;
       const uint32_t xph = (i >> 1) & 1;
+      const int c0 = i * 64 + h * 32;  // first streamed index (q for MODE_KV, kv otherwise) of my columns
+      if (MODE_KV) {  // per-column softmax statistics of this tile: coalesced load, broadcast through smem
+        const int cq = c0 + lane;
+        __syncwarp();
+        myws[lane] = cq < g.L ? lse_bh[cq] * kLog2e : 0.f;
+        myws[32 + lane] = cq < g.L ? delta_bh[cq] * g.scale : 0.f;
+        __syncwarp();
+      }
       mbar_wait(&x_full[xb], xph, 25);
       tc_fence_after();
-      const int c0 = i * 64;
-      uint32_t pp[32], dd[32];  // packed bf16 pairs: P and dS rows (64 values each)
-#pragma unroll
-      for (int hlf = 0; hlf < 2; ++hlf) {
-        uint32_t sv[32], dv[32];
-        tmem_ld_32x32(tX0[xb] + lane_off + hlf * 32, sv);
-        tmem_ld_32x32(tX1[xb] + lane_off + hlf * 32, dv);
-        tmem_ld_wait();
-#pragma unroll
-        for (int k = 0; k < 32; k += 2) {
-          float p2[2], d2[2];
-#pragma unroll
-          for (int e = 0; e < 2; ++e) {
-            const int cc = c0 + hlf * 32 + k + e;  // q index (MODE_KV) or kv index
-            const bool valid = (cc < g.L) && (ri < g.L);
-            float lse2, dl;
-            if (MODE_KV) {
-              const int cq = cc < g.L ? cc : 0;
-              lse2 = __ldg(lse_bh + cq) * kLog2e;
-              dl = __ldg(delta_bh + cq);
-            } else {
-              lse2 = my_lse2;
-              dl = my_delta;
-            }
-            const float p = valid ? ex2(__uint_as_float(sv[k + e]) * c2 - lse2) : 0.f;
-            p2[e] = p;
-            d2[e] = p * (__uint_as_float(dv[k + e]) - dl) * g.scale;
-          }
-          pp[hlf * 16 + k / 2] = pack_bf16x2(p2[0], p2[1]);
-          dd[hlf * 16 + k / 2] = pack_bf16x2(d2[0], d2[1]);
-        }
-      }
+      uint32_t sv[32], dv[32];
+      tmem_ld_32x32(tX0[xb] + lane_off + h * 32, sv);
+      tmem_ld_32x32(tX1[xb] + lane_off + h * 32, dv);
+      tmem_ld_wait();
       tc_fence_before();
       mbar_arrive(&x_empty[xb]);
+      const int nvalid = g.L - c0;
+      uint32_t pp[16], dd[16];  // packed bf16 pairs of my 32 columns: P and dS
+#pragma unroll
+      for (int k = 0; k < 32; k += 4) {
+        float l4[4], d4[4];
+        if (MODE_KV) {
+          *reinterpret_cast<float4*>(l4) = *reinterpret_cast<const float4*>(myws + k);
+          *reinterpret_cast<float4*>(d4) = *reinterpret_cast<const float4*>(myws + 32 + k);
+        } else {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            l4[e] = my_lse2;
+            d4[e] = my_dls;
+          }
+        }
+        float p4[4], s4[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          float p = ex2(__uint_as_float(sv[k + e]) * c2 - l4[e]);
+          if (nvalid < 32) p = (k + e < nvalid) ? p : 0.f;  // only the last tile has missing columns
+          p4[e] = p;
+          s4[e] = p * (__uint_as_float(dv[k + e]) * g.scale - d4[e]);
+        }
+        pp[k / 2] = pack_bf16x2(p4[0], p4[1]);
+        pp[k / 2 + 1] = pack_bf16x2(p4[2], p4[3]);
+        dd[k / 2] = pack_bf16x2(s4[0], s4[1]);
+        dd[k / 2 + 1] = pack_bf16x2(s4[2], s4[3]);
+      }
       if (i > 0) mbar_wait(pb_empty, (i - 1) & 1, 26);
 #pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        if (MODE_KV) st_sw128(sPB0, r, c, make_uint4(pp[c * 4], pp[c * 4 + 1], pp[c * 4 + 2], pp[c * 4 + 3]));
-        st_sw128(sPB1, r, c, make_uint4(dd[c * 4], dd[c * 4 + 1], dd[c * 4 + 2], dd[c * 4 + 3]));
+      for (int c = 0; c < 4; ++c) {
+        if (MODE_KV) st_sw128(sPB0, r, h * 4 + c, make_uint4(pp[c * 4], pp[c * 4 + 1], pp[c * 4 + 2], pp[c * 4 + 3]));
+        st_sw128(sPB1, r, h * 4 + c, make_uint4(dd[c * 4], dd[c * 4 + 1], dd[c * 4 + 2], dd[c * 4 + 3]));
       }
       fence_proxy_async_smem();
       mbar_arrive(pb_full);
@@ -561,12 +587,12 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmR0, const __grid_constant_
       const uint32_t ta = which == 0 ? tA0 : tA1;
       bf16* out = which == 0 ? g.out0 : g.out1;
 #pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
+      for (int c = 0; c < 2; ++c) {
         uint32_t v[32];
-        tmem_ld_32x32(ta + lane_off + c * 32, v);
+        tmem_ld_32x32(ta + lane_off + h * 64 + c * 32, v);
         tmem_ld_wait();
         if (ri < g.L) {
-          bf16* orow = out + (row_base + ri) * 128 + c * 32;
+          bf16* orow = out + (row_base + ri) * 128 + h * 64 + c * 32;
 #pragma unroll
           for (int k8 = 0; k8 < 4; ++k8) {
             uint4 u;
@@ -614,7 +640,7 @@ extern "C" int b200_attn_fwd(b200_ctx* ctx, const void* Q, const void* K, const 
   }
   AttnFwdArgs a{(bf16*)o0, ld0, (bf16*)o1, ld1, (float*)lse, B, H, L, split, scale};
   dim3 grid((L + 127) / 128, B * H);
-  attn_fwd_kernel<<<grid, 192, kFwdSmem, reinterpret_cast<cudaStream_t>(stream)>>>(tq, tk, tv, a);
+  attn_fwd_kernel<<<grid, kAttnThreads, kFwdSmem, reinterpret_cast<cudaStream_t>(stream)>>>(tq, tk, tv, a);
   B200_CUDA_CHECK(cudaGetLastError());
   ctx->launches.fetch_add(1);
   return B200_OK;
@@ -654,10 +680,10 @@ extern "C" int b200_attn_bwd(b200_ctx* ctx, const void* Q, const void* K, const 
   }
   dim3 grid((L + 127) / 128, B * H);
   AttnBwdArgs akv{(const float*)lse, (const float*)delta, (bf16*)dV, (bf16*)dK, L, scale};
-  attn_bwd_kernel<1><<<grid, 192, kBwdSmem, st>>>(k128, v128, q64, d64, akv);
+  attn_bwd_kernel<1><<<grid, kAttnThreads, kBwdSmem, st>>>(k128, v128, q64, d64, akv);
   B200_CUDA_CHECK(cudaGetLastError());
   AttnBwdArgs aq{(const float*)lse, (const float*)delta, (bf16*)dQ, nullptr, L, scale};
-  attn_bwd_kernel<0><<<grid, 192, kBwdSmem, st>>>(q128, d128, k64, v64, aq);
+  attn_bwd_kernel<0><<<grid, kAttnThreads, kBwdSmem, st>>>(q128, d128, k64, v64, aq);
   B200_CUDA_CHECK(cudaGetLastError());
   ctx->launches.fetch_add(3);
   return B200_OK;

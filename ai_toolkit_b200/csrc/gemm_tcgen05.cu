@@ -7,8 +7,8 @@
 // frozen base GEMM, so the adapter costs one extra 64-wide k-block and no extra pass over the output
 // (reference: toolkit/network_mixins.py:304-342 runs it as ~8 separate full-size elementwise kernels).
 //
-// Roles (192 threads):  warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread MMA issuer,
-// warps 2..5 = epilogue (one TMEM sub-partition each).  Two TMEM accumulator stages let the epilogue
+// Roles (320 threads):  warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread MMA issuer,
+// warps 2..9 = epilogue (two per TMEM sub-partition, alternating 32-column chunks).  Two TMEM accumulator stages let the epilogue
 // of tile i overlap the main loop of tile i+1.
 //
 // CG == 2 pairs two CTAs of a cluster on one 256 x BN tile (tcgen05.mma.cta_group::2): each CTA loads
@@ -209,7 +209,7 @@ struct GemmCfg {
 };
 
 template <int CG, int BN, int STAGES, int A_MN, int B_MN>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(320, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmB0,
                  const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmB1,
                  const GemmArgs g) {
@@ -244,7 +244,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       }
       for (int a = 0; a < 2; ++a) {
         mbar_init(&tfull[a], 1);
-        mbar_init(&tempty[a], 128 * CG);  // every epilogue thread of every CTA of the pair
+        mbar_init(&tempty[a], 256 * CG);  // every epilogue thread of every CTA of the pair
       }
       fence_barrier_init();
     }
@@ -384,8 +384,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       }
     }
   } else {
-    // ------------------------------------------------------------------ epilogue (warps 2..5)
+    // ------------------------------------------------------------------ epilogue (warps 2..9)
+    // two warps per TMEM sub-partition: warp (q, half) drains the 32-column chunks c with (c & 1) == half
     const int q = warp & 3;  // TMEM sub-partition this warp may read
+    const int half = (warp - 2) >> 2;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int t = worker; t < total_tiles; t += nworkers) {
@@ -402,6 +404,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
 #pragma unroll 1
       for (int c = 0; c < BN / 32; ++c) {
         if (n_base + c * 32 >= n_limit) break;
+        if ((c & 1) != half) continue;
         uint32_t r[32];
         if (kb_end > kb_begin) {
           tmem_ld_32x32(t_addr + static_cast<uint32_t>(c * 32), r);
@@ -457,7 +460,7 @@ static int launch_gemm(b200_ctx* ctx, const CUtensorMap& a0, const CUtensorMap& 
   if (total < workers) workers = total;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(workers * CG, 1, 1);
-  cfg.blockDim = dim3(192, 1, 1);
+  cfg.blockDim = dim3(320, 1, 1);
   cfg.dynamicSmemBytes = C::SMEM_BYTES;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];

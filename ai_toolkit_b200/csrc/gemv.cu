@@ -80,8 +80,9 @@ __global__ void __launch_bounds__(256) lora_gemv_fwd_kernel(const bf16* __restri
   }
 }
 
-// blocks [0, nb_db): dBw[n, j] += sum_b dy[b,n] z[b,j]        (thread per (n, j))
-// blocks [nb_db, ..): t[b, j]   = c * sum_n dy[b,n] Bw[n,j]    (warp per (b, j))
+// blocks [0, nb_db): dBw[n, j] += sum_b dy[b,n] z[b,j]                 (thread per (n, j))
+// blocks [nb_db, ..): t[b, j]   += c * sum_{n in 256-row slab} dy[b,n] Bw[n,j]   (thread (sub, j): j fastest, so the
+//                     reads of Bw rows are coalesced; fp32 atomics into t, which the caller zeroed)
 __global__ void __launch_bounds__(256) lora_gemv_bwd1_kernel(const float* __restrict__ dy, int lddy, const float* __restrict__ z,
                                                              const float* __restrict__ Bw, float c, float* __restrict__ dBw,
                                                              float* __restrict__ t, int Bm, int r, int N, int nb_db) {
@@ -93,14 +94,23 @@ __global__ void __launch_bounds__(256) lora_gemv_bwd1_kernel(const float* __rest
     for (int b = 0; b < Bm; ++b) acc += dy[static_cast<size_t>(b) * lddy + n] * z[b * r + j];
     dBw[idx] += acc;
   } else {
-    const int w = (blockIdx.x - nb_db) * 8 + (threadIdx.x >> 5);
-    const int lane = threadIdx.x & 31;
-    if (w >= Bm * r) return;
-    const int b = w / r, j = w % r;
-    float acc = 0.f;
-    for (int n = lane; n < N; n += 32) acc += dy[static_cast<size_t>(b) * lddy + n] * Bw[static_cast<size_t>(n) * r + j];
-    acc = warp_sum(acc);
-    if (lane == 0) t[b * r + j] = c * acc;
+    const int groups = 256 / r;
+    const int j = threadIdx.x % r, sub = threadIdx.x / r;
+    if (sub >= groups) return;
+    const int n0 = (blockIdx.x - nb_db) * 256;
+    const int n1 = min(n0 + 256, N);
+    float acc[kMaxRows];
+#pragma unroll
+    for (int b = 0; b < kMaxRows; ++b) acc[b] = 0.f;
+    for (int n = n0 + sub; n < n1; n += groups) {
+      const float w = Bw[static_cast<size_t>(n) * r + j];
+#pragma unroll
+      for (int b = 0; b < kMaxRows; ++b)
+        if (b < Bm) acc[b] += dy[static_cast<size_t>(b) * lddy + n] * w;
+    }
+#pragma unroll
+    for (int b = 0; b < kMaxRows; ++b)
+      if (b < Bm) atomicAdd(t + b * r + j, c * acc[b]);
   }
 }
 
@@ -163,7 +173,8 @@ extern "C" int b200_lora_gemv_bwd(b200_ctx* ctx, const void* dy, int lddy, const
   B200_REQUIRE(Bm >= 1 && Bm <= kMaxRows && r >= 1 && r <= kMaxRank && N > 0 && K > 0, "b200_lora_gemv_bwd: bad shape");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const int nb_db = static_cast<int>((static_cast<long long>(N) * r + 255) / 256);
-  const int nb_t = (Bm * r + 7) / 8;
+  const int nb_t = (N + 255) / 256;
+  B200_CUDA_CHECK(cudaMemsetAsync(t_ws, 0, sizeof(float) * Bm * r, st));
   lora_gemv_bwd1_kernel<<<nb_db + nb_t, 256, 0, st>>>((const float*)dy, lddy, (const float*)z, (const float*)Bw, c,
                                                       (float*)dBw, (float*)t_ws, Bm, r, N, nb_db);
   B200_CUDA_CHECK(cudaGetLastError());
