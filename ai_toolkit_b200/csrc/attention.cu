@@ -36,6 +36,14 @@ __device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t (&r
       "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
       : "memory");
 }
+__device__ __forceinline__ void tmem_st_32x16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+      "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
 // 16-byte store of 8 bf16 into a [rows x 128 B] SWIZZLE_128B tile (row r, 16-byte chunk c of 8)
 __device__ __forceinline__ void st_sw128(uint8_t* tile, int r, int c, uint4 v) {
   *reinterpret_cast<uint4*>(tile + r * 128 + ((c ^ (r & 7)) << 4)) = v;
@@ -57,7 +65,7 @@ struct AttnFwdArgs {
   float scale;
 };
 
-constexpr int kFwdSmem = 1024 + 32768 + 2 * 32768 + 2 * 32768 + 32768 + 16 * 8 + 16 + 2 * 2 * 128 * 4;
+constexpr int kFwdSmem = 1024 + 32768 + 2 * 32768 + 2 * 32768 + 16 * 8 + 16 + 2 * 2 * 128 * 4;
 constexpr int kAttnThreads = 320;  // TMA warp, MMA warp, 8 softmax warps (two per TMEM sub-partition)
 
 __global__ void __launch_bounds__(kAttnThreads, 1)
@@ -68,8 +76,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   uint8_t* sQ = smem;
   uint8_t* sK = sQ + 32768;
   uint8_t* sV = sK + 2 * 32768;
-  uint8_t* sP = sV + 2 * 32768;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 32768);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + 2 * 32768);
   uint64_t* q_full = bars;
   uint64_t* k_full = bars + 1;
   uint64_t* k_empty = bars + 3;
@@ -117,6 +124,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
   const uint32_t tS[2] = {tmem_base, tmem_base + 128u};
   const uint32_t tO = tmem_base + 256u;
+  const uint32_t tP[2] = {tmem_base + 384u, tmem_base + 448u};  // bf16 P, two K elements per 32-bit column
 
   if (warp == 0) {
     if (lane == 0) {
@@ -169,10 +177,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         tc_fence_after();
 #pragma unroll
         for (int kk = 0; kk < 8; ++kk) {
-          const uint64_t da = umma_desc_sw128(smem_u32(sP + (kk >> 2) * 16384), 1024, 16) + 2u * (kk & 3);
           const uint64_t db =
               umma_desc_sw128(smem_u32(sV + s * 32768 + (kk >> 2) * 8192 + (kk & 3) * 2048), 1024, 16384);
-          umma_bf16_ss(tO, da, db, idPV, (j > 0 || kk > 0) ? 1u : 0u);
+          umma_bf16_ts(tO, tP[s] + kk * 8, db, idPV, (j > 0 || kk > 0) ? 1u : 0u);  // A = P straight from TMEM
         }
         umma_commit(&v_empty[s]);
         umma_commit(pv_done);
@@ -251,25 +258,17 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           tmem_st_wait();
         }
       }
-      // P = exp2(S c - m_used) -> bf16 -> swizzled smem block h ([128 rows x 64 kv] K-major)
-      uint8_t* blk = sP + h * 16384;
+      // P = exp2(S c - m_used) -> bf16 pairs -> TMEM (the A operand of the P V MMA; no shared-memory round trip)
+      uint32_t pk[32];
 #pragma unroll
-      for (int k8 = 0; k8 < 8; ++k8) {
-        float p[8];
-#pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          p[e] = ex2(x[k8 * 8 + e] - m_used);
-          l_sum += p[e];
-        }
-        uint4 u;
-        u.x = pack_bf16x2(p[0], p[1]);
-        u.y = pack_bf16x2(p[2], p[3]);
-        u.z = pack_bf16x2(p[4], p[5]);
-        u.w = pack_bf16x2(p[6], p[7]);
-        st_sw128(blk, r, k8, u);
+      for (int k2 = 0; k2 < 32; ++k2) {
+        const float pa = ex2(x[2 * k2] - m_used), pb = ex2(x[2 * k2 + 1] - m_used);
+        l_sum += pa + pb;
+        pk[k2] = pack_bf16x2(pa, pb);
       }
+      tmem_st_32x32(tP[s] + lane_off + h * 32, pk);
+      tmem_st_wait();
       tc_fence_before();
-      fence_proxy_async_smem();
       mbar_arrive(p_full);
     }
     // combine the two half-row sums
@@ -357,7 +356,7 @@ struct AttnBwdArgs {
 };
 
 constexpr int kBwdStages = 3;
-constexpr int kBwdSmem = 1024 + 2 * 32768 + kBwdStages * 32768 + 2 * 16384 + 16 * 8 + 16 + 8 * 64 * 4;
+constexpr int kBwdSmem = 1024 + 2 * 32768 + kBwdStages * 32768 + 16 * 8 + 16 + 8 * 64 * 4;
 
 // MODE_KV = 1: stationary (R0, R1) = (K_j, V_j), streamed (T0, T1) = (Q_i, dO_i); outputs dV (acc0), dK (acc1)
 // MODE_KV = 0: stationary (R0, R1) = (Q_i, dO_i), streamed (T0, T1) = (K_j, V_j); output  dQ (acc0)
@@ -370,16 +369,14 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmR0, const __grid_constant_
   uint8_t* sR0 = smem;
   uint8_t* sR1 = sR0 + 32768;
   uint8_t* sT = sR1 + 32768;  // stage st: T0 at sT + st*32768, T1 at +16384
-  uint8_t* sPB0 = sT + kBwdStages * 32768;
-  uint8_t* sPB1 = sPB0 + 16384;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sPB1 + 16384);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sT + kBwdStages * 32768);
   uint64_t* r_full = bars;
   uint64_t* t_full = bars + 1;
   uint64_t* t_empty = bars + 4;
   uint64_t* x_full = bars + 7;
   uint64_t* x_empty = bars + 9;
   uint64_t* pb_full = bars + 11;
-  uint64_t* pb_empty = bars + 12;
+  uint64_t* done_bar = bars + 12;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
   float* colws = reinterpret_cast<float*>(bars + 14);  // per softmax warp: 32 x (lse2, delta*scale) of its columns
 
@@ -407,7 +404,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmR0, const __grid_constant_
         mbar_init(&x_empty[s], 256);
       }
       mbar_init(pb_full, 256);
-      mbar_init(pb_empty, 1);
+      mbar_init(done_bar, 1);
       fence_barrier_init();
     }
     __syncwarp();
@@ -451,9 +448,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmR0, const __grid_constant_
         const int st = i % kBwdStages;
         const uint32_t ph = (i / kBwdStages) & 1;
         const int xb = i & 1;
-        const uint32_t xph = (i >> 1) & 1;
         mbar_wait(&t_full[st], ph, 22);
-        mbar_wait(&x_empty[xb], xph ^ 1u, 23);
+        // X[xb] was last read by B(i-2) (P / dS alias it); MMAs of one thread execute in issue order, so no barrier
         tc_fence_after();
         const uint8_t* t0 = sT + st * 32768;
         const uint8_t* t1 = t0 + 16384;
@@ -478,35 +474,34 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmR0, const __grid_constant_
         const uint8_t* t0 = sT + st * 32768;
         const uint8_t* t1 = t0 + 16384;
         const uint32_t acc = i > 0 ? 1u : 0u;
+        const int xb = i & 1;
+        // A operands come from TMEM: thread (r, h) stored its 32 bf16 columns as 16 packed columns at X + 32 h
         if (MODE_KV) {
 #pragma unroll
           for (int kk = 0; kk < 4; ++kk) {  // dV += P^T dO_i
-            const uint64_t da = umma_desc_sw128(smem_u32(sPB0), 1024, 16) + 2u * kk;
             const uint64_t db = umma_desc_sw128(smem_u32(t1 + kk * 2048), 1024, 8192);
-            umma_bf16_ss(tA0, da, db, idB, (kk > 0) ? 1u : acc);
+            umma_bf16_ts(tA0, tX0[xb] + (kk >> 1) * 32 + (kk & 1) * 8, db, idB, (kk > 0) ? 1u : acc);
           }
 #pragma unroll
           for (int kk = 0; kk < 4; ++kk) {  // dK += dS^T Q_i
-            const uint64_t da = umma_desc_sw128(smem_u32(sPB1), 1024, 16) + 2u * kk;
             const uint64_t db = umma_desc_sw128(smem_u32(t0 + kk * 2048), 1024, 8192);
-            umma_bf16_ss(tA1, da, db, idB, (kk > 0) ? 1u : acc);
+            umma_bf16_ts(tA1, tX1[xb] + (kk >> 1) * 32 + (kk & 1) * 8, db, idB, (kk > 0) ? 1u : acc);
           }
         } else {
 #pragma unroll
           for (int kk = 0; kk < 4; ++kk) {  // dQ += dS K_j
-            const uint64_t da = umma_desc_sw128(smem_u32(sPB1), 1024, 16) + 2u * kk;
             const uint64_t db = umma_desc_sw128(smem_u32(t0 + kk * 2048), 1024, 8192);
-            umma_bf16_ss(tA0, da, db, idB, (kk > 0) ? 1u : acc);
+            umma_bf16_ts(tA0, tX1[xb] + (kk >> 1) * 32 + (kk & 1) * 8, db, idB, (kk > 0) ? 1u : acc);
           }
         }
         umma_commit(&t_empty[st]);
-        umma_commit(pb_empty);
       };
       issue_A(0);
       for (int i = 0; i < n_t; ++i) {
         if (i + 1 < n_t) issue_A(i + 1);
         issue_B(i);
       }
+      umma_commit(done_bar);
     }
   } else {
     // two threads per row: thread (r, h) owns columns [32 h, 32 h + 32) of each 64-column S / dP tile
@@ -541,8 +536,6 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmR0, const __grid_constant_
       tmem_ld_32x32(tX0[xb] + lane_off + h * 32, sv);
       tmem_ld_32x32(tX1[xb] + lane_off + h * 32, dv);
       tmem_ld_wait();
-      tc_fence_before();
-      mbar_arrive(&x_empty[xb]);
       const int nvalid = g.L - c0;
       uint32_t pp[16], dd[16];  // packed bf16 pairs of my 32 columns: P and dS
 #pragma unroll
@@ -571,16 +564,14 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmR0, const __grid_constant_
         dd[k / 2] = pack_bf16x2(s4[0], s4[1]);
         dd[k / 2 + 1] = pack_bf16x2(s4[2], s4[3]);
       }
-      if (i > 0) mbar_wait(pb_empty, (i - 1) & 1, 26);
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        if (MODE_KV) st_sw128(sPB0, r, h * 4 + c, make_uint4(pp[c * 4], pp[c * 4 + 1], pp[c * 4 + 2], pp[c * 4 + 3]));
-        st_sw128(sPB1, r, h * 4 + c, make_uint4(dd[c * 4], dd[c * 4 + 1], dd[c * 4 + 2], dd[c * 4 + 3]));
-      }
-      fence_proxy_async_smem();
+      // bf16 pairs back into TMEM, over the columns this thread just read (S -> P, dP -> dS)
+      if (MODE_KV) tmem_st_32x16(tX0[xb] + lane_off + h * 32, pp);
+      tmem_st_32x16(tX1[xb] + lane_off + h * 32, dd);
+      tmem_st_wait();
+      tc_fence_before();
       mbar_arrive(pb_full);
     }
-    mbar_wait(pb_empty, (n_t - 1) & 1, 27);
+    mbar_wait(done_bar, 0, 27);
     tc_fence_after();
 #pragma unroll 1
     for (int which = 0; which < (MODE_KV ? 2 : 1); ++which) {
