@@ -89,7 +89,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 15);
   float* xch = reinterpret_cast<float*>(bars + 16);  // [2 parity][2 halves][128 rows] row-max / row-sum exchange
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = warp_id_uniform(), lane = threadIdx.x & 31;
   const int bh = blockIdx.y;
   const int q0 = blockIdx.x * 128;
   const int n_kv = (g.L + 127) / 128;
@@ -150,24 +150,28 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {  // all 32 lanes run the control flow (converged); one elected lane issues each tcgen05 instruction
       constexpr uint32_t idS = umma_idesc_bf16(128, 128, 0, 0);
       constexpr uint32_t idPV = umma_idesc_bf16(128, 128, 0, 1);
       mbar_wait(q_full, 0, 12);
+      // descriptors: one base per operand buffer, compile-time offsets per k-step (address field is (addr >> 4))
+      const uint64_t dQ0 = umma_desc_sw128(smem_u32(sQ), 1024, 16);
+      const uint64_t dK0 = umma_desc_sw128(smem_u32(sK), 1024, 16);
+      const uint64_t dV0 = umma_desc_sw128(smem_u32(sV), 1024, 16384);
       auto issue_S = [&](int j) {
         const int s = j & 1;
         const uint32_t ph = (j >> 1) & 1;
         mbar_wait(&k_full[s], ph, 13);
         mbar_wait(&s_empty[s], ph ^ 1u, 14);
         tc_fence_after();
+        const uint64_t dk = dK0 + static_cast<uint64_t>(s * (32768 >> 4));
 #pragma unroll
         for (int kk = 0; kk < 8; ++kk) {
-          const uint64_t da = umma_desc_sw128(smem_u32(sQ + (kk >> 2) * 16384), 1024, 16) + 2u * (kk & 3);
-          const uint64_t db = umma_desc_sw128(smem_u32(sK + s * 32768 + (kk >> 2) * 16384), 1024, 16) + 2u * (kk & 3);
-          umma_bf16_ss(tS[s], da, db, idS, kk > 0 ? 1u : 0u);
+          const uint32_t off = (kk >> 2) * (16384 >> 4) + 2u * (kk & 3);
+          umma_bf16_ss_w(tS[s], dQ0 + off, dk + off, idS, kk > 0 ? 1u : 0u);
         }
-        umma_commit(&k_empty[s]);
-        umma_commit(&s_full[s]);
+        umma_commit_w(&k_empty[s]);
+        umma_commit_w(&s_full[s]);
       };
       auto issue_PV = [&](int j) {
         const int s = j & 1;
@@ -175,14 +179,14 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         mbar_wait(&v_full[s], ph, 15);
         mbar_wait(p_full, j & 1, 16);
         tc_fence_after();
+        const uint64_t dv = dV0 + static_cast<uint64_t>(s * (32768 >> 4));
 #pragma unroll
         for (int kk = 0; kk < 8; ++kk) {
-          const uint64_t db =
-              umma_desc_sw128(smem_u32(sV + s * 32768 + (kk >> 2) * 8192 + (kk & 3) * 2048), 1024, 16384);
-          umma_bf16_ts(tO, tP[s] + kk * 8, db, idPV, (j > 0 || kk > 0) ? 1u : 0u);  // A = P straight from TMEM
+          const uint32_t off = (kk >> 2) * (8192 >> 4) + (kk & 3) * (2048 >> 4);
+          umma_bf16_ts_w(tO, tP[s] + kk * 8, dv + off, idPV, (j > 0 || kk > 0) ? 1u : 0u);  // A = P straight from TMEM
         }
-        umma_commit(&v_empty[s]);
-        umma_commit(pv_done);
+        umma_commit_w(&v_empty[s]);
+        umma_commit_w(pv_done);
       };
       issue_S(0);
       for (int j = 0; j < n_kv; ++j) {
@@ -380,7 +384,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmR0, const __grid_constant_
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
   float* colws = reinterpret_cast<float*>(bars + 14);  // per softmax warp: 32 x (lse2, delta*scale) of its columns
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = warp_id_uniform(), lane = threadIdx.x & 31;
   const int bh = blockIdx.y;
   const int r0 = blockIdx.x * 128;
   const int n_t = (g.L + 63) / 64;
@@ -440,10 +444,14 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmR0, const __grid_constant_
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {  // converged MMA warp, elected issue (see common.cuh)
       constexpr uint32_t idA = umma_idesc_bf16(128, 64, 0, 0);
       constexpr uint32_t idB = umma_idesc_bf16(128, 128, 0, 1);
       mbar_wait(r_full, 0, 21);
+      const uint64_t dR0 = umma_desc_sw128(smem_u32(sR0), 1024, 16);
+      const uint64_t dR1 = umma_desc_sw128(smem_u32(sR1), 1024, 16);
+      const uint64_t dTk = umma_desc_sw128(smem_u32(sT), 1024, 16);     // streamed tiles read K-major (phase A)
+      const uint64_t dTm = umma_desc_sw128(smem_u32(sT), 1024, 8192);   // the same bytes read MN-major (phase B)
       auto issue_A = [&](int i) {
         const int st = i % kBwdStages;
         const uint32_t ph = (i / kBwdStages) & 1;
@@ -451,57 +459,51 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmR0, const __grid_constant_
         mbar_wait(&t_full[st], ph, 22);
         // X[xb] was last read by B(i-2) (P / dS alias it); MMAs of one thread execute in issue order, so no barrier
         tc_fence_after();
-        const uint8_t* t0 = sT + st * 32768;
-        const uint8_t* t1 = t0 + 16384;
+        const uint64_t d0 = dTk + static_cast<uint64_t>(st * (32768 >> 4));
+        const uint64_t d1 = d0 + (16384 >> 4);
 #pragma unroll
         for (int kk = 0; kk < 8; ++kk) {
-          const uint64_t da = umma_desc_sw128(smem_u32(sR0 + (kk >> 2) * 16384), 1024, 16) + 2u * (kk & 3);
-          const uint64_t db = umma_desc_sw128(smem_u32(t0 + (kk >> 2) * 8192), 1024, 16) + 2u * (kk & 3);
-          umma_bf16_ss(tX0[xb], da, db, idA, kk > 0 ? 1u : 0u);
+          const uint32_t offa = (kk >> 2) * (16384 >> 4) + 2u * (kk & 3);
+          const uint32_t offb = (kk >> 2) * (8192 >> 4) + 2u * (kk & 3);
+          umma_bf16_ss_w(tX0[xb], dR0 + offa, d0 + offb, idA, kk > 0 ? 1u : 0u);
         }
 #pragma unroll
         for (int kk = 0; kk < 8; ++kk) {
-          const uint64_t da = umma_desc_sw128(smem_u32(sR1 + (kk >> 2) * 16384), 1024, 16) + 2u * (kk & 3);
-          const uint64_t db = umma_desc_sw128(smem_u32(t1 + (kk >> 2) * 8192), 1024, 16) + 2u * (kk & 3);
-          umma_bf16_ss(tX1[xb], da, db, idA, kk > 0 ? 1u : 0u);
+          const uint32_t offa = (kk >> 2) * (16384 >> 4) + 2u * (kk & 3);
+          const uint32_t offb = (kk >> 2) * (8192 >> 4) + 2u * (kk & 3);
+          umma_bf16_ss_w(tX1[xb], dR1 + offa, d1 + offb, idA, kk > 0 ? 1u : 0u);
         }
-        umma_commit(&x_full[xb]);
+        umma_commit_w(&x_full[xb]);
       };
       auto issue_B = [&](int i) {
         const int st = i % kBwdStages;
         mbar_wait(pb_full, i & 1, 24);
         tc_fence_after();
-        const uint8_t* t0 = sT + st * 32768;
-        const uint8_t* t1 = t0 + 16384;
+        const uint64_t m0 = dTm + static_cast<uint64_t>(st * (32768 >> 4));  // T0 tile, MN-major view
+        const uint64_t m1 = m0 + (16384 >> 4);                                // T1 tile
         const uint32_t acc = i > 0 ? 1u : 0u;
         const int xb = i & 1;
         // A operands come from TMEM: thread (r, h) stored its 32 bf16 columns as 16 packed columns at X + 32 h
         if (MODE_KV) {
 #pragma unroll
-          for (int kk = 0; kk < 4; ++kk) {  // dV += P^T dO_i
-            const uint64_t db = umma_desc_sw128(smem_u32(t1 + kk * 2048), 1024, 8192);
-            umma_bf16_ts(tA0, tX0[xb] + (kk >> 1) * 32 + (kk & 1) * 8, db, idB, (kk > 0) ? 1u : acc);
-          }
+          for (int kk = 0; kk < 4; ++kk)  // dV += P^T dO_i
+            umma_bf16_ts_w(tA0, tX0[xb] + (kk >> 1) * 32 + (kk & 1) * 8, m1 + kk * (2048 >> 4), idB, (kk > 0) ? 1u : acc);
 #pragma unroll
-          for (int kk = 0; kk < 4; ++kk) {  // dK += dS^T Q_i
-            const uint64_t db = umma_desc_sw128(smem_u32(t0 + kk * 2048), 1024, 8192);
-            umma_bf16_ts(tA1, tX1[xb] + (kk >> 1) * 32 + (kk & 1) * 8, db, idB, (kk > 0) ? 1u : acc);
-          }
+          for (int kk = 0; kk < 4; ++kk)  // dK += dS^T Q_i
+            umma_bf16_ts_w(tA1, tX1[xb] + (kk >> 1) * 32 + (kk & 1) * 8, m0 + kk * (2048 >> 4), idB, (kk > 0) ? 1u : acc);
         } else {
 #pragma unroll
-          for (int kk = 0; kk < 4; ++kk) {  // dQ += dS K_j
-            const uint64_t db = umma_desc_sw128(smem_u32(t0 + kk * 2048), 1024, 8192);
-            umma_bf16_ts(tA0, tX1[xb] + (kk >> 1) * 32 + (kk & 1) * 8, db, idB, (kk > 0) ? 1u : acc);
-          }
+          for (int kk = 0; kk < 4; ++kk)  // dQ += dS K_j
+            umma_bf16_ts_w(tA0, tX1[xb] + (kk >> 1) * 32 + (kk & 1) * 8, m0 + kk * (2048 >> 4), idB, (kk > 0) ? 1u : acc);
         }
-        umma_commit(&t_empty[st]);
+        umma_commit_w(&t_empty[st]);
       };
       issue_A(0);
       for (int i = 0; i < n_t; ++i) {
         if (i + 1 < n_t) issue_A(i + 1);
         issue_B(i);
       }
-      umma_commit(done_bar);
+      umma_commit_w(done_bar);
     }
   } else {
     // two threads per row: thread (r, h) owns columns [32 h, 32 h + 32) of each 64-column S / dP tile

@@ -73,6 +73,28 @@ __device__ __forceinline__ void umma_bf16_ss_cg2(uint32_t tmem_d, uint64_t desc_
       "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// warp-converged variants (all 32 lanes execute, one elected lane issues; see common.cuh)
+__device__ __forceinline__ void umma_bf16_ss_cg2_w(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                                   uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, e;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "@e tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_cg2_mc_w(uint64_t* bar) {
+  const uint16_t mask = 3;
+  asm volatile(
+      "{\n\t.reg .pred e;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "@e tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n\t}" ::
+          "r"(smem_u32(bar)),
+      "h"(mask)
+      : "memory");
+}
 __device__ __forceinline__ void umma_commit_cg2_mc(uint64_t* bar) {
   const uint16_t mask = 3;
   asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::
@@ -222,10 +244,13 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
   uint64_t* tempty = tfull + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = warp_id_uniform();
   const int lane = threadIdx.x & 31;
   uint32_t cta_rank = 0;
-  if (CG == 2) asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(cta_rank));
+  if (CG == 2) {
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(cta_rank));
+    cta_rank = __shfl_sync(0xffffffffu, cta_rank, 0);  // provably warp-uniform for the compiler
+  }
   const bool leader = (cta_rank == 0);
 
   if (warp == 0 && lane == 0) {
@@ -331,8 +356,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer (one thread)
-    if (leader && lane == 0) {
+    // ------------------------------------------------------------------ MMA issuer (converged warp, one elected lane)
+    if (leader) {
       constexpr uint32_t idesc = umma_idesc_bf16(C::BM * CG, BN, A_MN, B_MN);
       // k-step of 16: +32 B inside the swizzle row (K-major) or +16 rows * 128 B (MN-major), in 16-byte units
       constexpr uint32_t a_kstep = A_MN ? 128u : 2u;
@@ -360,23 +385,23 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
           for (int k = 0; k < C::BK / 16; ++k) {
             const uint32_t accum = (kb > kb_begin || k > 0) ? 1u : 0u;
             if (CG == 2)
-              umma_bf16_ss_cg2(d_tmem, da + a_kstep * k, db + b_kstep * k, idesc, accum);
+              umma_bf16_ss_cg2_w(d_tmem, da + a_kstep * k, db + b_kstep * k, idesc, accum);
             else
-              umma_bf16_ss(d_tmem, da + a_kstep * k, db + b_kstep * k, idesc, accum);
+              umma_bf16_ss_w(d_tmem, da + a_kstep * k, db + b_kstep * k, idesc, accum);
           }
           if (CG == 2)
-            umma_commit_cg2_mc(&empty[stage]);
+            umma_commit_cg2_mc_w(&empty[stage]);
           else
-            umma_commit(&empty[stage]);
+            umma_commit_w(&empty[stage]);
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1u;
           }
         }
         if (CG == 2)
-          umma_commit_cg2_mc(&tfull[acc]);
+          umma_commit_cg2_mc_w(&tfull[acc]);
         else
-          umma_commit(&tfull[acc]);
+          umma_commit_w(&tfull[acc]);
         if (++acc == 2) {
           acc = 0;
           acc_phase ^= 1u;
@@ -519,6 +544,10 @@ extern "C" int b200_gemm_bf16(b200_ctx* ctx, const b200_gemm_desc* d, void* stre
         def = (e && e[0] == '1') ? B200_GEMM_1CTA_N256 : B200_GEMM_2CTA_N256;
       }
       config = def;
+      // few rows (the 512-token text stream): 256 x 256 pair tiles would leave most SMs idle; 128 x 128 tiles give
+      // 4x the CTAs at the cost of operand re-reads that L2 absorbs
+      const long long pair_tiles = static_cast<long long>((d->M + 255) / 256) * ((d->N + 255) / 256);
+      if (pair_tiles * 2 < ctx->sm_count) config = B200_GEMM_1CTA_N128;
     }
   }
 
