@@ -434,7 +434,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmR0, const __grid_constant_
         const int st = i % kBwdStages;
         const uint32_t ph = (i / kBwdStages) & 1;
         const int trow = static_cast<int>(row_base + i * 64);
-        mbar_wait(&t_empty[st], ph ^ 1u, 20);
+        mbar_wait(&t_empty[st], ph ^ 1u, 20000 + i);
         mbar_arrive_expect_tx(&t_full[st], 32768);
         uint8_t* d = sT + st * 32768;
         tma_load_2d(d, &tmT0, &t_full[st], 0, trow);
@@ -456,7 +456,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmR0, const __grid_constant_
         const int st = i % kBwdStages;
         const uint32_t ph = (i / kBwdStages) & 1;
         const int xb = i & 1;
-        mbar_wait(&t_full[st], ph, 22);
+        mbar_wait(&t_full[st], ph, 22000 + i);
         // X[xb] was last read by B(i-2) (P / dS alias it); MMAs of one thread execute in issue order, so no barrier
         tc_fence_after();
         const uint64_t d0 = dTk + static_cast<uint64_t>(st * (32768 >> 4));
@@ -477,7 +477,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmR0, const __grid_constant_
       };
       auto issue_B = [&](int i) {
         const int st = i % kBwdStages;
-        mbar_wait(pb_full, i & 1, 24);
+        mbar_wait(pb_full, i & 1, 24000 + i + 100000 * MODE_KV);
         tc_fence_after();
         const uint64_t m0 = dTm + static_cast<uint64_t>(st * (32768 >> 4));  // T0 tile, MN-major view
         const uint64_t m1 = m0 + (16384 >> 4);                                // T1 tile
@@ -532,7 +532,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmR0, const __grid_constant_
         myws[32 + lane] = cq < g.L ? delta_bh[cq] * g.scale : 0.f;
         __syncwarp();
       }
-      mbar_wait(&x_full[xb], xph, 25);
+      mbar_wait(&x_full[xb], xph, 25000 + i + 100000 * MODE_KV);
       tc_fence_after();
       uint32_t sv[32], dv[32];
       tmem_ld_32x32(tX0[xb] + lane_off + h * 32, sv);
@@ -566,6 +566,10 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmR0, const __grid_constant_
         dd[k / 2] = pack_bf16x2(s4[0], s4[1]);
         dd[k / 2 + 1] = pack_bf16x2(s4[2], s4[3]);
       }
+      // No warp may run a whole tile ahead of its peers: its arrival for tile i would be counted in phase i-1 of
+      // pb_full and release B(i-1) before a slower warp has stored its operands.  (Also orders this store after the
+      // completion of phase i-1, i.e. after every peer has finished reading tile i-1.)
+      if (i > 0) mbar_wait(pb_full, (i - 1) & 1, 26000 + i);
       // bf16 pairs back into TMEM, over the columns this thread just read (S -> P, dP -> dS)
       if (MODE_KV) tmem_st_32x16(tX0[xb] + lane_off + h * 32, pp);
       tmem_st_32x16(tX1[xb] + lane_off + h * 32, dd);
