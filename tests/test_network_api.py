@@ -1,0 +1,140 @@
+"""Host-side mirror of the reference's network API (no GPU): names, state dict, peft save format, load with
+rank expand / shrink, merge_in / merge_out, multiplier / is_active semantics, optimizer param groups, and the
+'no CPU fallback' rule for an active network."""
+import os
+
+import pytest
+import torch
+
+from ai_toolkit_b200 import LoRASpecialNetwork, cabi, get_network
+from ai_toolkit_b200.flux import FluxConfig, FluxTransformer2DModel
+from oracle import ref_import
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden", "lora_tiny.pt")
+CFG = dict(num_layers=1, num_single_layers=1, num_attention_heads=2, joint_attention_dim=64, pooled_projection_dim=32)
+
+
+def _net(rank=4, **kw):
+    model = FluxTransformer2DModel(FluxConfig(**CFG), dtype=torch.float32)
+    net = LoRASpecialNetwork(text_encoder=None, unet=model, lora_dim=rank, alpha=rank, train_unet=True, train_text_encoder=False,
+                             is_flux=True, transformer_only=True, **kw)
+    net.force_to("cpu", torch.float32)
+    net._update_torch_multiplier()
+    net.apply_to(None, model, False, True)
+    return model, net
+
+
+def test_names_and_saved_keys_match_reference_golden():
+    gold = torch.load(GOLD, weights_only=False)
+    model, net = _net()
+    assert [l.lora_name for l in net.unet_loras] == gold["lora_names"]
+    assert list(net.state_dict().keys()) == list(gold["init_state_dict"].keys())
+    assert list(net.get_state_dict(dtype=torch.float16).keys()) == gold["saved_keys"]
+    assert len(net.unet_loras) == 14 + 6  # every Linear under transformer_blocks / single_transformer_blocks
+    assert net.peft_format and all(l.scale == 1.0 for l in net.unet_loras)
+
+
+def test_flat_buffers_are_views():
+    model, net = _net()
+    n = sum(p.numel() for p in net.parameters())
+    assert net.n_params == n
+    w = net.unet_loras[3].lora_down.weight
+    w.data.fill_(0.25)
+    assert (net.flat_params == 0.25).sum() == w.numel()
+    assert w.grad.data_ptr() >= net.flat_grads.data_ptr()
+    groups = net.prepare_optimizer_params(None, 1e-4, 1e-4)
+    assert len(groups) == 1 and groups[0]["lr"] == 1e-4 and len(groups[0]["params"]) == 2 * len(net.unet_loras)
+
+
+def test_save_load_roundtrip_and_rank_change(tmp_path):
+    model, net = _net(rank=4)
+    with torch.no_grad():
+        for l in net.unet_loras:
+            l.lora_up.weight.normal_(0, 0.1)
+    f = str(tmp_path / "lora.safetensors")
+    net.save_weights(f, dtype=torch.float32, metadata={"ss_output_name": "t"})
+    from safetensors import safe_open
+
+    with safe_open(f, "pt") as sf:
+        keys = list(sf.keys())
+        meta = sf.metadata()
+    assert all(k.startswith("transformer.") and (".lora_A.weight" in k or ".lora_B.weight" in k) for k in keys)
+    assert "sshs_model_hash" in meta and len(meta["sshs_legacy_hash"]) == 8
+    model2, net2 = _net(rank=4)
+    assert net2.load_weights(f) is None
+    for a, b in zip(net.unet_loras, net2.unet_loras):
+        assert torch.equal(a.lora_up.weight, b.lora_up.weight) and torch.equal(a.lora_down.weight, b.lora_down.weight)
+    assert net2.flat_params.data_ptr() == net2.unet_loras[0].lora_down.weight.data_ptr()  # still views after loading
+    model3, net3 = _net(rank=8)  # expand (network_mixins.py:737-775)
+    net3.load_weights(f)
+    assert net3.did_change_weights
+    a, c = net.unet_loras[2], net3.unet_loras[2]
+    assert torch.equal(c.lora_down.weight[:4], a.lora_down.weight) and c.lora_down.weight[4:].abs().sum() == 0
+    assert torch.equal(c.lora_up.weight[:, :4], a.lora_up.weight) and c.lora_up.weight[:, 4:].abs().sum() == 0
+
+
+def test_merge_in_out_and_multiplier():
+    model, net = _net()
+    lin = model.transformer_blocks[0].attn.to_q
+    w0 = lin.weight.detach().clone()
+    lora = lin._b200_lora()
+    with torch.no_grad():
+        lora.lora_up.weight.normal_(0, 0.1)
+    net.merge_in(0.5)
+    want = w0 + 0.5 * lora.scale * (lora.lora_up.weight @ lora.lora_down.weight)
+    torch.testing.assert_close(lin.weight, want)
+    assert net.is_merged_in and not lora.is_live()
+    net.merge_out(0.5)
+    torch.testing.assert_close(lin.weight, w0, atol=1e-6, rtol=1e-5)
+    net.multiplier = [1.0, -1.0]
+    assert net.torch_multiplier.tolist() == [1.0, -1.0]
+    net.multiplier = 0
+    with net:
+        assert not lora.is_live()
+    net.multiplier = 1.0
+    assert not lora.is_live()  # inactive outside `with network:`
+    x = torch.randn(3, 5, lin.in_features)
+    assert torch.equal(lin(x), torch.nn.functional.linear(x, lin.weight, lin.bias))  # falls through to org_forward
+
+
+def test_active_network_has_no_cpu_fallback():
+    model, net = _net()
+    lin = model.transformer_blocks[0].attn.to_q
+    with net, pytest.raises(cabi.B200Error):
+        lin(torch.randn(4, lin.in_features))
+
+
+def test_get_network_factory_defaults():
+    class NC:
+        linear, linear_alpha, type, transformer_only, conv, conv_alpha, dropout, network_kwargs = 16, 16, "lora", True, None, None, None, {}
+
+    class MC:
+        is_flux = True
+
+    model = FluxTransformer2DModel(FluxConfig(**CFG), dtype=torch.float32)
+    net = get_network(model, network_config=NC(), model_config=MC(), device="cpu")
+    assert net.lora_dim == 16 and len(net.unet_loras) == 20 and net.flat_params is not None
+    with pytest.raises(NotImplementedError):
+        LoRASpecialNetwork(None, model, network_type="dora", is_flux=True)
+
+
+@pytest.mark.skipif(not ref_import.available(), reason="reference tree not present (GPU box)")
+def test_state_dict_identical_to_live_reference():
+    from oracle import flux_ref
+
+    RefNet, _ = ref_import.reference_lora()
+    m1 = flux_ref.FluxTransformer2DModel(flux_ref.FluxConfig(**CFG))
+    m2 = FluxTransformer2DModel(FluxConfig(**CFG), dtype=torch.float32)
+    kw = dict(text_encoder=None, lora_dim=4, alpha=4, train_unet=True, train_text_encoder=False, is_flux=True,
+              network_type="lora", transformer_only=True)
+    torch.manual_seed(1)
+    r = RefNet(unet=m1, **kw)
+    r.force_to("cpu", torch.float32); r._update_torch_multiplier(); r.apply_to(None, m1, False, True)
+    torch.manual_seed(1)
+    n = LoRASpecialNetwork(unet=m2, **kw)
+    n.force_to("cpu", torch.float32); n._update_torch_multiplier(); n.apply_to(None, m2, False, True)
+    sr, sn = r.state_dict(), n.state_dict()
+    assert list(sr.keys()) == list(sn.keys())
+    for k in sr:
+        assert torch.equal(sr[k], sn[k]), k
+    assert list(r.get_state_dict(dtype=torch.float16).keys()) == list(n.get_state_dict(dtype=torch.float16).keys())
