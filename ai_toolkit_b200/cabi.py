@@ -22,6 +22,7 @@ GEMM_1CTA_N256 = 1
 GEMM_2CTA_N256 = 2
 GEMM_1CTA_N128 = 3
 GEMM_1CTA_N64 = 4
+GEMM_SKINNY_CLUSTER = 5
 
 
 class B200Error(RuntimeError):

@@ -502,6 +502,10 @@ static int launch_gemm(b200_ctx* ctx, const CUtensorMap& a0, const CUtensorMap& 
 
 }  // namespace b200
 
+namespace b200 {
+int skinny_gemm_dispatch(b200_ctx* ctx, const b200_gemm_desc* d, cudaStream_t stream);  // skinny_gemm.cu
+}
+
 extern "C" int b200_gemm_bf16(b200_ctx* ctx, const b200_gemm_desc* d, void* stream_v) {
   using namespace b200;
   int rc = check_ctx(ctx);
@@ -532,6 +536,12 @@ extern "C" int b200_gemm_bf16(b200_ctx* ctx, const b200_gemm_desc* d, void* stre
   if (d->f32_mode == 1) B200_REQUIRE(d->ldo % 4 == 0 && !d->f32_trans, "b200_gemm_bf16: f32 partial store needs ldo %% 4");
 
   int config = d->config;
+  const bool plain_bf16 = !f32 && !d->trans_a && d->K1 == 0 && !d->bias && !d->res && !d->gate && !d->aux_in && !d->aux_out &&
+                          d->act == 0 && d->N <= 64;
+  if ((config == B200_GEMM_AUTO && plain_bf16) || config == B200_GEMM_SKINNY_CLUSTER) {
+    B200_REQUIRE(plain_bf16, "b200_gemm_bf16: SKINNY_CLUSTER needs N <= 64, bf16 output, one segment and no fused epilogue");
+    return skinny_gemm_dispatch(ctx, d, stream);
+  }
   if (config == B200_GEMM_AUTO) {
     if (d->N <= 64)
       config = B200_GEMM_1CTA_N64;

@@ -55,7 +55,7 @@ def linear_fwd(lin, x2, out, *, lora=None, zc_out=None, **epi):
         return None
     alpha, row_alpha, rps = lora_coeff(lora, x2.shape[0])
     zc = zc_out if zc_out is not None else torch.empty((x2.shape[0], RANK_PAD), device=x2.device, dtype=torch.bfloat16)
-    gemm_bf16(x2, lora.a_pack, zc, alpha=alpha, row_alpha=row_alpha, rows_per_sample=rps, config=cabi.GEMM_1CTA_N64)
+    gemm_bf16(x2, lora.a_pack, zc, alpha=alpha, row_alpha=row_alpha, rows_per_sample=rps)  # cluster split-K skinny GEMM
     gemm_bf16(x2, W, out, a1=zc, b1=lora.b_pack, bias=lin.bias, **epi)
     return zc
 
@@ -70,8 +70,7 @@ def linear_bwd(lin, dy, x2, zc, dx_out, *, lora=None, n_slices=None, **epi):
     if lora is not None:
         alpha, row_alpha, rps = lora_coeff(lora, dy.shape[0])
         t = torch.empty((dy.shape[0], RANK_PAD), device=dy.device, dtype=torch.bfloat16)
-        gemm_bf16(dy, lora.b_pack, t, trans_b=True, alpha=alpha, row_alpha=row_alpha, rows_per_sample=rps,
-                  config=cabi.GEMM_1CTA_N64)
+        gemm_bf16(dy, lora.b_pack, t, trans_b=True, alpha=alpha, row_alpha=row_alpha, rows_per_sample=rps)
     if dx_out is not None:
         slices = n_slices if n_slices is not None else [(0, W.shape[1], epi)]
         for c0, c1, e in slices:

@@ -39,6 +39,7 @@ extern "C" {
 #define B200_GEMM_2CTA_N256 2 /* 256x256 tile over a CTA pair, cta_group::2     */
 #define B200_GEMM_1CTA_N128 3
 #define B200_GEMM_1CTA_N64 4 /* skinny (rank-side) GEMM, optional split-K       */
+#define B200_GEMM_SKINNY_CLUSTER 5 /* N <= 64, bf16 out: split-K over a CTA cluster, DSMEM reduce */
 
 typedef struct b200_ctx b200_ctx;
 
