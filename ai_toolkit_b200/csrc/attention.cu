@@ -360,7 +360,7 @@ struct AttnBwdArgs {
 };
 
 constexpr int kBwdStages = 3;
-constexpr int kBwdSmem = 1024 + 2 * 32768 + kBwdStages * 32768 + 16 * 8 + 16 + 8 * 64 * 4;
+constexpr int kBwdSmem = 1024 + 2 * 32768 + kBwdStages * 32768 + 16 * 8 + 16 + 8 * 128 * 4;
 
 // MODE_KV = 1: stationary (R0, R1) = (K_j, V_j), streamed (T0, T1) = (Q_i, dO_i); outputs dV (acc0), dK (acc1)
 // MODE_KV = 0: stationary (R0, R1) = (Q_i, dO_i), streamed (T0, T1) = (K_j, V_j); output  dQ (acc0)
@@ -379,10 +379,10 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmR0, const __grid_constant_
   uint64_t* t_empty = bars + 4;
   uint64_t* x_full = bars + 7;
   uint64_t* x_empty = bars + 9;
-  uint64_t* pb_full = bars + 11;
-  uint64_t* done_bar = bars + 12;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
-  float* colws = reinterpret_cast<float*>(bars + 14);  // per softmax warp: 32 x (lse2, delta*scale) of its columns
+  uint64_t* pb_full = bars + 11;  // [2]: one per softmax group / TMEM buffer
+  uint64_t* done_bar = bars + 13;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
+  float* colws = reinterpret_cast<float*>(bars + 16);  // per softmax warp: 32 x (lse2, delta*scale) of its columns
 
   const int warp = warp_id_uniform(), lane = threadIdx.x & 31;
   const int bh = blockIdx.y;
@@ -407,7 +407,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmR0, const __grid_constant_
         mbar_init(&x_full[s], 1);
         mbar_init(&x_empty[s], 256);
       }
-      mbar_init(pb_full, 256);
+      mbar_init(&pb_full[0], 128);
+      mbar_init(&pb_full[1], 128);
       mbar_init(done_bar, 1);
       fence_barrier_init();
     }
@@ -477,24 +478,24 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmR0, const __grid_constant_
       };
       auto issue_B = [&](int i) {
         const int st = i % kBwdStages;
-        mbar_wait(pb_full, i & 1, 24000 + i + 100000 * MODE_KV);
+        mbar_wait(&pb_full[i & 1], (i >> 1) & 1, 24000 + i + 100000 * MODE_KV);
         tc_fence_after();
         const uint64_t m0 = dTm + static_cast<uint64_t>(st * (32768 >> 4));  // T0 tile, MN-major view
         const uint64_t m1 = m0 + (16384 >> 4);                                // T1 tile
         const uint32_t acc = i > 0 ? 1u : 0u;
         const int xb = i & 1;
-        // A operands come from TMEM: thread (r, h) stored its 32 bf16 columns as 16 packed columns at X + 32 h
+        // A operands come from TMEM: each row's 64 bf16 values sit in the first 32 columns of X (two per column)
         if (MODE_KV) {
 #pragma unroll
           for (int kk = 0; kk < 4; ++kk)  // dV += P^T dO_i
-            umma_bf16_ts_w(tA0, tX0[xb] + (kk >> 1) * 32 + (kk & 1) * 8, m1 + kk * (2048 >> 4), idB, (kk > 0) ? 1u : acc);
+            umma_bf16_ts_w(tA0, tX0[xb] + kk * 8, m1 + kk * (2048 >> 4), idB, (kk > 0) ? 1u : acc);
 #pragma unroll
           for (int kk = 0; kk < 4; ++kk)  // dK += dS^T Q_i
-            umma_bf16_ts_w(tA1, tX1[xb] + (kk >> 1) * 32 + (kk & 1) * 8, m0 + kk * (2048 >> 4), idB, (kk > 0) ? 1u : acc);
+            umma_bf16_ts_w(tA1, tX1[xb] + kk * 8, m0 + kk * (2048 >> 4), idB, (kk > 0) ? 1u : acc);
         } else {
 #pragma unroll
           for (int kk = 0; kk < 4; ++kk)  // dQ += dS K_j
-            umma_bf16_ts_w(tA0, tX1[xb] + (kk >> 1) * 32 + (kk & 1) * 8, m0 + kk * (2048 >> 4), idB, (kk > 0) ? 1u : acc);
+            umma_bf16_ts_w(tA0, tX1[xb] + kk * 8, m0 + kk * (2048 >> 4), idB, (kk > 0) ? 1u : acc);
         }
         umma_commit_w(&t_empty[st]);
       };
@@ -506,79 +507,93 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmR0, const __grid_constant_
       umma_commit_w(done_bar);
     }
   } else {
-    // two threads per row: thread (r, h) owns columns [32 h, 32 h + 32) of each 64-column S / dP tile
+    // Two softmax groups of 4 warps: group gq owns the tiles i == gq (mod 2), i.e. always the TMEM buffer X[gq], one
+    // thread per full 64-column row.  Each group has two MMA tile-times to turn S/dP into P/dS, so the tcgen05.ld ->
+    // ex2 -> tcgen05.st latency chain of one group hides behind the other's; a group cannot lap (its next x_full needs
+    // its own previous pb_full).
     const int q = warp & 3;
-    const int h = (warp - 2) >> 2;
+    const int gq = (warp - 2) >> 2;
     const int r = q * 32 + lane;
     const int ri = r0 + r;  // kv index (MODE_KV) or q index
     const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
     const float c2 = g.scale * kLog2e;
     const float* lse_bh = g.lse + row_base;
     const float* delta_bh = g.delta + row_base;
-    float* myws = colws + (warp - 2) * 64;
+    float* myws = colws + (warp - 2) * 128;  // per warp: 64 x lse2, 64 x delta*scale of the tile's columns
     float my_lse2 = 0.f, my_dls = 0.f;
     if (!MODE_KV && ri < g.L) {
       my_lse2 = lse_bh[ri] * kLog2e;
       my_dls = delta_bh[ri] * g.scale;
     }
-    for (int i = 0; i < n_t; ++i) {
-      const int xb = i & 1;
+    // software prefetch of the per-column statistics (MODE_KV): registers for the group's next tile
+    float nl0 = 0.f, nl1 = 0.f, nd0 = 0.f, nd1 = 0.f;
+    auto fetch_cols = [&](int i) {
+      const int c = i * 64 + lane;
+      nl0 = c < g.L ? lse_bh[c] * kLog2e : 0.f;
+      nd0 = c < g.L ? delta_bh[c] * g.scale : 0.f;
+      nl1 = c + 32 < g.L ? lse_bh[c + 32] * kLog2e : 0.f;
+      nd1 = c + 32 < g.L ? delta_bh[c + 32] * g.scale : 0.f;
+    };
+    if (MODE_KV && gq < n_t) fetch_cols(gq);
+    for (int i = gq; i < n_t; i += 2) {
       const uint32_t xph = (i >> 1) & 1;
-      const int c0 = i * 64 + h * 32;  // first streamed index (q for MODE_KV, kv otherwise) of my columns
-      if (MODE_KV) {  // per-column softmax statistics of this tile: coalesced load, broadcast through smem
-        const int cq = c0 + lane;
+      const int c0 = i * 64;  // first streamed index (q for MODE_KV, kv otherwise) of this tile
+      if (MODE_KV) {
         __syncwarp();
-        myws[lane] = cq < g.L ? lse_bh[cq] * kLog2e : 0.f;
-        myws[32 + lane] = cq < g.L ? delta_bh[cq] * g.scale : 0.f;
+        myws[lane] = nl0;
+        myws[32 + lane] = nl1;
+        myws[64 + lane] = nd0;
+        myws[96 + lane] = nd1;
         __syncwarp();
+        if (i + 2 < n_t) fetch_cols(i + 2);
       }
-      mbar_wait(&x_full[xb], xph, 25000 + i + 100000 * MODE_KV);
+      mbar_wait(&x_full[gq], xph, 25000 + i + 100000 * MODE_KV);
       tc_fence_after();
-      uint32_t sv[32], dv[32];
-      tmem_ld_32x32(tX0[xb] + lane_off + h * 32, sv);
-      tmem_ld_32x32(tX1[xb] + lane_off + h * 32, dv);
-      tmem_ld_wait();
       const int nvalid = g.L - c0;
-      uint32_t pp[16], dd[16];  // packed bf16 pairs of my 32 columns: P and dS
+      uint32_t pp[32], dd[32];  // packed bf16 pairs of the 64 columns: P and dS
 #pragma unroll
-      for (int k = 0; k < 32; k += 4) {
-        float l4[4], d4[4];
-        if (MODE_KV) {
-          *reinterpret_cast<float4*>(l4) = *reinterpret_cast<const float4*>(myws + k);
-          *reinterpret_cast<float4*>(d4) = *reinterpret_cast<const float4*>(myws + 32 + k);
-        } else {
+      for (int hlf = 0; hlf < 2; ++hlf) {
+        uint32_t sv[32], dv[32];
+        tmem_ld_32x32(tX0[gq] + lane_off + hlf * 32, sv);
+        tmem_ld_32x32(tX1[gq] + lane_off + hlf * 32, dv);
+        tmem_ld_wait();
+#pragma unroll
+        for (int k = 0; k < 32; k += 4) {
+          float l4[4], d4[4];
+          if (MODE_KV) {
+            *reinterpret_cast<float4*>(l4) = *reinterpret_cast<const float4*>(myws + hlf * 32 + k);
+            *reinterpret_cast<float4*>(d4) = *reinterpret_cast<const float4*>(myws + 64 + hlf * 32 + k);
+          } else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              l4[e] = my_lse2;
+              d4[e] = my_dls;
+            }
+          }
+          float p4[4], s4[4];
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
-            l4[e] = my_lse2;
-            d4[e] = my_dls;
+            float p = ex2(__uint_as_float(sv[k + e]) * c2 - l4[e]);
+            if (nvalid < 64) p = (hlf * 32 + k + e < nvalid) ? p : 0.f;  // only the last tile has missing columns
+            p4[e] = p;
+            s4[e] = p * (__uint_as_float(dv[k + e]) * g.scale - d4[e]);
           }
+          pp[hlf * 16 + k / 2] = pack_bf16x2(p4[0], p4[1]);
+          pp[hlf * 16 + k / 2 + 1] = pack_bf16x2(p4[2], p4[3]);
+          dd[hlf * 16 + k / 2] = pack_bf16x2(s4[0], s4[1]);
+          dd[hlf * 16 + k / 2 + 1] = pack_bf16x2(s4[2], s4[3]);
         }
-        float p4[4], s4[4];
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          float p = ex2(__uint_as_float(sv[k + e]) * c2 - l4[e]);
-          if (nvalid < 32) p = (k + e < nvalid) ? p : 0.f;  // only the last tile has missing columns
-          p4[e] = p;
-          s4[e] = p * (__uint_as_float(dv[k + e]) * g.scale - d4[e]);
-        }
-        pp[k / 2] = pack_bf16x2(p4[0], p4[1]);
-        pp[k / 2 + 1] = pack_bf16x2(p4[2], p4[3]);
-        dd[k / 2] = pack_bf16x2(s4[0], s4[1]);
-        dd[k / 2 + 1] = pack_bf16x2(s4[2], s4[3]);
       }
-      // No warp may run a whole tile ahead of its peers: its arrival for tile i would be counted in phase i-1 of
-      // pb_full and release B(i-1) before a slower warp has stored its operands.  (Also orders this store after the
-      // completion of phase i-1, i.e. after every peer has finished reading tile i-1.)
-      if (i > 0) mbar_wait(pb_full, (i - 1) & 1, 26000 + i);
-      // bf16 pairs back into TMEM, over the columns this thread just read (S -> P, dP -> dS)
-      if (MODE_KV) tmem_st_32x16(tX0[xb] + lane_off + h * 32, pp);
-      tmem_st_32x16(tX1[xb] + lane_off + h * 32, dd);
+      // bf16 pairs back into TMEM over the columns this thread just read (S -> P, dP -> dS): 64 values = 32 columns
+      if (MODE_KV) tmem_st_32x32(tX0[gq] + lane_off, pp);
+      tmem_st_32x32(tX1[gq] + lane_off, dd);
       tmem_st_wait();
       tc_fence_before();
-      mbar_arrive(pb_full);
+      mbar_arrive(&pb_full[gq]);
     }
     mbar_wait(done_bar, 0, 27);
     tc_fence_after();
+    // epilogue: the 8 warps split the accumulator columns (gq = column half)
 #pragma unroll 1
     for (int which = 0; which < (MODE_KV ? 2 : 1); ++which) {
       const uint32_t ta = which == 0 ? tA0 : tA1;
@@ -586,10 +601,10 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmR0, const __grid_constant_
 #pragma unroll 1
       for (int c = 0; c < 2; ++c) {
         uint32_t v[32];
-        tmem_ld_32x32(ta + lane_off + h * 64 + c * 32, v);
+        tmem_ld_32x32(ta + lane_off + gq * 64 + c * 32, v);
         tmem_ld_wait();
         if (ri < g.L) {
-          bf16* orow = out + (row_base + ri) * 128 + h * 64 + c * 32;
+          bf16* orow = out + (row_base + ri) * 128 + gq * 64 + c * 32;
 #pragma unroll
           for (int k8 = 0; k8 < 4; ++k8) {
             uint4 u;
