@@ -24,7 +24,7 @@ import torch
 
 from . import attention, cabi, ops
 from .cabi import ACT_GELU_TANH, gemm_bf16
-from .linear import linear_bwd, linear_fwd, live_lora, lora_coeff
+from .linear import group_bwd, group_fwd, linear_bwd, linear_fwd, live_lora, lora_coeff
 
 
 def _empty(shape, like, dtype=torch.bfloat16):
@@ -61,6 +61,42 @@ class FluxEngine:
         out = (torch.cat(cos, -1).contiguous(), torch.cat(sin, -1).contiguous())
         self._rope_cache[key] = out
         return out
+
+    def _register_groups(self, net):
+        """q/k/v projections share their input: fuse each triple into one GEMM (weights re-pointed at one matrix)."""
+        m = self.model
+        groups = []
+        for blk in m.transformer_blocks:
+            a = blk.attn
+            groups.append([live_lora(l) for l in (a.to_q, a.to_k, a.to_v)])
+            groups.append([live_lora(l) for l in (a.add_q_proj, a.add_k_proj, a.add_v_proj)])
+        for blk in m.single_transformer_blocks:
+            a = blk.attn
+            groups.append([live_lora(l) for l in (a.to_q, a.to_k, a.to_v)])
+        net.register_fused_groups(groups)
+        self._groups_for = net
+
+    @staticmethod
+    def _qkv_fwd(lins, n, qkv):
+        """Three projections of the same input -> column blocks of `qkv`; fused when the adapters form a group."""
+        loras = [live_lora(l) for l in lins]
+        grp = loras[0].network_ref().fused_group(loras) if loras[0] is not None else None
+        if grp is not None:
+            return ("g", group_fwd(grp, lins, n, qkv))
+        D = lins[0].out_features
+        return ("s", [linear_fwd(lin, n, qkv[:, j * D:(j + 1) * D], lora=lo) for j, (lin, lo) in enumerate(zip(lins, loras))])
+
+    @staticmethod
+    def _qkv_bwd(lins, dqkv, n, saved, dn, accumulate):
+        loras = [live_lora(l) for l in lins]
+        kind, z = saved
+        if kind == "g":
+            grp = loras[0].network_ref().fused_group(loras)
+            group_bwd(grp, lins, dqkv, n, z, dn, **({"res": dn} if accumulate else {}))
+            return
+        D = lins[0].out_features
+        for j, (lin, lo) in enumerate(zip(lins, loras)):
+            linear_bwd(lin, dqkv[:, j * D:(j + 1) * D], n, z[j], dn, lora=lo, **({"res": dn} if (accumulate or j > 0) else {}))
 
     @staticmethod
     def _lin(lin, x, out, **epi):
@@ -106,6 +142,8 @@ class FluxEngine:
         net_mods = [live_lora(m.transformer_blocks[0].attn.to_q)] if len(m.transformer_blocks) else []
         if net_mods and net_mods[0] is not None:
             net = net_mods[0].network_ref()
+            if getattr(self, "_groups_for", None) is not net:
+                self._register_groups(net)
             net.refresh_packs()
             net.ensure_grad_views()
         cos, sin = self.rope_tables(txt_ids, img_ids)
@@ -177,7 +215,7 @@ class FluxEngine:
             mod, zmod, amod = self._mod_fwd(norm.linear, temb_silu)
             n, mean, rstd = ops.ln_modulate_fwd(x, mod[:, 0:D], mod[:, D:2 * D], Ls)
             qkv = _empty((B * Ls, 3 * D), x)
-            zq = [self._lin(lin, n, qkv[:, j * D:(j + 1) * D]) for j, lin in enumerate(qkv_lins)]
+            zq = self._qkv_fwd(qkv_lins, n, qkv)
             streams.append(dict(name=name, x=x, mod=mod, zmod=zmod, amod=amod, n=n, mean=mean, rstd=rstd, qkv=qkv, zq=zq, Ls=Ls))
         si, st = streams
         Q = _empty((B, H, L, 128), img)
@@ -219,7 +257,7 @@ class FluxEngine:
         mod, zmod, amod = self._mod_fwd(blk.norm.linear, temb_silu)
         n, mean, rstd = ops.ln_modulate_fwd(x, mod[:, 0:D], mod[:, D:2 * D], L)
         qkv = _empty((B * L, 3 * D), x)
-        zq = [self._lin(lin, n, qkv[:, j * D:(j + 1) * D]) for j, lin in enumerate((a.to_q, a.to_k, a.to_v))]
+        zq = self._qkv_fwd((a.to_q, a.to_k, a.to_v), n, qkv)
         inner = blk.proj_mlp.out_features
         cat = _empty((B * L, D + inner), x)
         pre = _empty((B * L, inner), x)
@@ -297,8 +335,7 @@ class FluxEngine:
         dqkv = _empty(qkv.shape, qkv)
         ops.qk_norm_rope_bwd(dQ, dK, dV, qkv[:, :D], qkv[:, D:2 * D], a.norm_q.weight, a.norm_k.weight, cos, sin,
                              dqkv[:, :D], dqkv[:, D:2 * D], dqkv[:, 2 * D:], B, L, 0)
-        for j, lin in enumerate((a.to_q, a.to_k, a.to_v)):
-            linear_bwd(lin, dqkv[:, j * D:(j + 1) * D], s["n"], s["zq"][j], dn, lora=live_lora(lin), res=dn)
+        self._qkv_bwd((a.to_q, a.to_k, a.to_v), dqkv, s["n"], s["zq"], dn, accumulate=True)
         # AdaLN: dx = dx1 + dLN(dn); modulation-vector gradients
         dx = ops.ln_modulate_bwd(dn, s["x"], s["mean"], s["rstd"], mod[:, D:2 * D], L, dres=dx1)
         ops.col_reduce(dn, L, b=s["x"], mean=s["mean"], rstd=s["rstd"], sum_a=dmod[:, 0:D], sum_ab=dmod[:, D:2 * D])
@@ -343,9 +380,7 @@ class FluxEngine:
             ops.qk_norm_rope_bwd(dQ, dK, dV, qkv[:, :D], qkv[:, D:2 * D], wq, wk, cos, sin, dqkv[:, :D], dqkv[:, D:2 * D],
                                  dqkv[:, 2 * D:], B, Ls, off)
             dn = _empty(sd["x"].shape, qkv)
-            for j, lin in enumerate(qkv_lins):
-                linear_bwd(lin, dqkv[:, j * D:(j + 1) * D], sd["n"], sd["zq"][j], dn, lora=live_lora(lin),
-                           **({"res": dn} if j > 0 else {}))
+            self._qkv_bwd(qkv_lins, dqkv, sd["n"], sd["zq"], dn, accumulate=False)
             ops.col_reduce(dn, Ls, b=sd["x"], mean=sd["mean"], rstd=sd["rstd"], sum_a=dmod[:, 0:D], sum_ab=dmod[:, D:2 * D])
             outs[key] = ops.ln_modulate_bwd(dn, sd["x"], sd["mean"], sd["rstd"], mod[:, D:2 * D], Ls, dres=d1[key]) \
                 if need_dx else None

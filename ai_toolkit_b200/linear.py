@@ -96,3 +96,59 @@ def live_lora(lin):
     if lora is None or not lora.is_live():
         return None
     return lora
+
+
+# ------------------------------------------------------------------------------------------------------
+# adapters that share one input (to_q / to_k / to_v ...): one rank-side GEMM + one fused GEMM for the group
+# ------------------------------------------------------------------------------------------------------
+def fuse_linear_weights(lins):
+    """Re-point the weights / biases of Linear layers that share an input at row blocks of ONE contiguous
+    [sum out, in] matrix (no extra copy afterwards; state_dict / load_state_dict keep working on the views)."""
+    first = lins[0]
+    cached = getattr(first, "_b200_fused_w", None)
+    if cached is not None and cached[0].data_ptr() == first.weight.data_ptr():
+        return cached
+    with torch.no_grad():
+        W = torch.cat([l.weight.detach() for l in lins], 0).contiguous()
+        bias = torch.cat([l.bias.detach() for l in lins], 0).contiguous() if first.bias is not None else None
+        row = 0
+        for l in lins:
+            n = l.weight.shape[0]
+            l.weight.data = W[row:row + n]
+            if bias is not None:
+                l.bias.data = bias[row:row + n]
+            row += n
+    first._b200_fused_w = (W, bias)
+    return W, bias
+
+
+def group_fwd(group, lins, x2, out):
+    """out[M, sum out] = x2 @ [W_0; W_1; ...]^T + Zc @ B_fused^T + bias, Zc = bf16(c * x2 @ A_fused^T)."""
+    W, bias = fuse_linear_weights(lins)
+    alpha, row_alpha, rps = lora_coeff(group.loras[0], x2.shape[0])
+    zc = torch.empty((x2.shape[0], RANK_PAD), device=x2.device, dtype=torch.bfloat16)
+    gemm_bf16(x2, group.a_fused, zc, alpha=alpha, row_alpha=row_alpha, rows_per_sample=rps)
+    gemm_bf16(x2, W, out, a1=zc, b1=group.b_fused, bias=bias)
+    return zc
+
+
+def group_bwd(group, lins, dy, x2, zc, dx_out, **epi):
+    """dX for the whole group in one GEMM (K = sum out), dA / dB per adapter from column slices of T / Zc."""
+    W, _ = fuse_linear_weights(lins)
+    alpha, row_alpha, rps = lora_coeff(group.loras[0], dy.shape[0])
+    t = torch.empty((dy.shape[0], RANK_PAD), device=dy.device, dtype=torch.bfloat16)
+    gemm_bf16(dy, group.b_fused, t, trans_b=True, alpha=alpha, row_alpha=row_alpha, rows_per_sample=rps)
+    if dx_out is not None:
+        gemm_bf16(dy, W, dx_out, a1=t, b1=group.a_fused, trans_b=True, **epi)
+    tokens = dy.shape[0]
+    r = group.r
+    row = 0
+    for j, lora in enumerate(group.loras):
+        n = lora.out_dim
+        g_up = lora.lora_up.weight.grad.view(n, r)
+        g_down = lora.lora_down.weight.grad.view(r, lora.in_dim)
+        gemm_bf16(dy[:, row:row + n], zc[:, j * r:], g_up, trans_a=True, trans_b=True, f32_mode=2, n_store=r,
+                  splits=wgrad_splits(tokens, n), config=cabi.GEMM_1CTA_N64)
+        gemm_bf16(x2, t[:, j * r:], g_down, trans_a=True, trans_b=True, f32_mode=2, f32_trans=True, n_store=r,
+                  splits=wgrad_splits(tokens, lora.in_dim), config=cabi.GEMM_1CTA_N64)
+        row += n

@@ -160,6 +160,15 @@ class LoRAModule(nn.Module):
         raise NotImplementedError("extract_weight (LoRA extraction from a tuned model) is outside the training hot path")
 
 
+class FusedGroup:
+    """Adapters that share one input (to_q / to_k / to_v, ...): fused bf16 operands for one GEMM over the group."""
+
+    def __init__(self, loras, a_fused, b_fused):
+        self.loras, self.a_fused, self.b_fused = loras, a_fused, b_fused
+        self.r = loras[0].lora_dim
+        self.out_dims = [m.out_dim for m in loras]
+
+
 class LoRASpecialNetwork(nn.Module):
     NUM_OF_BLOCKS = 12
     UNET_TARGET_REPLACE_MODULE = ["UNet2DConditionModel"]
@@ -337,6 +346,8 @@ class LoRASpecialNetwork(nn.Module):
         self.flat_grads: Optional[torch.Tensor] = None
         self.pack_buf: Optional[torch.Tensor] = None
         self._repack_table = None
+        self._fused_group_defs = []
+        self.fused_groups = {}
         self.torch_multiplier = torch.tensor((1.0,))
         self.multiplier = multiplier
 
@@ -357,31 +368,91 @@ class LoRASpecialNetwork(nn.Module):
         total_pad = (total + 3) // 4 * 4
         flat = torch.zeros(total_pad, device=dev, dtype=torch.float32)
         grads = torch.zeros(total_pad, device=dev, dtype=torch.float32)
-        pack_elems = sum(RANK_PAD * m.in_dim + m.out_dim * RANK_PAD for m in mods)
-        pack = torch.zeros(pack_elems, device=dev, dtype=torch.bfloat16)
-        table = (cabi.RepackEntry * (2 * len(mods)))()
-        off = poff = 0
-        for i, m in enumerate(mods):
-            for j, (lin, rows, cols) in enumerate(((m.lora_down, m.lora_dim, m.in_dim), (m.lora_up, m.out_dim, m.lora_dim))):
-                n = rows * cols
+        off = 0
+        self._param_offsets = {}
+        for m in mods:
+            for lin in (m.lora_down, m.lora_up):
+                n = lin.weight.numel()
                 flat[off:off + n].copy_(lin.weight.detach().reshape(-1).to(dev, torch.float32))
                 lin.weight.data = flat[off:off + n].view(lin.weight.shape)
                 lin.weight.grad = grads[off:off + n].view(lin.weight.shape)
-                if j == 0:
-                    m.a_pack = pack[poff:poff + RANK_PAD * cols].view(RANK_PAD, cols)
-                    table[2 * i] = cabi.RepackEntry(off, poff, rows, cols, cols, 0)
-                    poff += RANK_PAD * cols
-                else:
-                    m.b_pack = pack[poff:poff + rows * RANK_PAD].view(rows, RANK_PAD)
-                    table[2 * i + 1] = cabi.RepackEntry(off, poff, rows, cols, RANK_PAD, 0)
-                    poff += rows * RANK_PAD
+                self._param_offsets[id(lin)] = off
                 off += n
-            m._packed_versions = (-1, -1)
-        self.flat_params, self.flat_grads, self.pack_buf = flat, grads, pack
+        self.flat_params, self.flat_grads = flat, grads
         self.n_params = total
+        self._build_packs()
+
+    @torch.no_grad()
+    def _build_packs(self):
+        """bf16 operand buffers: per module A_pack [64, in] / B_pack [out, 64], plus one (A_fused [64, in],
+        B_fused [sum out, 64]) pair per fused group (adapters sharing an input, e.g. to_q/to_k/to_v: module j's A goes
+        to rows [j r, (j+1) r) of A_fused and its B to the block (rows of module j, columns [j r, (j+1) r)) of B_fused,
+        so ONE rank-side GEMM and ONE fused GEMM serve the whole group).  One repack table covers everything."""
+        mods = self.get_all_modules()
+        dev = self.flat_params.device
+        groups = [g for g in self._fused_group_defs]
+        pack_elems = sum(RANK_PAD * m.in_dim + m.out_dim * RANK_PAD for m in mods)
+        pack_elems += sum(RANK_PAD * g[0].in_dim + sum(m.out_dim for m in g) * RANK_PAD for g in groups)
+        pack = torch.zeros(pack_elems, device=dev, dtype=torch.bfloat16)
+        entries = []
+        poff = 0
+        for m in mods:
+            oa, ob = self._param_offsets[id(m.lora_down)], self._param_offsets[id(m.lora_up)]
+            m.a_pack = pack[poff:poff + RANK_PAD * m.in_dim].view(RANK_PAD, m.in_dim)
+            entries.append(cabi.RepackEntry(oa, poff, m.lora_dim, m.in_dim, m.in_dim, 0))
+            poff += RANK_PAD * m.in_dim
+            m.b_pack = pack[poff:poff + m.out_dim * RANK_PAD].view(m.out_dim, RANK_PAD)
+            entries.append(cabi.RepackEntry(ob, poff, m.out_dim, m.lora_dim, RANK_PAD, 0))
+            poff += m.out_dim * RANK_PAD
+            m._packed_versions = (-1, -1)
+        self.fused_groups = {}
+        for g in groups:
+            r, k = g[0].lora_dim, g[0].in_dim
+            n_out = sum(m.out_dim for m in g)
+            a_f = pack[poff:poff + RANK_PAD * k].view(RANK_PAD, k)
+            a_off = poff
+            poff += RANK_PAD * k
+            b_f = pack[poff:poff + n_out * RANK_PAD].view(n_out, RANK_PAD)
+            b_off = poff
+            poff += n_out * RANK_PAD
+            row = 0
+            for j, m in enumerate(g):
+                entries.append(cabi.RepackEntry(self._param_offsets[id(m.lora_down)], a_off + j * r * k, r, k, k, 0))
+                entries.append(cabi.RepackEntry(self._param_offsets[id(m.lora_up)], b_off + row * RANK_PAD + j * r, m.out_dim, r,
+                                                RANK_PAD, 0))
+                row += m.out_dim
+            self.fused_groups[tuple(id(m) for m in g)] = FusedGroup(list(g), a_f, b_f)
+        table = (cabi.RepackEntry * len(entries))(*entries)
+        self.pack_buf = pack
+        self._repack_entries = len(entries)
         self._repack_table_host = table
         self._repack_table = torch.frombuffer(bytearray(bytes(table)), dtype=torch.uint8).to(dev) if dev.type == "cuda" else None
         self._pack_dirty = True
+
+    def register_fused_groups(self, groups):
+        """Register lists of adapters that share one input; invalid groups (different input / rank / scale, rank not a
+        multiple of 8, more than 64 rank columns in total, a missing adapter) are skipped.  One pack rebuild."""
+        added = False
+        for loras in groups:
+            if any(l is None for l in loras):
+                continue
+            key = tuple(id(m) for m in loras)
+            if key in self.fused_groups or any(tuple(id(m) for m in g) == key for g in self._fused_group_defs):
+                continue
+            r, k = loras[0].lora_dim, loras[0].in_dim
+            if any(m.lora_dim != r or m.in_dim != k or m.scale != loras[0].scale for m in loras) or r % 8 != 0 \
+                    or r * len(loras) > RANK_PAD:
+                continue
+            self._fused_group_defs.append(list(loras))
+            added = True
+        if added:
+            self._build_packs()
+
+    def fused_group(self, loras):
+        """The registered FusedGroup of these adapters, or None."""
+        if any(l is None for l in loras):
+            return None
+        return self.fused_groups.get(tuple(id(m) for m in loras))
 
     def _apply(self, fn, recurse=True):
         out = super()._apply(fn, recurse)
@@ -428,7 +499,7 @@ class LoRASpecialNetwork(nn.Module):
             raise cabi.B200Error("LoRASpecialNetwork is active on a non-CUDA device; the B200 path has no CPU fallback")
         from . import ops
 
-        ops.repack_lora(self.flat_params, self.pack_buf, self._repack_table, 2 * len(mods))
+        ops.repack_lora(self.flat_params, self.pack_buf, self._repack_table, self._repack_entries)
         for m in mods:
             m._packed_versions = (m.lora_down.weight._version, m.lora_up.weight._version)
         self._pack_dirty = False

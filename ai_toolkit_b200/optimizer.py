@@ -58,7 +58,7 @@ class B200AdamW(torch.optim.Optimizer):
         ops.grad_sumsq(net.flat_grads, self.sumsq)
         ops.clip_adamw(net.flat_params, net.flat_grads, self.exp_avg, self.exp_avg_sq, self.sumsq, self.hyper, self.state_buf,
                        ema=self.ema, norm_out=self.grad_norm)
-        ops.repack_lora(net.flat_params, net.pack_buf, net._repack_table, 2 * len(net.get_all_modules()))
+        ops.repack_lora(net.flat_params, net.pack_buf, net._repack_table, net._repack_entries)
         net._pack_dirty = False
         return None
 
