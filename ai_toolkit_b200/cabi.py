@@ -49,6 +49,7 @@ class GemmDesc(Structure):
         ("aux_out", c_void_p), ("ldaux_out", c_int32),
         ("out", c_void_p), ("ldo", c_int32),
         ("act", c_int32),
+        ("act_ncols", c_int32),
         ("f32_mode", c_int32),
         ("f32_trans", c_int32),
         ("n_store", c_int32),
@@ -175,7 +176,7 @@ def _ld(t):
 
 
 def gemm_bf16(a0, b0, out, *, a1=None, b1=None, trans_a=False, trans_b=False, alpha=1.0, row_alpha=None, bias=None,
-              res=None, gate=None, rows_per_sample=0, aux_in=None, aux_out=None, act=ACT_NONE, f32_mode=0,
+              res=None, gate=None, rows_per_sample=0, aux_in=None, aux_out=None, act=ACT_NONE, act_ncols=0, f32_mode=0,
               f32_trans=False, n_store=0, splits=1, config=GEMM_AUTO, M=None, N=None, stream=None, ctx=None):
     """acc = op(a0) @ op(b0)^T (+ op(a1) @ op(b1)^T) with the fused epilogue of ``b200_gemm_bf16``.
 
@@ -209,6 +210,7 @@ def gemm_bf16(a0, b0, out, *, a1=None, b1=None, trans_a=False, trans_b=False, al
     d.out = _ptr(out)
     d.ldo = int(out.stride(-2)) if out.dim() >= 2 else int(out.shape[-1])
     d.act = int(act)
+    d.act_ncols = int(act_ncols)
     d.f32_mode = int(f32_mode)
     d.f32_trans = int(bool(f32_trans))
     d.n_store = int(n_store)

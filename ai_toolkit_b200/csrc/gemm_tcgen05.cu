@@ -36,6 +36,7 @@ struct GemmArgs {
   void* out;
   int ldo;
   int act;
+  int act_ncols;  // activation / aux_out apply to columns n < act_ncols only
   int f32_mode;   // 0 = bf16 epilogue, 1 = fp32 partial store (split-K), 2 = fp32 atomic accumulate
   int f32_trans;  // f32_mode 2: write out[n * ldo + m] instead of out[m * ldo + n]
   int n_store;    // f32 modes: only columns [0, n_store) are written
@@ -188,8 +189,9 @@ __device__ __forceinline__ void epilogue_row32(const GemmArgs& g, int row, int n
     }
 #pragma unroll
     for (int i = 0; i < 8; ++i) v[i] = bf16_round(v[i]);
-    if (g.aux_out != nullptr) store8_bf16(g.aux_out + static_cast<size_t>(row) * g.ldaux_out + n, v);
-    if (g.act == B200_ACT_GELU_TANH) {
+    const bool in_act = n < g.act_ncols;
+    if (g.aux_out != nullptr && in_act) store8_bf16(g.aux_out + static_cast<size_t>(row) * g.ldaux_out + n, v);
+    if (g.act == B200_ACT_GELU_TANH && in_act) {
 #pragma unroll
       for (int i = 0; i < 8; ++i) v[i] = bf16_round(gelu_tanh(v[i]));
     }
@@ -581,6 +583,7 @@ extern "C" int b200_gemm_bf16(b200_ctx* ctx, const b200_gemm_desc* d, void* stre
   a.out = d->out;
   a.ldo = d->ldo;
   a.act = d->act;
+  a.act_ncols = (d->act_ncols > 0 && d->act_ncols < d->N) ? d->act_ncols : d->N;
   a.f32_mode = d->f32_mode;
   a.f32_trans = d->f32_trans;
   a.n_store = (d->n_store > 0 && d->n_store < d->N) ? d->n_store : d->N;

@@ -72,7 +72,11 @@ class FluxEngine:
             groups.append([live_lora(l) for l in (a.add_q_proj, a.add_k_proj, a.add_v_proj)])
         for blk in m.single_transformer_blocks:
             a = blk.attn
-            groups.append([live_lora(l) for l in (a.to_q, a.to_k, a.to_v)])
+            quad = [live_lora(l) for l in (blk.proj_mlp, a.to_q, a.to_k, a.to_v)]
+            if all(l is not None for l in quad) and quad[0].lora_dim % 8 == 0 and 4 * quad[0].lora_dim <= 64:
+                groups.append(quad)  # [proj_mlp; q; k; v] share the AdaLN output: one GEMM, N = 4D + 3D
+            else:
+                groups.append(quad[1:])
         net.register_fused_groups(groups)
         self._groups_for = net
 
@@ -256,12 +260,21 @@ class FluxEngine:
         a = blk.attn
         mod, zmod, amod = self._mod_fwd(blk.norm.linear, temb_silu)
         n, mean, rstd = ops.ln_modulate_fwd(x, mod[:, 0:D], mod[:, D:2 * D], L)
-        qkv = _empty((B * L, 3 * D), x)
-        zq = self._qkv_fwd((a.to_q, a.to_k, a.to_v), n, qkv)
         inner = blk.proj_mlp.out_features
-        cat = _empty((B * L, D + inner), x)
+        # one activation buffer per block: [attention out (D) | GELU(mlp) (4D) | q k v pre-norm (3D)]
+        big = _empty((B * L, D + inner + 3 * D), x)
+        cat = big[:, :D + inner]
+        qkv = big[:, D + inner:]
         pre = _empty((B * L, inner), x)
-        z_mlp = self._lin(blk.proj_mlp, n, cat[:, D:], act=ACT_GELU_TANH, aux_out=pre)
+        lins4 = (blk.proj_mlp, a.to_q, a.to_k, a.to_v)
+        loras4 = [live_lora(l) for l in lins4]
+        grp4 = loras4[0].network_ref().fused_group(loras4) if all(l is not None for l in loras4) else None
+        if grp4 is not None:
+            zq = ("g4", group_fwd(grp4, lins4, n, big[:, D:], act=ACT_GELU_TANH, act_ncols=inner, aux_out=pre))
+            z_mlp = None
+        else:
+            zq = self._qkv_fwd((a.to_q, a.to_k, a.to_v), n, qkv)
+            z_mlp = self._lin(blk.proj_mlp, n, cat[:, D:], act=ACT_GELU_TANH, aux_out=pre)
         Q = _empty((B, H, L, 128), x)
         K = _empty((B, H, L, 128), x)
         V = _empty((B, H, L, 128), x)
@@ -323,19 +336,25 @@ class FluxEngine:
         dy = _empty(dx1.shape, dx1)
         ops.col_reduce(dx1, L, b=s["y"], g=mod[:, 2 * D:3 * D], mul_out=dy, sum_ab=dmod[:, 2 * D:3 * D])
         inner = blk.proj_mlp.out_features
-        dcat = _empty((B * L, D + inner), dx1)
+        dbig = _empty((B * L, D + inner + 3 * D), dx1)  # [dO (D) | d mlp pre-activation (4D) | d qkv (3D)]
+        dcat = dbig[:, :D + inner]
+        dqkv = dbig[:, D + inner:]
         linear_bwd(blk.proj_out, dy, s["cat"], s["z_out"], dcat, lora=live_lora(blk.proj_out),
                    n_slices=[(0, D, {}), (D, D + inner, dict(aux_in=s["pre"]))])
-        # MLP branch: dcat[:, D:] already carries gelu'
-        dn = _empty((B * L, D), dx1)
-        linear_bwd(blk.proj_mlp, dcat[:, D:], s["n"], s["z_mlp"], dn, lora=live_lora(blk.proj_mlp))
         # attention branch
         dQ, dK, dV = attention.bwd(s["Q"], s["K"], s["V"], None, s["cat"][:, :D], None, dcat[:, :D], s["lse"], 0)
         qkv = s["qkv"]
-        dqkv = _empty(qkv.shape, qkv)
         ops.qk_norm_rope_bwd(dQ, dK, dV, qkv[:, :D], qkv[:, D:2 * D], a.norm_q.weight, a.norm_k.weight, cos, sin,
                              dqkv[:, :D], dqkv[:, D:2 * D], dqkv[:, 2 * D:], B, L, 0)
-        self._qkv_bwd((a.to_q, a.to_k, a.to_v), dqkv, s["n"], s["zq"], dn, accumulate=True)
+        dn = _empty((B * L, D), dx1)
+        if s["zq"][0] == "g4":
+            lins4 = (blk.proj_mlp, a.to_q, a.to_k, a.to_v)
+            loras4 = [live_lora(l) for l in lins4]
+            group_bwd(loras4[0].network_ref().fused_group(loras4), lins4, dbig[:, D:], s["n"], s["zq"][1], dn)
+        else:
+            # MLP branch: dcat[:, D:] already carries gelu'
+            linear_bwd(blk.proj_mlp, dcat[:, D:], s["n"], s["z_mlp"], dn, lora=live_lora(blk.proj_mlp))
+            self._qkv_bwd((a.to_q, a.to_k, a.to_v), dqkv, s["n"], s["zq"], dn, accumulate=True)
         # AdaLN: dx = dx1 + dLN(dn); modulation-vector gradients
         dx = ops.ln_modulate_bwd(dn, s["x"], s["mean"], s["rstd"], mod[:, D:2 * D], L, dres=dx1)
         ops.col_reduce(dn, L, b=s["x"], mean=s["mean"], rstd=s["rstd"], sum_a=dmod[:, 0:D], sum_ab=dmod[:, D:2 * D])

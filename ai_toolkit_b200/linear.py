@@ -122,13 +122,13 @@ def fuse_linear_weights(lins):
     return W, bias
 
 
-def group_fwd(group, lins, x2, out):
+def group_fwd(group, lins, x2, out, **epi):
     """out[M, sum out] = x2 @ [W_0; W_1; ...]^T + Zc @ B_fused^T + bias, Zc = bf16(c * x2 @ A_fused^T)."""
     W, bias = fuse_linear_weights(lins)
     alpha, row_alpha, rps = lora_coeff(group.loras[0], x2.shape[0])
     zc = torch.empty((x2.shape[0], RANK_PAD), device=x2.device, dtype=torch.bfloat16)
     gemm_bf16(x2, group.a_fused, zc, alpha=alpha, row_alpha=row_alpha, rows_per_sample=rps)
-    gemm_bf16(x2, W, out, a1=zc, b1=group.b_fused, bias=bias)
+    gemm_bf16(x2, W, out, a1=zc, b1=group.b_fused, bias=bias, **epi)
     return zc
 
 

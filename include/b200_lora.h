@@ -98,6 +98,7 @@ typedef struct b200_gemm_desc {
   void* aux_out; int32_t ldaux_out;       /* bf16 [M,N] or NULL */
   void* out; int32_t ldo;                 /* bf16 [M,N]; fp32 per f32_mode */
   int32_t act;
+  int32_t act_ncols;                      /* act and aux_out apply to columns n < act_ncols (0 = all) */
   int32_t f32_mode;
   int32_t f32_trans;
   int32_t n_store;                        /* fp32 modes: columns written (0 = N) */
