@@ -40,14 +40,17 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ uint32_t mbar_try_wait(uint64_t* bar, uint32_t parity) {
+// try_wait with a suspend-time hint: the thread sleeps IN HARDWARE until the phase completes (or the hint, in ns,
+// expires) instead of spinning through the issue slots — waiting warps then cost (almost) no power, which matters
+// on a part that runs at its 1 kW cap (measured: the spinning version pulled the SM clock ~15 % lower than cuBLAS).
+__device__ __forceinline__ uint32_t mbar_try_wait(uint64_t* bar, uint32_t parity, uint32_t hint_ns = 1000000u) {
   uint32_t ok;
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
       "selp.u32 %0, 1, 0, p;\n\t}"
       : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(hint_ns)
       : "memory");
   return ok;
 }
