@@ -593,10 +593,23 @@ extern "C" int b200_gemm_bf16(b200_ctx* ctx, const b200_gemm_desc* d, void* stre
   int cg = 1, bn = 256;
   switch (config) {
     case B200_GEMM_1CTA_N256: cg = 1; bn = 256; break;
-    case B200_GEMM_2CTA_N256: cg = 2; bn = 256; a.group_m = 4; break;
+    case B200_GEMM_2CTA_N256: cg = 2; bn = 256; break;
     case B200_GEMM_1CTA_N128: cg = 1; bn = 128; break;
     case B200_GEMM_1CTA_N64: cg = 1; bn = 64; break;
     default: set_error("b200_gemm_bf16: unknown config %d", config); return B200_ERR_INVALID;
+  }
+  {
+    // Rasterisation: tiles of `group_m` consecutive tile-rows are visited column by column, so the A rows of a group
+    // stay in L2 while B streams past once per group.  DRAM traffic ~ A + B * (m_tiles / group_m): make the group as
+    // tall as ~30 MB of A allows (the whole M for the K = 3072 layers, where A is the 28 MB activation).
+    const long long row_tile_bytes = 128LL * cg * (static_cast<long long>(d->K0) + d->K1) * 2;
+    long long gm = (30LL << 20) / (row_tile_bytes > 0 ? row_tile_bytes : 1);
+    const int m_tiles_h = (d->M + 128 * cg - 1) / (128 * cg);
+    if (gm < 1) gm = 1;
+    if (gm > m_tiles_h) gm = m_tiles_h;
+    a.group_m = static_cast<int>(gm);
+    const char* e = getenv("B200_GEMM_GROUP_M");
+    if (e) a.group_m = atoi(e) > 0 ? atoi(e) : a.group_m;
   }
   const int ta = d->trans_a ? 1 : 0, tb = d->trans_b ? 1 : 0;
   const uint32_t box_b_rows = static_cast<uint32_t>(bn / cg);
