@@ -12,7 +12,7 @@ import threading
 from ctypes import POINTER, Structure, byref, c_char_p, c_float, c_int, c_int32, c_int64, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libb200lora.so")
+LIB_PATH = os.environ.get("B200_LIB", os.path.join(_HERE, "lib", "libb200lora.so"))  # B200_LIB: tuning variants only
 
 B200_OK = 0
 ACT_NONE = 0

@@ -25,6 +25,18 @@ __device__ __forceinline__ float ex2(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+// 2^x on the FMA pipe (Cody-Waite split + degree-3 minimax polynomial, rel. error ~1e-4, plenty for a bf16 P):
+// the softmax is MUFU-bound (16 ex2 / clk / SM = the same 1024 cycles per 128 x 128 tile as the two MMAs), so a share
+// of the exponentials is computed here instead.  Valid for x in [-126, 127].
+__device__ __forceinline__ float ex2_poly(float x) {
+  x = fmaxf(x, -126.0f);
+  const float xr = __fadd_rd(x, 12582912.0f);       // 1.5 * 2^23: the integer part lands in the low mantissa bits
+  const float f = x - (xr - 12582912.0f);           // fractional part in [0, 1)
+  float p = fmaf(f, 0.077119089663028717f, 0.227564394474029541f);
+  p = fmaf(p, f, 0.695146143436431885f);
+  p = fmaf(p, f, 1.0f);
+  return __int_as_float(__float_as_int(p) + (__float_as_int(xr) << 23));
+}
 __device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t (&r)[32]) {
   asm volatile(
       "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
@@ -49,6 +61,10 @@ __device__ __forceinline__ void st_sw128(uint8_t* tile, int r, int c, uint4 v) {
   *reinterpret_cast<uint4*>(tile + r * 128 + ((c ^ (r & 7)) << 4)) = v;
 }
 
+#ifndef B200_ATTN_POLY
+#define B200_ATTN_POLY 1
+#endif
+constexpr int kPolyPairsOf4 = B200_ATTN_POLY;  // of every 4 column pairs, how many use ex2_poly (0 = all MUFU)
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kLn2 = 0.6931471805599453f;
 
@@ -266,7 +282,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       uint32_t pk[32];
 #pragma unroll
       for (int k2 = 0; k2 < 32; ++k2) {
-        const float pa = ex2(x[2 * k2] - m_used), pb = ex2(x[2 * k2 + 1] - m_used);
+        // every other pair goes to the FMA-pipe polynomial (kPolyShare of the exponentials), the rest to MUFU
+        const bool poly = (k2 % 4) < kPolyPairsOf4;
+        const float pa = poly ? ex2_poly(x[2 * k2] - m_used) : ex2(x[2 * k2] - m_used);
+        const float pb = poly ? ex2_poly(x[2 * k2 + 1] - m_used) : ex2(x[2 * k2 + 1] - m_used);
         l_sum += pa + pb;
         pk[k2] = pack_bf16x2(pa, pb);
       }

@@ -34,9 +34,9 @@ __device__ __forceinline__ void cluster_barrier() {
 }
 __device__ __forceinline__ float ld_dsmem_f32(uint32_t local_addr, uint32_t rank) {
   uint32_t remote;
-  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local_addr), "r"(rank));
+  asm("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local_addr), "r"(rank));
   float v;
-  asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(remote) : "memory");
+  asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(remote));
   return v;
 }
 
@@ -149,12 +149,24 @@ skinny_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       float a = g.alpha;
       if (g.row_alpha) a *= g.row_alpha[grow / g.rows_per_sample];
       const uint32_t base = smem_u32(partial);
+      // issue every remote load of a column pair before the first add (DSMEM latency ~200 cycles: keep 2 S in flight)
       for (int c = 0; c < cols_per; c += 2) {
         const int col = cgrp * cols_per + c;
+        float v0[8], v1[8];
+#pragma unroll
+        for (int p = 0; p < 8; ++p) {
+          if (p < g.S) {
+            v0[p] = ld_dsmem_f32(base + ((col)*128 + r_in) * 4, p);
+            v1[p] = ld_dsmem_f32(base + ((col + 1) * 128 + r_in) * 4, p);
+          }
+        }
         float s0 = 0.f, s1 = 0.f;
-        for (int p = 0; p < g.S; ++p) {
-          s0 += ld_dsmem_f32(base + ((col)*128 + r_in) * 4, p);
-          s1 += ld_dsmem_f32(base + ((col + 1) * 128 + r_in) * 4, p);
+#pragma unroll
+        for (int p = 0; p < 8; ++p) {
+          if (p < g.S) {
+            s0 += v0[p];
+            s1 += v1[p];
+          }
         }
         if (col < g.n_store)
           *reinterpret_cast<uint32_t*>(g.out + static_cast<size_t>(grow) * g.ldo + col) = pack_bf16x2(s0 * a, s1 * a);

@@ -145,7 +145,7 @@ def test_bad_arguments_fail_loudly():
                                            (4096, 64, 15360, False), (200, 48, 328, True), (4608, 64, 12288, True),
                                            (130, 16, 64, False)])
 def test_skinny_cluster_splitk(M, N, K, trans_b):
-    """Rank-side GEMM with the contraction split over a CTA cluster and reduced through DSMEM (AUTO for N <= 64)."""
+    """Rank-side GEMM with the contraction split over a CTA cluster and reduced through DSMEM (config 5)."""
     from ai_toolkit_b200 import cabi
     torch.manual_seed(M + K)
     dev = torch.device("cuda:0")
@@ -154,7 +154,7 @@ def test_skinny_cluster_splitk(M, N, K, trans_b):
     ra = torch.rand(2, device=dev) + 0.5
     rps = (M + 1) // 2
     out = torch.full((M, 64), float("nan"), device=dev, dtype=torch.bfloat16)
-    cabi.gemm_bf16(a, b, out, trans_b=trans_b, alpha=0.7, row_alpha=ra, rows_per_sample=rps, N=N)
+    cabi.gemm_bf16(a, b, out, trans_b=trans_b, alpha=0.7, row_alpha=ra, rows_per_sample=rps, N=N, config=cabi.GEMM_SKINNY_CLUSTER)
     torch.cuda.synchronize()
     want = 0.7 * (a.float() @ (b.float() if trans_b else b.float().t()))
     want = want * ra[torch.arange(M, device=dev) // rps][:, None]
