@@ -318,11 +318,17 @@ class FluxTransformer2DModel(nn.Module):
         enc = self.context_embedder(encoder_hidden_states)
         ids = torch.cat((txt_ids, img_ids), dim=0)
         rope = rope_cos_sin(ids, self.cfg.axes_dims_rope)
+        ckpt = getattr(self, "gradient_checkpointing", False) and torch.is_grad_enabled()
+        if ckpt:
+            from torch.utils.checkpoint import checkpoint
         for blk in self.transformer_blocks:
-            enc, hidden = blk(hidden, enc, temb, rope)
+            if ckpt:  # the reference's default (config_modules.py:413): re-run the block's forward in backward
+                enc, hidden = checkpoint(blk, hidden, enc, temb, rope, use_reentrant=False)
+            else:
+                enc, hidden = blk(hidden, enc, temb, rope)
         hidden = torch.cat([enc, hidden], dim=1)
         for blk in self.single_transformer_blocks:
-            hidden = blk(hidden, temb, rope)
+            hidden = checkpoint(blk, hidden, temb, rope, use_reentrant=False) if ckpt else blk(hidden, temb, rope)
         hidden = hidden[:, enc.shape[1]:, ...]
         hidden = self.norm_out(hidden, temb)
         return self.proj_out(hidden)
