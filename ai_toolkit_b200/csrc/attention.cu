@@ -167,10 +167,6 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     }
   } else if (warp == 1) {
     {  // all 32 lanes run the control flow (converged); one elected lane issues each tcgen05 instruction
-      const uint32_t tbu = __shfl_sync(0xffffffffu, tmem_base, 0);  // provably warp-uniform (see the backward kernel)
-      const uint32_t tS[2] = {tbu, tbu + 128u};
-      const uint32_t tO = tbu + 256u;
-      const uint32_t tP[2] = {tbu + 384u, tbu + 448u};
       constexpr uint32_t idS = umma_idesc_bf16(128, 128, 0, 0);
       constexpr uint32_t idPV = umma_idesc_bf16(128, 128, 0, 1);
       mbar_wait(q_full, 0, 12);
@@ -185,16 +181,13 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         mbar_wait(&s_empty[s], ph ^ 1u, 14);
         tc_fence_after();
         const uint64_t dk = dK0 + static_cast<uint64_t>(s * (32768 >> 4));
-        if (elect_one_pred()) {  // single-thread region: back-to-back UTCHMMA in the uniform datapath
 #pragma unroll
-          for (int kk = 0; kk < 8; ++kk) {
-            const uint32_t off = (kk >> 2) * (16384 >> 4) + 2u * (kk & 3);
-            umma_bf16_ss(tS[s], dQ0 + off, dk + off, idS, kk > 0 ? 1u : 0u);
-          }
-          umma_commit(&k_empty[s]);
-          umma_commit(&s_full[s]);
+        for (int kk = 0; kk < 8; ++kk) {
+          const uint32_t off = (kk >> 2) * (16384 >> 4) + 2u * (kk & 3);
+          umma_bf16_ss_w(tS[s], dQ0 + off, dk + off, idS, kk > 0 ? 1u : 0u);
         }
-        __syncwarp();
+        umma_commit_w(&k_empty[s]);
+        umma_commit_w(&s_full[s]);
       };
       auto issue_PV = [&](int j) {
         const int s = j & 1;
@@ -203,16 +196,13 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         mbar_wait(p_full, j & 1, 16);
         tc_fence_after();
         const uint64_t dv = dV0 + static_cast<uint64_t>(s * (32768 >> 4));
-        if (elect_one_pred()) {
 #pragma unroll
-          for (int kk = 0; kk < 8; ++kk) {
-            const uint32_t off = (kk >> 2) * (8192 >> 4) + (kk & 3) * (2048 >> 4);
-            umma_bf16_ts(tO, tP[s] + kk * 8, dv + off, idPV, (j > 0 || kk > 0) ? 1u : 0u);  // A = P straight from TMEM
-          }
-          umma_commit(&v_empty[s]);
-          umma_commit(pv_done);
+        for (int kk = 0; kk < 8; ++kk) {
+          const uint32_t off = (kk >> 2) * (8192 >> 4) + (kk & 3) * (2048 >> 4);
+          umma_bf16_ts_w(tO, tP[s] + kk * 8, dv + off, idPV, (j > 0 || kk > 0) ? 1u : 0u);  // A = P straight from TMEM
         }
-        __syncwarp();
+        umma_commit_w(&v_empty[s]);
+        umma_commit_w(pv_done);
       };
       issue_S(0);
       for (int j = 0; j < n_kv; ++j) {
@@ -477,12 +467,6 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmR0, const __grid_constant_
     {  // converged MMA warp, elected issue (see common.cuh)
       constexpr uint32_t idA = umma_idesc_bf16(128, 64, 0, 0);
       constexpr uint32_t idB = umma_idesc_bf16(128, 128, 0, 1);
-      // re-derive the TMEM addresses from a shuffled (provably warp-uniform) base so that the compiler keeps the whole
-      // issue path in the uniform datapath instead of moving every operand through R2UR
-      const uint32_t tbu = __shfl_sync(0xffffffffu, tmem_base, 0);
-      const uint32_t tX0[2] = {tbu, tbu + 64u};
-      const uint32_t tX1[2] = {tbu + 128u, tbu + 192u};
-      const uint32_t tA0 = tbu + 256u, tA1 = tbu + 384u;
       mbar_wait(r_full, 0, 21);
       const uint64_t dR0 = umma_desc_sw128(smem_u32(sR0), 1024, 16);
       const uint64_t dR1 = umma_desc_sw128(smem_u32(sR1), 1024, 16);
@@ -497,22 +481,19 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmR0, const __grid_constant_
         tc_fence_after();
         const uint64_t d0 = dTk + static_cast<uint64_t>(st * (32768 >> 4));
         const uint64_t d1 = d0 + (16384 >> 4);
-        if (elect_one_pred()) {
 #pragma unroll
-          for (int kk = 0; kk < 8; ++kk) {
-            const uint32_t offa = (kk >> 2) * (16384 >> 4) + 2u * (kk & 3);
-            const uint32_t offb = (kk >> 2) * (8192 >> 4) + 2u * (kk & 3);
-            umma_bf16_ss(tX0[xb], dR0 + offa, d0 + offb, idA, kk > 0 ? 1u : 0u);
-          }
-#pragma unroll
-          for (int kk = 0; kk < 8; ++kk) {
-            const uint32_t offa = (kk >> 2) * (16384 >> 4) + 2u * (kk & 3);
-            const uint32_t offb = (kk >> 2) * (8192 >> 4) + 2u * (kk & 3);
-            umma_bf16_ss(tX1[xb], dR1 + offa, d1 + offb, idA, kk > 0 ? 1u : 0u);
-          }
-          umma_commit(&x_full[xb]);
+        for (int kk = 0; kk < 8; ++kk) {
+          const uint32_t offa = (kk >> 2) * (16384 >> 4) + 2u * (kk & 3);
+          const uint32_t offb = (kk >> 2) * (8192 >> 4) + 2u * (kk & 3);
+          umma_bf16_ss_w(tX0[xb], dR0 + offa, d0 + offb, idA, kk > 0 ? 1u : 0u);
         }
-        __syncwarp();
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk) {
+          const uint32_t offa = (kk >> 2) * (16384 >> 4) + 2u * (kk & 3);
+          const uint32_t offb = (kk >> 2) * (8192 >> 4) + 2u * (kk & 3);
+          umma_bf16_ss_w(tX1[xb], dR1 + offa, d1 + offb, idA, kk > 0 ? 1u : 0u);
+        }
+        umma_commit_w(&x_full[xb]);
       };
       auto issue_B = [&](int i) {
         const int st = i % kBwdStages;
@@ -523,30 +504,26 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmR0, const __grid_constant_
         const uint32_t acc = i > 0 ? 1u : 0u;
         const int xb = i & 1;
         // A operands come from TMEM: each row's 64 bf16 values sit in the first 32 columns of X (two per column)
-        if (elect_one_pred()) {
-          if (MODE_KV) {
+        if (MODE_KV) {
 #pragma unroll
-            for (int kk = 0; kk < 4; ++kk)  // dV += P^T dO_i
-              umma_bf16_ts(tA0, tX0[xb] + kk * 8, m1 + kk * (2048 >> 4), idB, (kk > 0) ? 1u : acc);
+          for (int kk = 0; kk < 4; ++kk)  // dV += P^T dO_i
+            umma_bf16_ts_w(tA0, tX0[xb] + kk * 8, m1 + kk * (2048 >> 4), idB, (kk > 0) ? 1u : acc);
 #pragma unroll
-            for (int kk = 0; kk < 4; ++kk)  // dK += dS^T Q_i
-              umma_bf16_ts(tA1, tX1[xb] + kk * 8, m0 + kk * (2048 >> 4), idB, (kk > 0) ? 1u : acc);
-          } else {
+          for (int kk = 0; kk < 4; ++kk)  // dK += dS^T Q_i
+            umma_bf16_ts_w(tA1, tX1[xb] + kk * 8, m0 + kk * (2048 >> 4), idB, (kk > 0) ? 1u : acc);
+        } else {
 #pragma unroll
-            for (int kk = 0; kk < 4; ++kk)  // dQ += dS K_j
-              umma_bf16_ts(tA0, tX1[xb] + kk * 8, m0 + kk * (2048 >> 4), idB, (kk > 0) ? 1u : acc);
-          }
-          umma_commit(&t_empty[st]);
+          for (int kk = 0; kk < 4; ++kk)  // dQ += dS K_j
+            umma_bf16_ts_w(tA0, tX1[xb] + kk * 8, m0 + kk * (2048 >> 4), idB, (kk > 0) ? 1u : acc);
         }
-        __syncwarp();
+        umma_commit_w(&t_empty[st]);
       };
       issue_A(0);
       for (int i = 0; i < n_t; ++i) {
         if (i + 1 < n_t) issue_A(i + 1);
         issue_B(i);
       }
-      if (elect_one_pred()) umma_commit(done_bar);
-      __syncwarp();
+      umma_commit_w(done_bar);
     }
   } else {
     // Two softmax groups of 4 warps: group gq owns the tiles i == gq (mod 2), i.e. always the TMEM buffer X[gq], one

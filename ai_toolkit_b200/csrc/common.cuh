@@ -154,17 +154,6 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
 // every instruction in an ELECT / R2UR.BROADCAST / BRA.U.ANY loop with register->uniform-register moves
 // (~15 SASS instructions, ~100 cycles) and the tensor pipe starves on narrow tiles.  These variants are executed
 // by ALL 32 lanes of the (converged) MMA warp with warp-uniform operands; one elected lane issues.
-// true in exactly one lane of a converged warp; `if (elect_one_pred()) { ... }` is the CUTLASS idiom the compiler
-// recognises as a single-thread region (uniform-datapath code without per-instruction uniformisation)
-__device__ __forceinline__ bool elect_one_pred() {
-  uint32_t pred;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "elect.sync _|p, 0xffffffff;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(pred));
-  return pred != 0;
-}
 __device__ __forceinline__ int warp_id_uniform() { return __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0); }
 __device__ __forceinline__ void umma_bf16_ss_w(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
                                                uint32_t accumulate) {

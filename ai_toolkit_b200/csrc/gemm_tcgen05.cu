@@ -383,33 +383,27 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
           const uint32_t sb = sa + C::A_BYTES;
           const uint64_t da = umma_desc_sw128(sa, 1024, A_MN ? 8192 : 16);
           const uint64_t db = umma_desc_sw128(sb, 1024, B_MN ? 8192 : 16);
-          if (elect_one_pred()) {  // single-thread region (CUTLASS idiom): back-to-back UTCHMMA, uniform datapath
 #pragma unroll
-            for (int k = 0; k < C::BK / 16; ++k) {
-              const uint32_t accum = (kb > kb_begin || k > 0) ? 1u : 0u;
-              if (CG == 2)
-                umma_bf16_ss_cg2(d_tmem, da + a_kstep * k, db + b_kstep * k, idesc, accum);
-              else
-                umma_bf16_ss(d_tmem, da + a_kstep * k, db + b_kstep * k, idesc, accum);
-            }
+          for (int k = 0; k < C::BK / 16; ++k) {
+            const uint32_t accum = (kb > kb_begin || k > 0) ? 1u : 0u;
             if (CG == 2)
-              umma_commit_cg2_mc(&empty[stage]);
+              umma_bf16_ss_cg2_w(d_tmem, da + a_kstep * k, db + b_kstep * k, idesc, accum);
             else
-              umma_commit(&empty[stage]);
+              umma_bf16_ss_w(d_tmem, da + a_kstep * k, db + b_kstep * k, idesc, accum);
           }
-          __syncwarp();
+          if (CG == 2)
+            umma_commit_cg2_mc_w(&empty[stage]);
+          else
+            umma_commit_w(&empty[stage]);
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1u;
           }
         }
-        if (elect_one_pred()) {
-          if (CG == 2)
-            umma_commit_cg2_mc(&tfull[acc]);
-          else
-            umma_commit(&tfull[acc]);
-        }
-        __syncwarp();
+        if (CG == 2)
+          umma_commit_cg2_mc_w(&tfull[acc]);
+        else
+          umma_commit_w(&tfull[acc]);
         if (++acc == 2) {
           acc = 0;
           acc_phase ^= 1u;

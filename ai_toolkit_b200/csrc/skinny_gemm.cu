@@ -106,16 +106,12 @@ skinny_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       mbar_wait(&full[st], ph, 31);
       tc_fence_after();
       const uint64_t off = static_cast<uint64_t>(st) * ((kSkA + kSkB) >> 4);
-      if (elect_one_pred()) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-          umma_bf16_ss(tmem_base, dA + off + 2u * k, dB + off + (B_MN ? 128u : 2u) * k, idesc, (i > 0 || k > 0) ? 1u : 0u);
-        umma_commit(&empty[st]);
-      }
-      __syncwarp();
+      for (int k = 0; k < 4; ++k)
+        umma_bf16_ss_w(tmem_base, dA + off + 2u * k, dB + off + (B_MN ? 128u : 2u) * k, idesc, (i > 0 || k > 0) ? 1u : 0u);
+      umma_commit_w(&empty[st]);
     }
-    if (elect_one_pred()) umma_commit(done);
-    __syncwarp();
+    umma_commit_w(done);
   } else {
     // ---- epilogue warps: TMEM -> transposed fp32 partial tile in shared memory
     const int q = warp & 3;
