@@ -41,6 +41,13 @@ struct GemmArgs {
   int f32_trans;  // f32_mode 2: write out[n * ldo + m] instead of out[m * ldo + n]
   int n_store;    // f32 modes: only columns [0, n_store) are written
   float alpha;    // accumulator scale applied before the epilogue
+  // dual-problem mode (the two wgrads of one adapter in one launch): tile rows >= dual_mt0 belong to problem 1, which
+  // reads its operands through the segment-1 tensor maps and writes out1; both share K (tokens), N = 64, alpha, splits
+  int dual_mt0;
+  int M0, M1;
+  void* out1;
+  int ldo1;
+  int f32_trans1;
   const float* row_alpha;  // optional per-sample scale [ceil(M / rows_per_sample)]
 };
 
@@ -147,6 +154,23 @@ __device__ __forceinline__ void store8_bf16(bf16* p, const float (&v)[8]) {
 
 // Epilogue for 32 consecutive columns of one output row held in registers.
 __device__ __forceinline__ void epilogue_row32(const GemmArgs& g, int row, int n0, int split, const uint32_t (&r)[32]) {
+  if (g.dual_mt0 > 0) {  // dual wgrad: fp32 atomic accumulate only
+    const bool p1 = row >= g.dual_mt0 * 128;
+    const int lrow = p1 ? row - g.dual_mt0 * 128 : row;
+    if (lrow >= (p1 ? g.M1 : g.M0)) return;
+    float* o = reinterpret_cast<float*>(p1 ? g.out1 : g.out);
+    const int ldo = p1 ? g.ldo1 : g.ldo;
+    const bool tr = p1 ? g.f32_trans1 != 0 : g.f32_trans != 0;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      const int n = n0 + j;
+      if (n < g.n_store) {
+        const size_t idx = tr ? static_cast<size_t>(n) * ldo + lrow : static_cast<size_t>(lrow) * ldo + n;
+        atomicAdd(o + idx, g.alpha * __uint_as_float(r[j]));
+      }
+    }
+    return;
+  }
   if (row >= g.M) return;
   const int sample = (g.gate != nullptr || g.row_alpha != nullptr) ? row / g.rows_per_sample : 0;
   const float alpha = g.alpha * (g.row_alpha != nullptr ? g.row_alpha[sample] : 1.0f);
@@ -306,7 +330,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       for (int t = worker; t < total_tiles; t += nworkers) {
         int split, m_blk, n_blk;
         tile_coords(t, m_tiles, n_tiles, g.group_m, split, m_blk, n_blk);
-        const int row_a = m_blk * C::BM * CG + static_cast<int>(cta_rank) * C::BM;
+        int row_a = m_blk * C::BM * CG + static_cast<int>(cta_rank) * C::BM;
+        if (g.dual_mt0 > 0 && m_blk >= g.dual_mt0) row_a -= g.dual_mt0 * C::BM;  // problem 1 rows restart at 0
         const int row_b = n_blk * BN + static_cast<int>(cta_rank) * C::BNL;
         const int kb_begin = split * kb_per_split;
         const int kb_end = min(kb_total, kb_begin + kb_per_split);
@@ -314,10 +339,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
           mbar_wait(&empty[stage], phase ^ 1u, 1);
           uint8_t* sa = smem + stage * C::STAGE_BYTES;
           uint8_t* sb = sa + C::A_BYTES;
-          const bool seg1 = kb >= g.kb0;
+          const bool seg1 = g.dual_mt0 > 0 ? (m_blk >= g.dual_mt0) : (kb >= g.kb0);
           const CUtensorMap* ma = seg1 ? &tmA1 : &tmA0;
           const CUtensorMap* mb = seg1 ? &tmB1 : &tmB0;
-          const int kc = (seg1 ? kb - g.kb0 : kb) * C::BK;
+          const int kc = ((seg1 && g.dual_mt0 == 0) ? kb - g.kb0 : kb) * C::BK;
           // K-major operand: one box {64 k, rows}.  MN-major operand (stored [k][mn], mn contiguous):
           // boxes of {64 mn, 64 k}, 8 KB each, one per 64 rows of the tile (descriptor LBO = 8192).
           if (CG == 2) {
@@ -592,6 +617,11 @@ extern "C" int b200_gemm_bf16(b200_ctx* ctx, const b200_gemm_desc* d, void* stre
   a.n_store = (d->n_store > 0 && d->n_store < d->N) ? d->n_store : d->N;
   a.alpha = d->alpha;
   a.row_alpha = reinterpret_cast<const float*>(d->row_alpha);
+  a.dual_mt0 = 0;
+  a.M0 = a.M1 = 0;
+  a.out1 = nullptr;
+  a.ldo1 = 0;
+  a.f32_trans1 = 0;
 
   int cg = 1, bn = 256;
   switch (config) {
@@ -652,4 +682,45 @@ extern "C" int b200_gemm_bf16(b200_ctx* ctx, const b200_gemm_desc* d, void* stre
 #undef B200_LAUNCH
   set_error("b200_gemm_bf16: no kernel for config %d trans_a %d trans_b %d", config, ta, tb);
   return B200_ERR_INVALID;
+}
+
+// dB[out, r] += alpha * dY^T Zc   and   dA[r, in] += alpha * T^T X   in ONE launch (both contract over the tokens)
+extern "C" int b200_lora_wgrad(b200_ctx* ctx, const void* dY, int lddy, const void* Zc, int ldz, const void* X, int ldx,
+                               const void* T, int ldt, void* dB, void* dA, int tokens, int out_dim, int in_dim, int r,
+                               int zcols, float alpha, int splits, void* stream_v) {
+  using namespace b200;
+  int rc = check_ctx(ctx);
+  if (rc != B200_OK) return rc;
+  B200_REQUIRE(dY && Zc && X && T && dB && dA, "b200_lora_wgrad: null operand");
+  B200_REQUIRE(tokens > 0 && out_dim % 8 == 0 && in_dim % 8 == 0 && r > 0 && r <= 64 && zcols % 8 == 0 && zcols >= r && zcols <= 64,
+               "b200_lora_wgrad: bad shape tokens=%d out=%d in=%d r=%d zcols=%d", tokens, out_dim, in_dim, r, zcols);
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_v);
+  GemmArgs a = {};
+  const int mt0 = (out_dim + 127) / 128, mt1 = (in_dim + 127) / 128;
+  a.M = mt0 * 128 + in_dim;  // virtual row space: problem 0 padded to whole tiles, then problem 1
+  a.N = 64;
+  a.kb0 = (tokens + 63) / 64;
+  a.kb1 = 0;
+  a.splits = splits > 1 ? splits : 1;
+  a.group_m = mt0 + mt1;
+  a.rows_per_sample = 1;
+  a.out = dB;
+  a.ldo = r;
+  a.f32_mode = 2;
+  a.f32_trans = 0;
+  a.n_store = r;
+  a.act_ncols = 64;
+  a.alpha = alpha;
+  a.dual_mt0 = mt0;
+  a.M0 = out_dim;
+  a.M1 = in_dim;
+  a.out1 = dA;
+  a.ldo1 = in_dim;
+  a.f32_trans1 = 1;
+  CUtensorMap tA0, tB0, tA1, tB1;
+  if ((rc = make_tmap_bf16_2d(ctx, &tA0, dY, tokens, out_dim, lddy, 64, 64))) return rc;
+  if ((rc = make_tmap_bf16_2d(ctx, &tB0, Zc, tokens, zcols, ldz, 64, 64))) return rc;
+  if ((rc = make_tmap_bf16_2d(ctx, &tA1, X, tokens, in_dim, ldx, 64, 64))) return rc;
+  if ((rc = make_tmap_bf16_2d(ctx, &tB1, T, tokens, zcols, ldt, 64, 64))) return rc;
+  return launch_gemm<1, 64, 8, 1, 1>(ctx, tA0, tB0, tA1, tB1, a, stream);
 }

@@ -26,8 +26,22 @@ def wgrad_splits(tokens: int, features: int, sm_count: int = 148) -> int:
     """Split the token contraction so that (features/128) * splits CTAs fill the GPU."""
     tiles = max(1, (features + 127) // 128)
     kb = max(1, (tokens + 63) // 64)
-    s = max(1, min(kb, (sm_count + tiles - 1) // tiles))
+    s = max(1, min(kb, sm_count // tiles))  # whole waves: tiles * splits <= SMs
     return s
+
+
+def lora_wgrad(lora, dy, zc, x2, t):
+    """dB += dY^T Zc, dA += T^T X for one adapter in ONE launch (zc / t may be column slices of a fused group's Zc / T)."""
+    from ctypes import c_void_p
+
+    tokens = dy.shape[0]
+    r = lora.lora_dim
+    zcols = int(zc.shape[1])
+    feats = lora.out_dim + lora.in_dim
+    cabi.call("b200_lora_wgrad", c_void_p(dy.data_ptr()), int(dy.stride(0)), c_void_p(zc.data_ptr()), int(zc.stride(0)),
+              c_void_p(x2.data_ptr()), int(x2.stride(0)), c_void_p(t.data_ptr()), int(t.stride(0)),
+              c_void_p(lora.lora_up.weight.grad.data_ptr()), c_void_p(lora.lora_down.weight.grad.data_ptr()), tokens,
+              lora.out_dim, lora.in_dim, r, zcols, 1.0, wgrad_splits(tokens, feats), device=dy.device.index)
 
 
 def lora_coeff(lora, n_rows: int):
@@ -78,14 +92,7 @@ def linear_bwd(lin, dy, x2, zc, dx_out, *, lora=None, n_slices=None, **epi):
             b1 = lora.a_pack[:, c0:c1] if lora is not None else None
             gemm_bf16(dy, W[:, c0:c1], dx_out[:, c0:c1], a1=a1, b1=b1, trans_b=True, N=c1 - c0, **e)
     if lora is not None:
-        r = lora.lora_dim
-        tokens = dy.shape[0]
-        g_up = lora.lora_up.weight.grad.view(lora.out_dim, r)
-        g_down = lora.lora_down.weight.grad.view(r, lora.in_dim)
-        gemm_bf16(dy, zc, g_up, trans_a=True, trans_b=True, f32_mode=2, n_store=r,
-                  splits=wgrad_splits(tokens, lora.out_dim), config=cabi.GEMM_1CTA_N64)
-        gemm_bf16(x2, t, g_down, trans_a=True, trans_b=True, f32_mode=2, f32_trans=True, n_store=r,
-                  splits=wgrad_splits(tokens, lora.in_dim), config=cabi.GEMM_1CTA_N64)
+        lora_wgrad(lora, dy, zc, x2, t)
     return t
 
 
@@ -140,15 +147,9 @@ def group_bwd(group, lins, dy, x2, zc, dx_out, **epi):
     gemm_bf16(dy, group.b_fused, t, trans_b=True, alpha=alpha, row_alpha=row_alpha, rows_per_sample=rps)
     if dx_out is not None:
         gemm_bf16(dy, W, dx_out, a1=t, b1=group.a_fused, trans_b=True, **epi)
-    tokens = dy.shape[0]
     r = group.r
     row = 0
     for j, lora in enumerate(group.loras):
         n = lora.out_dim
-        g_up = lora.lora_up.weight.grad.view(n, r)
-        g_down = lora.lora_down.weight.grad.view(r, lora.in_dim)
-        gemm_bf16(dy[:, row:row + n], zc[:, j * r:], g_up, trans_a=True, trans_b=True, f32_mode=2, n_store=r,
-                  splits=wgrad_splits(tokens, n), config=cabi.GEMM_1CTA_N64)
-        gemm_bf16(x2, t[:, j * r:], g_down, trans_a=True, trans_b=True, f32_mode=2, f32_trans=True, n_store=r,
-                  splits=wgrad_splits(tokens, lora.in_dim), config=cabi.GEMM_1CTA_N64)
+        lora_wgrad(lora, dy[:, row:row + n], zc[:, j * r:], x2, t[:, j * r:])
         row += n

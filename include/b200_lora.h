@@ -108,6 +108,17 @@ typedef struct b200_gemm_desc {
 
 int b200_gemm_bf16(b200_ctx* ctx, const b200_gemm_desc* d, void* stream);
 
+/*
+ * Both rank-side weight gradients of ONE adapter in one launch (they contract over the same tokens):
+ *   dB[out, r] += alpha * dY[tokens, out]^T . Zc[tokens, :r]        dA[r, in] += alpha * T[tokens, :r]^T . X[tokens, in]
+ * fp32 atomics into the flat gradient buffer, split-K over `splits` CTAs per 128-row tile; dW [out, in] is never formed.
+ * Zc / T have `zcols` (<= 64, multiple of 8) valid columns starting at the given pointer (column slices of a fused group).
+ * Replaces autograd's grads of lora_up / lora_down (toolkit/network_mixins.py:304-342 backward).
+ */
+int b200_lora_wgrad(b200_ctx* ctx, const void* dY, int lddy, const void* Zc, int ldz, const void* X, int ldx, const void* T,
+                    int ldt, void* dB, void* dA, int tokens, int out_dim, int in_dim, int r, int zcols, float alpha,
+                    int splits, void* stream);
+
 
 /* -------------------------------------------------------------------------------------------------
  * AdaLN-Zero modulation around LayerNorm (no affine):
