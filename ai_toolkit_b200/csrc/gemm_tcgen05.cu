@@ -198,47 +198,115 @@ __device__ __forceinline__ void epilogue_row32(const GemmArgs& g, int row, int n
     }
     return;
   }
+  // (bf16 epilogue is warp-cooperative: epilogue_warp32_bf16)
+}
+
+// ---- warp-cooperative bf16 epilogue ---------------------------------------------------------------------
+// tcgen05.ld hands every thread ONE ROW (32 columns).  Reading / writing global memory in that shape makes each
+// warp instruction touch 32 different 128-byte lines with 16 bytes each (measured: every extra full-size stream —
+// aux_out, aux_in, res — cost ~12 % of the GEMM).  So the [32 rows x 32 cols] bf16 block is transposed through a
+// 2 KB per-warp shared-memory scratch (XOR-swizzled 16-byte chunks, conflict-free both ways): global accesses are
+// then 4 instructions of 8 rows x 64 contiguous bytes.
+__device__ __forceinline__ uint32_t epi_off(int row, int chunk) { return row * 64 + ((chunk ^ ((row >> 1) & 3)) << 4); }
+
+// block [row0 .. row0+31] x [n0 .. n0+31] of a row-major bf16 matrix -> this thread's row as 32 floats
+__device__ __forceinline__ void epi_load_block(uint8_t* scratch, const bf16* base, int ld, int row0, int n0, int M, int N,
+                                               int lane, float (&out)[32]) {
+  __syncwarp();
 #pragma unroll
-  for (int j = 0; j < 32; j += 8) {
-    const int n = n0 + j;
-    if (n >= g.N) break;
-    float v[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) v[i] = alpha * __uint_as_float(r[j + i]);
-    if (g.bias != nullptr) {
-      float b[8];
-      load8_bf16(g.bias + n, b);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) v[i] += b[i];
-    }
-#pragma unroll
-    for (int i = 0; i < 8; ++i) v[i] = bf16_round(v[i]);
-    const bool in_act = n < g.act_ncols;
-    if (g.aux_out != nullptr && in_act) store8_bf16(g.aux_out + static_cast<size_t>(row) * g.ldaux_out + n, v);
-    if (g.act == B200_ACT_GELU_TANH && in_act) {
-#pragma unroll
-      for (int i = 0; i < 8; ++i) v[i] = bf16_round(gelu_tanh(v[i]));
-    }
-    if (g.aux_in != nullptr) {
-      float a[8];
-      load8_bf16(g.aux_in + static_cast<size_t>(row) * g.ldaux_in + n, a);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) v[i] = bf16_round(v[i] * gelu_tanh_grad(a[i]));
-    }
-    if (g.gate != nullptr) {
-      float gt[8];
-      load8_bf16(g.gate + static_cast<size_t>(sample) * g.ldgate + n, gt);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) v[i] = bf16_round(v[i] * gt[i]);
-    }
-    if (g.res != nullptr) {
-      float rs[8];
-      load8_bf16(g.res + static_cast<size_t>(row) * g.ldres + n, rs);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) v[i] = bf16_round(v[i] + rs[i]);
-    }
-    store8_bf16(reinterpret_cast<bf16*>(g.out) + static_cast<size_t>(row) * g.ldo + n, v);
+  for (int p = 0; p < 4; ++p) {
+    const int rr = p * 8 + (lane >> 2), ch = lane & 3;
+    const int grow = row0 + rr, gn = n0 + ch * 8;
+    uint4 u = make_uint4(0u, 0u, 0u, 0u);
+    if (grow < M && gn < N) u = *reinterpret_cast<const uint4*>(base + static_cast<size_t>(grow) * ld + gn);
+    *reinterpret_cast<uint4*>(scratch + epi_off(rr, ch)) = u;
   }
+  __syncwarp();
+#pragma unroll
+  for (int ch = 0; ch < 4; ++ch) {
+    const uint4 u = *reinterpret_cast<const uint4*>(scratch + epi_off(lane, ch));
+    const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
+    out[ch * 8 + 0] = a.x; out[ch * 8 + 1] = a.y; out[ch * 8 + 2] = b.x; out[ch * 8 + 3] = b.y;
+    out[ch * 8 + 4] = c.x; out[ch * 8 + 5] = c.y; out[ch * 8 + 6] = d.x; out[ch * 8 + 7] = d.y;
+  }
+}
+// this thread's row (32 floats, already bf16-exact) -> block of a row-major bf16 matrix, columns < ncols_limit only
+__device__ __forceinline__ void epi_store_block(uint8_t* scratch, bf16* base, int ld, int row0, int n0, int M, int ncols_limit,
+                                                int lane, const float (&v)[32]) {
+  __syncwarp();
+#pragma unroll
+  for (int ch = 0; ch < 4; ++ch) {
+    uint4 u;
+    u.x = pack_bf16x2(v[ch * 8 + 0], v[ch * 8 + 1]);
+    u.y = pack_bf16x2(v[ch * 8 + 2], v[ch * 8 + 3]);
+    u.z = pack_bf16x2(v[ch * 8 + 4], v[ch * 8 + 5]);
+    u.w = pack_bf16x2(v[ch * 8 + 6], v[ch * 8 + 7]);
+    *reinterpret_cast<uint4*>(scratch + epi_off(lane, ch)) = u;
+  }
+  __syncwarp();
+#pragma unroll
+  for (int p = 0; p < 4; ++p) {
+    const int rr = p * 8 + (lane >> 2), ch = lane & 3;
+    const int grow = row0 + rr, gn = n0 + ch * 8;
+    if (grow < M && gn < ncols_limit)
+      *reinterpret_cast<uint4*>(base + static_cast<size_t>(grow) * ld + gn) = *reinterpret_cast<const uint4*>(scratch + epi_off(rr, ch));
+  }
+}
+
+// 32 rows (row0 + lane) x 32 columns (n0 ..): the whole warp must call this together.
+__device__ __forceinline__ void epilogue_warp32_bf16(const GemmArgs& g, uint8_t* scratch, int row0, int lane, int n0,
+                                                     const uint32_t (&r)[32]) {
+  const int row = row0 + lane;
+  const int rowc = row < g.M ? row : g.M - 1;  // clamp for per-row parameter loads; stores are guarded
+  const int sample = (g.gate != nullptr || g.row_alpha != nullptr) ? rowc / g.rows_per_sample : 0;
+  const float alpha = g.alpha * (g.row_alpha != nullptr ? g.row_alpha[sample] : 1.0f);
+  float v[32];
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = alpha * __uint_as_float(r[i]);
+  if (g.bias != nullptr) {
+#pragma unroll
+    for (int j = 0; j < 32; j += 8) {
+      if (n0 + j < g.N) {
+        float b[8];
+        load8_bf16(g.bias + n0 + j, b);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[j + i] += b[i];
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = bf16_round(v[i]);
+  const int act_lim = min(g.act_ncols, g.N);
+  if (g.aux_out != nullptr && n0 < act_lim) epi_store_block(scratch, g.aux_out, g.ldaux_out, row0, n0, g.M, act_lim, lane, v);
+  if (g.act == B200_ACT_GELU_TANH) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i)
+      if (n0 + i < act_lim) v[i] = bf16_round(gelu_tanh(v[i]));
+  }
+  if (g.aux_in != nullptr) {
+    float a[32];
+    epi_load_block(scratch, g.aux_in, g.ldaux_in, row0, n0, g.M, g.N, lane, a);
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = bf16_round(v[i] * gelu_tanh_grad(a[i]));
+  }
+  if (g.gate != nullptr) {
+#pragma unroll
+    for (int j = 0; j < 32; j += 8) {
+      if (n0 + j < g.N) {
+        float gt[8];
+        load8_bf16(g.gate + static_cast<size_t>(sample) * g.ldgate + n0 + j, gt);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[j + i] = bf16_round(v[j + i] * gt[i]);
+      }
+    }
+  }
+  if (g.res != nullptr) {
+    float rs[32];
+    epi_load_block(scratch, g.res, g.ldres, row0, n0, g.M, g.N, lane, rs);
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = bf16_round(v[i] + rs[i]);
+  }
+  epi_store_block(scratch, reinterpret_cast<bf16*>(g.out), g.ldo, row0, n0, g.M, g.N, lane, v);
 }
 
 template <int CG, int BN, int STAGES, int A_MN, int B_MN>
@@ -250,7 +318,8 @@ struct GemmCfg {
   static constexpr uint32_t B_BYTES = BNL * BK * 2;
   static constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int TMEM_COLS = 2 * BN;
-  static constexpr size_t SMEM_BYTES = 1024 + static_cast<size_t>(STAGES) * STAGE_BYTES + (2 * STAGES + 4) * 8 + 16;
+  static constexpr size_t EPI_SCRATCH = 8 * 2048;  // per epilogue warp: 32 x 64 B transpose buffer
+  static constexpr size_t SMEM_BYTES = 1024 + static_cast<size_t>(STAGES) * STAGE_BYTES + EPI_SCRATCH + (2 * STAGES + 4) * 8 + 16;
   static_assert(BN % 16 == 0 && BN >= 32 && BN <= 256, "invalid UMMA N");
   static_assert(TMEM_COLS == 64 || TMEM_COLS == 128 || TMEM_COLS == 256 || TMEM_COLS == 512, "TMEM cols pow2");
   static_assert(SMEM_BYTES <= 232448, "exceeds 227 KB of shared memory");
@@ -264,7 +333,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
   using C = GemmCfg<CG, BN, STAGES, A_MN, B_MN>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * C::STAGE_BYTES);
+  uint8_t* epi_scratch = smem + STAGES * C::STAGE_BYTES;
+  uint64_t* full = reinterpret_cast<uint64_t*>(epi_scratch + C::EPI_SCRATCH);
   uint64_t* empty = full + STAGES;
   uint64_t* tfull = empty + STAGES;
   uint64_t* tempty = tfull + 2;
@@ -465,7 +535,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
 #pragma unroll
           for (int i = 0; i < 32; ++i) r[i] = 0u;
         }
-        epilogue_row32(g, row, n_base + c * 32, split, r);
+        if (g.f32_mode != 0 || g.dual_mt0 > 0)
+          epilogue_row32(g, row, n_base + c * 32, split, r);
+        else
+          epilogue_warp32_bf16(g, epi_scratch + (warp - 2) * 2048, row - lane, lane, n_base + c * 32, r);
       }
       tc_fence_before();
       if (CG == 2)
