@@ -209,26 +209,36 @@ __device__ __forceinline__ void epilogue_row32(const GemmArgs& g, int row, int n
 // then 4 instructions of 8 rows x 64 contiguous bytes.
 __device__ __forceinline__ uint32_t epi_off(int row, int chunk) { return row * 64 + ((chunk ^ ((row >> 1) & 3)) << 4); }
 
-// block [row0 .. row0+31] x [n0 .. n0+31] of a row-major bf16 matrix -> this thread's row as 32 floats
-__device__ __forceinline__ void epi_load_block(uint8_t* scratch, const bf16* base, int ld, int row0, int n0, int M, int N,
-                                               int lane, float (&out)[32]) {
-  __syncwarp();
+// block [row0 .. row0+31] x [n0 .. n0+31] of a row-major bf16 matrix: issue the 4 coalesced loads (8 rows x 64 B each) ...
+__device__ __forceinline__ void epi_prefetch(const bf16* base, int ld, int row0, int n0, int M, int N, int lane, uint4 (&u)[4]) {
 #pragma unroll
   for (int p = 0; p < 4; ++p) {
     const int rr = p * 8 + (lane >> 2), ch = lane & 3;
     const int grow = row0 + rr, gn = n0 + ch * 8;
-    uint4 u = make_uint4(0u, 0u, 0u, 0u);
-    if (grow < M && gn < N) u = *reinterpret_cast<const uint4*>(base + static_cast<size_t>(grow) * ld + gn);
-    *reinterpret_cast<uint4*>(scratch + epi_off(rr, ch)) = u;
+    u[p] = make_uint4(0u, 0u, 0u, 0u);
+    if (grow < M && gn < N) u[p] = *reinterpret_cast<const uint4*>(base + static_cast<size_t>(grow) * ld + gn);
   }
+}
+// ... and later transpose them through the warp's scratch into this thread's row (32 floats).  Issued a whole chunk
+// ahead (the first one before the accumulator is even ready), so the global-load latency is off the critical path.
+__device__ __forceinline__ void epi_unpack(uint8_t* scratch, const uint4 (&u)[4], int lane, float (&out)[32]) {
+  __syncwarp();
+#pragma unroll
+  for (int p = 0; p < 4; ++p) *reinterpret_cast<uint4*>(scratch + epi_off(p * 8 + (lane >> 2), lane & 3)) = u[p];
   __syncwarp();
 #pragma unroll
   for (int ch = 0; ch < 4; ++ch) {
-    const uint4 u = *reinterpret_cast<const uint4*>(scratch + epi_off(lane, ch));
-    const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
+    const uint4 w = *reinterpret_cast<const uint4*>(scratch + epi_off(lane, ch));
+    const float2 a = unpack_bf16x2(w.x), b = unpack_bf16x2(w.y), c = unpack_bf16x2(w.z), d = unpack_bf16x2(w.w);
     out[ch * 8 + 0] = a.x; out[ch * 8 + 1] = a.y; out[ch * 8 + 2] = b.x; out[ch * 8 + 3] = b.y;
     out[ch * 8 + 4] = c.x; out[ch * 8 + 5] = c.y; out[ch * 8 + 6] = d.x; out[ch * 8 + 7] = d.y;
   }
+}
+__device__ __forceinline__ void epi_load_block(uint8_t* scratch, const bf16* base, int ld, int row0, int n0, int M, int N,
+                                               int lane, float (&out)[32]) {
+  uint4 u[4];
+  epi_prefetch(base, ld, row0, n0, M, N, lane, u);
+  epi_unpack(scratch, u, lane, out);
 }
 // this thread's row (32 floats, already bf16-exact) -> block of a row-major bf16 matrix, columns < ncols_limit only
 __device__ __forceinline__ void epi_store_block(uint8_t* scratch, bf16* base, int ld, int row0, int n0, int M, int ncols_limit,
@@ -254,8 +264,9 @@ __device__ __forceinline__ void epi_store_block(uint8_t* scratch, bf16* base, in
 }
 
 // 32 rows (row0 + lane) x 32 columns (n0 ..): the whole warp must call this together.
+// `pf` holds the prefetched block of the "extra input" stream: res when present, else aux_in.
 __device__ __forceinline__ void epilogue_warp32_bf16(const GemmArgs& g, uint8_t* scratch, int row0, int lane, int n0,
-                                                     const uint32_t (&r)[32]) {
+                                                     const uint32_t (&r)[32], const uint4 (&pf)[4]) {
   const int row = row0 + lane;
   const int rowc = row < g.M ? row : g.M - 1;  // clamp for per-row parameter loads; stores are guarded
   const int sample = (g.gate != nullptr || g.row_alpha != nullptr) ? rowc / g.rows_per_sample : 0;
@@ -285,7 +296,10 @@ __device__ __forceinline__ void epilogue_warp32_bf16(const GemmArgs& g, uint8_t*
   }
   if (g.aux_in != nullptr) {
     float a[32];
-    epi_load_block(scratch, g.aux_in, g.ldaux_in, row0, n0, g.M, g.N, lane, a);
+    if (g.res == nullptr)
+      epi_unpack(scratch, pf, lane, a);
+    else
+      epi_load_block(scratch, g.aux_in, g.ldaux_in, row0, n0, g.M, g.N, lane, a);
 #pragma unroll
     for (int i = 0; i < 32; ++i) v[i] = bf16_round(v[i] * gelu_tanh_grad(a[i]));
   }
@@ -302,7 +316,7 @@ __device__ __forceinline__ void epilogue_warp32_bf16(const GemmArgs& g, uint8_t*
   }
   if (g.res != nullptr) {
     float rs[32];
-    epi_load_block(scratch, g.res, g.ldres, row0, n0, g.M, g.N, lane, rs);
+    epi_unpack(scratch, pf, lane, rs);
 #pragma unroll
     for (int i = 0; i < 32; ++i) v[i] = bf16_round(v[i] + rs[i]);
   }
@@ -519,14 +533,21 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       const int kb_end = min(kb_total, kb_begin + kb_per_split);
       const int row = m_blk * C::BM * CG + static_cast<int>(cta_rank) * C::BM + q * 32 + lane;
       const int n_base = n_blk * BN;
+      // extra input stream of the bf16 epilogue (residual, or the saved pre-activation for gelu'): fetched one 32-column
+      // chunk ahead; the first chunk is requested before the accumulator of this tile is even complete
+      const bool bf16_epi = (g.f32_mode == 0 && g.dual_mt0 == 0);
+      const bf16* in_ptr = g.res != nullptr ? g.res : g.aux_in;
+      const int in_ld = g.res != nullptr ? g.ldres : g.ldaux_in;
+      const int n_limit = g.f32_mode ? g.n_store : g.N;
+      uint4 pf[4] = {};
+      if (bf16_epi && in_ptr != nullptr && n_base + half * 32 < n_limit)
+        epi_prefetch(in_ptr, in_ld, row - lane, n_base + half * 32, g.M, g.N, lane, pf);
       mbar_wait(&tfull[acc], acc_phase, 4);
       tc_fence_after();
       const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * BN);
-      const int n_limit = g.f32_mode ? g.n_store : g.N;
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
+      for (int c = half; c < BN / 32; c += 2) {
         if (n_base + c * 32 >= n_limit) break;
-        if ((c & 1) != half) continue;
         uint32_t r[32];
         if (kb_end > kb_begin) {
           tmem_ld_32x32(t_addr + static_cast<uint32_t>(c * 32), r);
@@ -535,10 +556,16 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
 #pragma unroll
           for (int i = 0; i < 32; ++i) r[i] = 0u;
         }
-        if (g.f32_mode != 0 || g.dual_mt0 > 0)
+        if (!bf16_epi) {
           epilogue_row32(g, row, n_base + c * 32, split, r);
-        else
-          epilogue_warp32_bf16(g, epi_scratch + (warp - 2) * 2048, row - lane, lane, n_base + c * 32, r);
+        } else {
+          uint4 cur[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) cur[i] = pf[i];
+          if (in_ptr != nullptr && c + 2 < BN / 32 && n_base + (c + 2) * 32 < n_limit)
+            epi_prefetch(in_ptr, in_ld, row - lane, n_base + (c + 2) * 32, g.M, g.N, lane, pf);
+          epilogue_warp32_bf16(g, epi_scratch + (warp - 2) * 2048, row - lane, lane, n_base + c * 32, r, cur);
+        }
       }
       tc_fence_before();
       if (CG == 2)
