@@ -75,7 +75,8 @@ def _oracle_step(om, on, batch, dtype):
     return loss.item(), pred.detach(), grads
 
 
-@pytest.mark.parametrize("layers,single,heads,B,hl,wl,Lt,rank", [(1, 1, 2, 1, 16, 16, 24, 4), (2, 2, 2, 2, 16, 24, 40, 16)])
+@pytest.mark.parametrize("layers,single,heads,B,hl,wl,Lt,rank", [(1, 1, 2, 1, 16, 16, 24, 4), (2, 2, 2, 2, 16, 24, 40, 16),
+                                                                   (1, 1, 2, 1, 16, 16, 24, 32), (1, 1, 2, 3, 16, 16, 8, 64)])
 def test_engine_step_matches_oracle(layers, single, heads, B, hl, wl, Lt, rank):
     from oracle import flux_ref
     from ai_toolkit_b200 import ops
