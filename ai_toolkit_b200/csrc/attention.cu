@@ -336,6 +336,272 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   if (warp == 1) tmem_dealloc<512>(tmem_base);
 }
 
+// -------------------------------------------------------------------------------------------------
+// forward, variant 2: TWO independent online-softmax streams per Q tile.  Softmax group g (4 warps, one thread per
+// full 128-column row) owns the kv blocks j == g (mod 2), its own S buffer (P is written back in place over S) and its
+// own O accumulator; the two partial results are combined in the epilogue (split-KV combine).  While one group works
+// through its tcgen05.ld -> exp2 -> tcgen05.st chain the tensor core serves the other, so the per-block latency chain
+// is hidden without the row-max exchange / bar.sync of variant 1.
+// -------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kAttnThreads, 1)
+attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                 const __grid_constant__ CUtensorMap tmV, const AttnFwdArgs g) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;
+  uint8_t* sK = sQ + 32768;
+  uint8_t* sV = sK + 2 * 32768;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + 2 * 32768);
+  uint64_t* q_full = bars;
+  uint64_t* k_full = bars + 1;
+  uint64_t* k_empty = bars + 3;
+  uint64_t* v_full = bars + 5;
+  uint64_t* v_empty = bars + 7;
+  uint64_t* s_full = bars + 9;
+  uint64_t* p_full = bars + 11;
+  uint64_t* pv_done = bars + 13;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 15);
+  float* xch = reinterpret_cast<float*>(bars + 16);  // [2 groups][128 rows][2]: (m, l) of each stream
+
+  const int warp = warp_id_uniform(), lane = threadIdx.x & 31;
+  const int bh = blockIdx.y;
+  const int q0 = blockIdx.x * 128;
+  const int n_kv = (g.L + 127) / 128;
+  const long long row_base = static_cast<long long>(bh) * g.L;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmV);
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      mbar_init(q_full, 1);
+      for (int s = 0; s < 2; ++s) {
+        mbar_init(&k_full[s], 1);
+        mbar_init(&k_empty[s], 1);
+        mbar_init(&v_full[s], 1);
+        mbar_init(&v_empty[s], 1);
+        mbar_init(&s_full[s], 1);
+        mbar_init(&p_full[s], 128);
+        mbar_init(&pv_done[s], 1);
+      }
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc<512>(tmem_slot);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
+  const uint32_t tS[2] = {tmem_base, tmem_base + 128u};         // S of stream g; P (bf16 pairs) overwrites its first 64 columns
+  const uint32_t tO[2] = {tmem_base + 256u, tmem_base + 384u};  // O accumulator of stream g
+
+  if (warp == 0) {
+    if (lane == 0) {
+      const int qrow = static_cast<int>(row_base + q0);
+      mbar_arrive_expect_tx(q_full, 32768);
+      tma_load_2d(sQ, &tmQ, q_full, 0, qrow);
+      tma_load_2d(sQ + 16384, &tmQ, q_full, 64, qrow);
+      for (int j = 0; j < n_kv; ++j) {
+        const int s = j & 1;
+        const uint32_t ph = (j >> 1) & 1;
+        const int kvrow = static_cast<int>(row_base + j * 128);
+        mbar_wait(&k_empty[s], ph ^ 1u, 10);
+        mbar_arrive_expect_tx(&k_full[s], 32768);
+        tma_load_2d(sK + s * 32768, &tmK, &k_full[s], 0, kvrow);
+        tma_load_2d(sK + s * 32768 + 16384, &tmK, &k_full[s], 64, kvrow);
+        mbar_wait(&v_empty[s], ph ^ 1u, 11);
+        mbar_arrive_expect_tx(&v_full[s], 32768);
+#pragma unroll
+        for (int jc = 0; jc < 2; ++jc)
+#pragma unroll
+          for (int ih = 0; ih < 2; ++ih)
+            tma_load_2d(sV + s * 32768 + (jc * 2 + ih) * 8192, &tmV, &v_full[s], jc * 64, kvrow + ih * 64);
+      }
+    }
+  } else if (warp == 1) {
+    {  // converged MMA warp, elected issue
+      constexpr uint32_t idS = umma_idesc_bf16(128, 128, 0, 0);
+      constexpr uint32_t idPV = umma_idesc_bf16(128, 128, 0, 1);
+      mbar_wait(q_full, 0, 12);
+      const uint64_t dQ0 = umma_desc_sw128(smem_u32(sQ), 1024, 16);
+      const uint64_t dK0 = umma_desc_sw128(smem_u32(sK), 1024, 16);
+      const uint64_t dV0 = umma_desc_sw128(smem_u32(sV), 1024, 16384);
+      auto issue_S = [&](int j) {  // S(j) overwrites the buffer whose P was read by PV(j-2): same thread, issue order
+        const int s = j & 1;
+        const uint32_t ph = (j >> 1) & 1;
+        mbar_wait(&k_full[s], ph, 13);
+        tc_fence_after();
+        const uint64_t dk = dK0 + static_cast<uint64_t>(s * (32768 >> 4));
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk) {
+          const uint32_t off = (kk >> 2) * (16384 >> 4) + 2u * (kk & 3);
+          umma_bf16_ss_w(tS[s], dQ0 + off, dk + off, idS, kk > 0 ? 1u : 0u);
+        }
+        umma_commit_w(&k_empty[s]);
+        umma_commit_w(&s_full[s]);
+      };
+      auto issue_PV = [&](int j) {
+        const int s = j & 1;
+        const uint32_t ph = (j >> 1) & 1;
+        mbar_wait(&v_full[s], ph, 15);
+        mbar_wait(&p_full[s], ph, 16);
+        tc_fence_after();
+        const uint64_t dv = dV0 + static_cast<uint64_t>(s * (32768 >> 4));
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk) {
+          const uint32_t off = (kk >> 2) * (8192 >> 4) + (kk & 3) * (2048 >> 4);
+          umma_bf16_ts_w(tO[s], tS[s] + kk * 8, dv + off, idPV, (j >= 2 || kk > 0) ? 1u : 0u);  // A = P in TMEM
+        }
+        umma_commit_w(&v_empty[s]);
+        umma_commit_w(&pv_done[s]);
+      };
+      issue_S(0);
+      if (n_kv > 1) issue_S(1);
+      for (int j = 0; j < n_kv; ++j) {
+        issue_PV(j);
+        if (j + 2 < n_kv) issue_S(j + 2);
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    const int gq = (warp - 2) >> 2;  // stream / group
+    const int r = q * 32 + lane;
+    const int qi = q0 + r;
+    const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
+    const float c2 = g.scale * kLog2e;
+    float m_used = -INFINITY, l_sum = 0.f;
+    for (int j = gq; j < n_kv; j += 2) {
+      const uint32_t ph = (j >> 1) & 1;
+      mbar_wait(&s_full[gq], ph, 17);
+      tc_fence_after();
+      const int nvalid = g.L - j * 128;
+      // pass 1: row max (S stays in TMEM; reading it twice is cheaper than 128 live registers)
+      float mx = -INFINITY;
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t v[32];
+        tmem_ld_32x32(tS[gq] + lane_off + c * 32, v);
+        tmem_ld_wait();
+        if (nvalid >= 128) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, (c * 32 + i < nvalid) ? __uint_as_float(v[i]) : -INFINITY);
+        }
+      }
+      mx *= c2;  // c2 > 0: max commutes with the scale
+      const float m_new = fmaxf(m_used, mx);
+      const bool need = (m_new > m_used + 8.0f);
+      const bool any_need = __any_sync(0xffffffffu, need);
+      if (j >= 2) {
+        mbar_wait(&pv_done[gq], ((j >> 1) - 1) & 1, 18);  // PV of this stream's previous block: O_g stable
+        tc_fence_after();
+      }
+      if (any_need) {
+        const float f = need ? ex2(m_used - m_new) : 1.0f;
+        if (need) {
+          m_used = m_new;
+          l_sum *= f;
+        }
+        if (j >= 2) {
+#pragma unroll 1
+          for (int c = 0; c < 4; ++c) {
+            uint32_t v[32];
+            tmem_ld_32x32(tO[gq] + lane_off + c * 32, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * f);
+            tmem_st_32x32(tO[gq] + lane_off + c * 32, v);
+          }
+          tmem_st_wait();
+        }
+      }
+      // pass 2: P = exp2(S c2 - m) in place: chunk c (32 fp32 columns) -> 16 packed bf16 columns at 16 c (already consumed)
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t v[32];
+        tmem_ld_32x32(tS[gq] + lane_off + c * 32, v);
+        tmem_ld_wait();
+        uint32_t pk[16];
+#pragma unroll
+        for (int k2 = 0; k2 < 16; ++k2) {
+          const float xa = fmaf(__uint_as_float(v[2 * k2]), c2, -m_used), xb = fmaf(__uint_as_float(v[2 * k2 + 1]), c2, -m_used);
+          const bool poly = (k2 % 4) < kPolyPairsOf4;
+          float pa = poly ? ex2_poly(xa) : ex2(xa);
+          float pb = poly ? ex2_poly(xb) : ex2(xb);
+          if (nvalid < 128) {
+            pa = (c * 32 + 2 * k2 < nvalid) ? pa : 0.f;
+            pb = (c * 32 + 2 * k2 + 1 < nvalid) ? pb : 0.f;
+          }
+          l_sum += pa + pb;
+          pk[k2] = pack_bf16x2(pa, pb);
+        }
+        tmem_st_32x16(tS[gq] + lane_off + c * 16, pk);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(&p_full[gq]);
+    }
+    // ---- combine the two streams
+    xch[(gq * 128 + r) * 2] = m_used;
+    xch[(gq * 128 + r) * 2 + 1] = l_sum;
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    const float m0 = xch[r * 2], l0 = xch[r * 2 + 1], m1 = xch[(128 + r) * 2], l1 = xch[(128 + r) * 2 + 1];
+    const bool has1 = n_kv > 1;
+    const float m = has1 ? fmaxf(m0, m1) : m0;
+    const float f0 = ex2(m0 - m), f1 = has1 ? ex2(m1 - m) : 0.f;
+    const float l = l0 * f0 + (has1 ? l1 * f1 : 0.f);
+    const int nb0 = (n_kv + 1) / 2, nb1 = n_kv / 2;  // blocks of stream 0 / 1
+    mbar_wait(&pv_done[0], (nb0 - 1) & 1, 19);
+    if (has1) mbar_wait(&pv_done[1], (nb1 - 1) & 1, 19);
+    tc_fence_after();
+    const float inv = 1.0f / l;
+    const float w0 = f0 * inv, w1 = f1 * inv;
+    const bool live = qi < g.L;
+    bf16* orow = nullptr;
+    if (live) {
+      const int b = bh / g.H, hh = bh % g.H;
+      if (qi < g.split)
+        orow = g.o0 + (static_cast<size_t>(b) * g.split + qi) * g.ld0 + hh * 128 + gq * 64;
+      else
+        orow = g.o1 + (static_cast<size_t>(b) * (g.L - g.split) + (qi - g.split)) * g.ld1 + hh * 128 + gq * 64;
+      if (gq == 0) g.lse[row_base + qi] = (m + log2f(l)) * kLn2;
+    }
+#pragma unroll 1
+    for (int c = 0; c < 2; ++c) {  // group gq writes output columns [64 gq, 64 gq + 64)
+      uint32_t a0[32], a1[32];
+      tmem_ld_32x32(tO[0] + lane_off + gq * 64 + c * 32, a0);
+      if (has1) tmem_ld_32x32(tO[1] + lane_off + gq * 64 + c * 32, a1);
+      tmem_ld_wait();
+      if (live) {
+#pragma unroll
+        for (int k8 = 0; k8 < 4; ++k8) {
+          float o[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            o[e] = __uint_as_float(a0[k8 * 8 + e]) * w0;
+            if (has1) o[e] = fmaf(__uint_as_float(a1[k8 * 8 + e]), w1, o[e]);
+          }
+          uint4 u;
+          u.x = pack_bf16x2(o[0], o[1]);
+          u.y = pack_bf16x2(o[2], o[3]);
+          u.z = pack_bf16x2(o[4], o[5]);
+          u.w = pack_bf16x2(o[6], o[7]);
+          *reinterpret_cast<uint4*>(orow + c * 32 + k8 * 8) = u;
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (warp == 1) tmem_dealloc<512>(tmem_base);
+}
+
 // =================================================================================================
 // backward
 // =================================================================================================
@@ -665,13 +931,20 @@ extern "C" int b200_attn_fwd(b200_ctx* ctx, const void* Q, const void* K, const 
   if ((rc = attn_maps(ctx, K, rows, 128, &tk))) return rc;
   if ((rc = attn_maps(ctx, V, rows, 64, &tv))) return rc;
   static bool configured = false;
+  static int variant = 2;
   if (!configured) {
     B200_CUDA_CHECK(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwdSmem));
+    B200_CUDA_CHECK(cudaFuncSetAttribute(attn_fwd2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwdSmem));
+    const char* e = getenv("B200_ATTN_FWD");
+    if (e) variant = atoi(e) == 1 ? 1 : 2;
     configured = true;
   }
   AttnFwdArgs a{(bf16*)o0, ld0, (bf16*)o1, ld1, (float*)lse, B, H, L, split, scale};
   dim3 grid((L + 127) / 128, B * H);
-  attn_fwd_kernel<<<grid, kAttnThreads, kFwdSmem, reinterpret_cast<cudaStream_t>(stream)>>>(tq, tk, tv, a);
+  if (variant == 1)
+    attn_fwd_kernel<<<grid, kAttnThreads, kFwdSmem, reinterpret_cast<cudaStream_t>(stream)>>>(tq, tk, tv, a);
+  else
+    attn_fwd2_kernel<<<grid, kAttnThreads, kFwdSmem, reinterpret_cast<cudaStream_t>(stream)>>>(tq, tk, tv, a);
   B200_CUDA_CHECK(cudaGetLastError());
   ctx->launches.fetch_add(1);
   return B200_OK;
