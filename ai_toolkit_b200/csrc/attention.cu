@@ -931,12 +931,13 @@ extern "C" int b200_attn_fwd(b200_ctx* ctx, const void* Q, const void* K, const 
   if ((rc = attn_maps(ctx, K, rows, 128, &tk))) return rc;
   if ((rc = attn_maps(ctx, V, rows, 64, &tv))) return rc;
   static bool configured = false;
-  static int variant = 2;
+  // variant 1 (one stream, two threads per row) measured 278 us vs 304 us for variant 2 (two streams) at 24 x 4608 x 128
+  static int variant = 1;
   if (!configured) {
     B200_CUDA_CHECK(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwdSmem));
     B200_CUDA_CHECK(cudaFuncSetAttribute(attn_fwd2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwdSmem));
     const char* e = getenv("B200_ATTN_FWD");
-    if (e) variant = atoi(e) == 1 ? 1 : 2;
+    if (e) variant = atoi(e) == 2 ? 2 : 1;
     configured = true;
   }
   AttnFwdArgs a{(bf16*)o0, ld0, (bf16*)o1, ld1, (float*)lse, B, H, L, split, scale};

@@ -82,3 +82,24 @@ def test_attention_flux_shape_timing():
     ref = torch.nn.functional.scaled_dot_product_attention(Q, K, V).transpose(1, 2).reshape(B, L, D)
     got = torch.cat([o0.view(B, split, D), o1.view(B, L - split, D)], 1)
     assert _rel(got, ref) < 1e-2
+
+
+def test_attention_fwd_variant2_two_streams():
+    """The alternative forward kernel (two independent online-softmax streams, B200_ATTN_FWD=2) stays correct; it is read
+    once per process, so run it in a child process."""
+    import os
+    import subprocess
+    import sys
+    code = (
+        "import sys, math, torch; sys.path.insert(0, '.');\n"
+        "from ai_toolkit_b200 import attention\n"
+        "B,H,L,split=1,3,1000,0\n"
+        "Q,K,V=(torch.randn(B,H,L,128,device='cuda').bfloat16() for _ in range(3))\n"
+        "o1=torch.empty(B*L,H*128,device='cuda',dtype=torch.bfloat16)\n"
+        "lse=attention.fwd(Q,K,V,None,o1,0)\n"
+        "ref=torch.nn.functional.scaled_dot_product_attention(Q.float(),K.float(),V.float()).transpose(1,2).reshape(B*L,H*128)\n"
+        "err=((o1.float()-ref).norm()/ref.norm()).item(); print('ERR',err); assert err<1e-2\n")
+    env = dict(os.environ, B200_ATTN_FWD="2")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, "-c", code], cwd=root, env=env, capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout + out.stderr
