@@ -143,58 +143,48 @@ __global__ void __launch_bounds__(256) ln_modulate_bwd_kernel(const bf16* __rest
 //   sum_a [s, d] += sum_rows a[m, d]
 //   sum_ab[s, d] += sum_rows a[m, d] * f(b[m, d]),   f(b) = (b - mean[m]) * rstd[m]  or  b
 //   mul_out[m, d] = bf16(a[m, d] * g[s, d])                                  (optional)
+// Block: 256 threads = 256 column pairs (512 columns) x ROWS rows of one sample; fp32 atomics to [S, D].
 // ------------------------------------------------------------------------------------------------
-constexpr int kColRows = 32;
-// Block: 128 threads x 8 columns (16-byte loads) = 1024 columns, kColRows rows of one sample; fp32 atomics to [S, D].
-__global__ void __launch_bounds__(128) col_reduce_kernel(const bf16* __restrict__ a, int lda, const bf16* __restrict__ b, int ldb,
+constexpr int kColRows = 64;
+__global__ void __launch_bounds__(256) col_reduce_kernel(const bf16* __restrict__ a, int lda, const bf16* __restrict__ b, int ldb,
                                                          const float* __restrict__ mean, const float* __restrict__ rstd,
                                                          const bf16* __restrict__ g, int ldg, bf16* __restrict__ mul_out,
                                                          int ldmul, float* __restrict__ sum_a, float* __restrict__ sum_ab,
                                                          int ldsum, int rows_per_sample, int M, int D) {
-  const int col = (blockIdx.x * 128 + threadIdx.x) * 8;
+  const int col = (blockIdx.x * 256 + threadIdx.x) * 2;
   if (col >= D) return;
   const int chunks_per_sample = (rows_per_sample + kColRows - 1) / kColRows;
   const int sample = blockIdx.y / chunks_per_sample;
   const int r0 = sample * rows_per_sample + (blockIdx.y % chunks_per_sample) * kColRows;
   const int r1 = min(min(r0 + kColRows, (sample + 1) * rows_per_sample), M);
-  float gv[8];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) gv[i] = 0.f;
-  if (g) ld8(g + static_cast<size_t>(sample) * ldg + col, gv);
-  float sa[8], sb[8];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) sa[i] = sb[i] = 0.f;
+  float2 gv = make_float2(0.f, 0.f);
+  if (g) gv = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(g + static_cast<size_t>(sample) * ldg + col));
+  float sa0 = 0.f, sa1 = 0.f, sb0 = 0.f, sb1 = 0.f;
 #pragma unroll 4
   for (int r = r0; r < r1; ++r) {
-    float av[8];
-    ld8(a + static_cast<size_t>(r) * lda + col, av);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) sa[i] += av[i];
+    const float2 av = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(a + static_cast<size_t>(r) * lda + col));
+    sa0 += av.x;
+    sa1 += av.y;
     if (b) {
-      float bv[8];
-      ld8(b + static_cast<size_t>(r) * ldb + col, bv);
+      float2 bv = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(b + static_cast<size_t>(r) * ldb + col));
       if (mean) {
         const float mu = mean[r], rs = rstd[r];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) bv[i] = (bv[i] - mu) * rs;
+        bv.x = (bv.x - mu) * rs;
+        bv.y = (bv.y - mu) * rs;
       }
-#pragma unroll
-      for (int i = 0; i < 8; ++i) sb[i] += av[i] * bv[i];
+      sb0 += av.x * bv.x;
+      sb1 += av.y * bv.y;
     }
-    if (mul_out) {
-      float o[8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) o[i] = av[i] * gv[i];
-      st8(mul_out + static_cast<size_t>(r) * ldmul + col, o);
-    }
+    if (mul_out)
+      *reinterpret_cast<uint32_t*>(mul_out + static_cast<size_t>(r) * ldmul + col) = pack_bf16x2(av.x * gv.x, av.y * gv.y);
   }
   if (sum_a) {
-#pragma unroll
-    for (int i = 0; i < 8; ++i) atomicAdd(sum_a + static_cast<size_t>(sample) * ldsum + col + i, sa[i]);
+    atomicAdd(sum_a + static_cast<size_t>(sample) * ldsum + col, sa0);
+    atomicAdd(sum_a + static_cast<size_t>(sample) * ldsum + col + 1, sa1);
   }
   if (sum_ab) {
-#pragma unroll
-    for (int i = 0; i < 8; ++i) atomicAdd(sum_ab + static_cast<size_t>(sample) * ldsum + col + i, sb[i]);
+    atomicAdd(sum_ab + static_cast<size_t>(sample) * ldsum + col, sb0);
+    atomicAdd(sum_ab + static_cast<size_t>(sample) * ldsum + col + 1, sb1);
   }
 }
 
@@ -413,14 +403,14 @@ extern "C" int b200_col_reduce(b200_ctx* ctx, const void* a, int lda, const void
                                int ldsum, int rows_per_sample, int M, int D, void* stream) {
   int rc = check_ctx(ctx);
   if (rc) return rc;
-  B200_REQUIRE(a && M > 0 && D > 0 && D % 8 == 0 && rows_per_sample > 0, "b200_col_reduce: bad args (D %% 8)");
-  B200_REQUIRE(lda % 8 == 0 && ldb % 8 == 0 && ldg % 8 == 0 && ldmul % 8 == 0, "b200_col_reduce: leading dims must be multiples of 8");
+  B200_REQUIRE(a && M > 0 && D > 0 && D % 2 == 0 && rows_per_sample > 0, "b200_col_reduce: bad args");
+  B200_REQUIRE(lda % 2 == 0 && ldb % 2 == 0 && ldg % 2 == 0 && ldmul % 2 == 0, "b200_col_reduce: leading dims must be even");
   B200_REQUIRE((mean == nullptr) == (rstd == nullptr), "b200_col_reduce: mean and rstd go together");
   if (mul_out) B200_REQUIRE(g != nullptr, "b200_col_reduce: mul_out needs g");
   const int samples = (M + rows_per_sample - 1) / rows_per_sample;
   const int chunks = (rows_per_sample + kColRows - 1) / kColRows;
-  dim3 grid((D / 8 + 127) / 128, samples * chunks);
-  col_reduce_kernel<<<grid, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+  dim3 grid((D / 2 + 255) / 256, samples * chunks);
+  col_reduce_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       (const bf16*)a, lda, (const bf16*)b, ldb, (const float*)mean, (const float*)rstd, (const bf16*)g, ldg, (bf16*)mul_out,
       ldmul, (float*)sum_a, (float*)sum_ab, ldsum, rows_per_sample, M, D);
   B200_CUDA_CHECK(cudaGetLastError());
