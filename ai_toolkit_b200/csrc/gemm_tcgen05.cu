@@ -665,10 +665,12 @@ extern "C" int b200_gemm_bf16(b200_ctx* ctx, const b200_gemm_desc* d, void* stre
   int config = d->config;
   const bool plain_bf16 = !f32 && !d->trans_a && d->K1 == 0 && !d->bias && !d->res && !d->gate && !d->aux_in && !d->aux_out &&
                           d->act == 0 && d->N <= 64;
-  // Measured on B200 (4608 x 64 x 3072, L2-hot): persistent 128 x 64 kernel 14-15 us, cluster split-K + DSMEM
-  // reduction 18-20 us (cluster scheduling + two cluster barriers outweigh the extra CTAs) -> AUTO keeps the former;
-  // the cluster variant stays selectable (and tested) as B200_GEMM_SKINNY_CLUSTER.
-  if (config == B200_GEMM_SKINNY_CLUSTER) {
+  // Rank-side GEMMs (N <= 64).  Measured on B200, L2-hot, persistent 128 x 64 kernel vs cluster split-K + DSMEM reduce:
+  //   M 4608, K 3072: 16 vs 18.5 us | K 9216: 35 vs 27 | K 21504: 71 vs 58 | M 4096, K 12288: 43 vs 21 | M 512, K 9216: 33 vs 11
+  // -> the cluster variant wins as soon as the contraction is long or the row tiles are few.
+  const int sk_mtiles = (d->M + 127) / 128;
+  const bool sk_cluster = plain_bf16 && (d->K0 >= 6144 || sk_mtiles <= 16) && d->K0 >= 512;
+  if ((config == B200_GEMM_AUTO && sk_cluster) || config == B200_GEMM_SKINNY_CLUSTER) {
     B200_REQUIRE(plain_bf16, "b200_gemm_bf16: SKINNY_CLUSTER needs N <= 64, bf16 output, one segment and no fused epilogue");
     return skinny_gemm_dispatch(ctx, d, stream);
   }

@@ -7,5 +7,7 @@ ncu --set full --clock-control none --import-source on -k regex:gemm_bf16 -s 2 -
     python tools/profile_kernels.py gemm > gpurun_out/prof_gemm.log 2>&1; echo "gemm fwd full exit $?"
 ncu --set full --clock-control none --import-source on -k regex:gemm_bf16 -s 5 -c 1 -o gpurun_out/r1_gemm_dgrad -f \
     python tools/profile_kernels.py gemm >> gpurun_out/prof_gemm.log 2>&1; echo "gemm dgrad full exit $?"
-ncu --set full --clock-control none --import-source on -k regex:attn_ -s 2 -c 4 -o gpurun_out/r1_attn -f \
-    python tools/profile_kernels.py attn > gpurun_out/prof_attn.log 2>&1; echo "attn full exit $?"
+ncu --set full --clock-control none --import-source on -k regex:attn_fwd -s 1 -c 1 -o gpurun_out/r1_attn_fwd -f \
+    python tools/profile_kernels.py attn > gpurun_out/prof_attn.log 2>&1; echo "attn fwd full exit $?"
+ncu --set full --clock-control none --import-source on -k regex:attn_bwd -s 2 -c 2 -o gpurun_out/r1_attn_bwd -f \
+    python tools/profile_kernels.py attn >> gpurun_out/prof_attn.log 2>&1; echo "attn bwd full exit $?"
