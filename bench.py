@@ -287,9 +287,9 @@ def run_b200(args):
                 "achieved": ach, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": ach / peaks["bf16_tflops"],
                 "peak_kind": f"{peak_kind} burst (kernel timed alone, L2 flushed)",
                 # dram__bytes_read.sum + dram__bytes_write.sum of this launch, ncu --set full
-                # (profiles/r1_gemm_fwd_ncu_full_summary.csv): 134.0 MB + 189.6 MB; algorithmic bytes 332 MB
-                "traffic": 323.6e6, "traffic_unit": "bytes/launch", "algorithmic_bytes": 2.0 * (M_ * K_ + N_ * K_ + 2 * M_ * N_ + M_ * 64 + N_ * 64),
-                "tensor_pipe_active_pct_ncu": 87.8, "us_per_launch": kms * 1e3}
+                # (profiles/r1_gemm_fwd_ncu_full_summary.csv): 137.2 MB + 191.3 MB; algorithmic bytes 332 MB
+                "traffic": 328.5e6, "traffic_unit": "bytes/launch", "algorithmic_bytes": 2.0 * (M_ * K_ + N_ * K_ + 2 * M_ * N_ + M_ * 64 + N_ * 64),
+                "tensor_pipe_active_pct_ncu": 85.6, "us_per_launch": kms * 1e3}
     if rank != 0:
         return
     f_step, f_lin, f_attn, f_lora = flux_flops(1, RANK, n_double=cfg.num_layers, n_single=cfg.num_single_layers)
