@@ -71,16 +71,6 @@ __device__ __forceinline__ void tma_load_2d_cg2(uint32_t smem_dst, const CUtenso
       "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar_addr), "r"(c0), "r"(c1)
       : "memory");
 }
-__device__ __forceinline__ void umma_bf16_ss_cg2(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
-                                                 uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_d),
-      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
 // warp-converged variants (all 32 lanes execute, one elected lane issues; see common.cuh)
 __device__ __forceinline__ void umma_bf16_ss_cg2_w(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
                                                    uint32_t accumulate) {
@@ -102,13 +92,6 @@ __device__ __forceinline__ void umma_commit_cg2_mc_w(uint64_t* bar) {
           "r"(smem_u32(bar)),
       "h"(mask)
       : "memory");
-}
-__device__ __forceinline__ void umma_commit_cg2_mc(uint64_t* bar) {
-  const uint16_t mask = 3;
-  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::
-                   "r"(smem_u32(bar)),
-               "h"(mask)
-               : "memory");
 }
 template <int NCOLS>
 __device__ __forceinline__ void tmem_alloc_cg2(uint32_t* smem_result) {

@@ -62,6 +62,42 @@ class B200AdamW(torch.optim.Optimizer):
         net._pack_dirty = False
         return None
 
+    # -- interchange with torch.optim.AdamW (the reference saves `optimizer.pt`, BaseSDTrainProcess.py:702-714) ------
+    def torch_state_dict(self):
+        """State in torch.optim.AdamW's own layout (per-parameter `step` / `exp_avg` / `exp_avg_sq`, one param group),
+        so that a run can be resumed by the reference's optimizer and vice versa."""
+        step = float(self.state_buf[0].item())
+        state, off = {}, 0
+        params = self.param_groups[0]["params"]
+        for i, p in enumerate(params):
+            n = p.numel()
+            state[i] = {"step": torch.tensor(step), "exp_avg": self.exp_avg[off:off + n].view(p.shape).detach().cpu().clone(),
+                        "exp_avg_sq": self.exp_avg_sq[off:off + n].view(p.shape).detach().cpu().clone()}
+            off += n
+        g = self.param_groups[0]
+        group = {"lr": g["lr"], "betas": tuple(g["betas"]), "eps": g["eps"], "weight_decay": g["weight_decay"], "amsgrad": False,
+                 "maximize": False, "foreach": None, "capturable": False, "differentiable": False, "fused": None,
+                 "params": list(range(len(params)))}
+        return {"state": state, "param_groups": [group]}
+
+    def load_torch_state_dict(self, sd):
+        params = self.param_groups[0]["params"]
+        off, step = 0, 0
+        for i, p in enumerate(params):
+            n = p.numel()
+            st = sd["state"].get(i)
+            if st is not None:
+                self.exp_avg[off:off + n].copy_(st["exp_avg"].reshape(-1))
+                self.exp_avg_sq[off:off + n].copy_(st["exp_avg_sq"].reshape(-1))
+                step = int(float(st["step"]))
+            off += n
+        self.state_buf.zero_()
+        self.state_buf[0] = step
+        g = sd["param_groups"][0]
+        self.param_groups[0].update({k: g[k] for k in ("lr", "betas", "eps", "weight_decay") if k in g})
+        self._hyper_host = None
+        self.sync_hyper()
+
     # -- checkpointing (flat tensors instead of per-parameter dicts) ---------------------------------
     def state_dict(self):
         return {"b200_flat": True, "exp_avg": self.exp_avg.cpu(), "exp_avg_sq": self.exp_avg_sq.cpu(),

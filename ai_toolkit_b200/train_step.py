@@ -64,7 +64,6 @@ class FluxLoRATrainStep:
     # -- the launch schedule -------------------------------------------------------------------------
     def _forward_backward(self):
         net = self.network
-        net.flat_grads.zero_()
         packed = ops.flow_add_noise(self.latents, self.noise, self.timesteps, pack=True)
         # the trainer passes timestep / 1000 (stable_diffusion_model.py:2196) and the bf16 model re-scales by 1000 in
         # bf16: both happen inside the timestep-embedding kernel (t_div=1000)
@@ -95,13 +94,21 @@ class FluxLoRATrainStep:
         self.text.copy_(text_embeds, non_blocking=True)
         self.pooled.copy_(pooled_embeds, non_blocking=True)
 
-    def run(self):
-        """Launch one step on the resident batch; returns the device loss scalar (no host sync)."""
+    def run(self, first_micro_batch=True, last_micro_batch=True):
+        """Launch one (micro-)step on the resident batch; returns the device loss scalar (no host sync).
+
+        Gradient accumulation (`SDTrainer.hook_train_loop`, SDTrainer.py:2250-2268: gradients of the micro-batches are
+        SUMMED, the optimizer runs after the last one): `first_micro_batch` zeroes the flat gradient buffer,
+        `last_micro_batch` runs all-reduce + clip + AdamW + EMA."""
         self.optimizer.sync_hyper()
+        if first_micro_batch:
+            self.network.ensure_grad_views()
+            self.network.flat_grads.zero_()
         if not self.use_cuda_graph or self._warm < 2:
             self._forward_backward()
-            self._all_reduce()
-            self._optimizer()
+            if last_micro_batch:
+                self._all_reduce()
+                self._optimizer()
             self._warm += 1
             return self.loss_ws[self.B:self.B + 1]
         if self._graph_fb is None:
@@ -114,15 +121,21 @@ class FluxLoRATrainStep:
                 self._optimizer()
             # capture does not execute: run the step that was just recorded
         self._graph_fb.replay()
-        self._all_reduce()
-        self._graph_opt.replay()
+        if last_micro_batch:
+            self._all_reduce()
+            self._graph_opt.replay()
         return self.loss_ws[self.B:self.B + 1]
 
     def hook_train_loop(self, batch) -> OrderedDict:
-        """`batch` = dict(latents, noise, timesteps, text_embeds, pooled_embeds); returns OrderedDict(loss=float)
-        like SDTrainer.hook_train_loop (:2312-2317).  The `.item()` there is the same one device->host sync here."""
-        self.load_batch(batch["latents"], batch["noise"], batch["timesteps"], batch["text_embeds"], batch["pooled_embeds"])
-        loss = self.run()
-        self.loss_host.copy_(loss, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
-        return OrderedDict(loss=float(self.loss_host[0]))
+        """`batch` = dict(latents, noise, timesteps, text_embeds, pooled_embeds), or a LIST of such dicts (gradient
+        accumulation, as the reference's `batch_list`); returns OrderedDict(loss=float) like SDTrainer.hook_train_loop
+        (:2312-2317): the mean of the micro-batch losses.  The `.item()` there is the same one device->host sync here."""
+        batches = batch if isinstance(batch, (list, tuple)) else [batch]
+        total = 0.0
+        for i, b in enumerate(batches):
+            self.load_batch(b["latents"], b["noise"], b["timesteps"], b["text_embeds"], b["pooled_embeds"])
+            loss = self.run(first_micro_batch=(i == 0), last_micro_batch=(i == len(batches) - 1))
+            self.loss_host.copy_(loss, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+            total += float(self.loss_host[0])
+        return OrderedDict(loss=total / len(batches))

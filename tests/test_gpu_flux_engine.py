@@ -228,3 +228,25 @@ def test_loss_curve_matches_oracle_over_steps():
     p_mine = net.flat_params[:p_ref.numel()]
     assert _rel(p_mine - p_init, p_ref - p_init) < 5e-2
     assert int(opt.state_buf[0].item()) == 20
+
+
+def test_gradient_accumulation_sums_micro_batches():
+    """hook_train_loop([b0, b1]) == reference semantics: gradients summed over micro-batches, one optimizer step, mean
+    loss (SDTrainer.py:2250-2268, :2312).  Checked against two separate engine backward passes."""
+    from ai_toolkit_b200.optimizer import B200AdamW
+    from ai_toolkit_b200.train_step import FluxLoRATrainStep
+    model, net, onets, batch = _setup(1, 1, 2, 2, 16, 16, 24, 8, seed=9)
+    lat, noise, t, text, pooled = batch
+    opt = B200AdamW(net, lr=0.0, weight_decay=0.0, max_grad_norm=0.0)  # lr 0: keep the parameters, look at the gradients
+    step = FluxLoRATrainStep(model, net, opt, batch_size=1, latent_shape=(16, 16, 16), text_len=24, use_cuda_graph=False)
+    mb = [dict(latents=lat[i:i + 1], noise=noise[i:i + 1], timesteps=t[i:i + 1], text_embeds=text[i:i + 1],
+               pooled_embeds=pooled[i:i + 1]) for i in range(2)]
+    g = []
+    losses = []
+    for b in mb:
+        losses.append(step.hook_train_loop(b)["loss"])
+        g.append(net.flat_grads.clone())
+    out = step.hook_train_loop(mb)
+    assert abs(out["loss"] - sum(losses) / 2) < 1e-6 * abs(out["loss"]) + 1e-7
+    assert _rel(net.flat_grads, g[0] + g[1]) < 1e-5
+    assert int(opt.state_buf[0].item()) == 3

@@ -138,3 +138,22 @@ def test_state_dict_identical_to_live_reference():
     for k in sr:
         assert torch.equal(sr[k], sn[k]), k
     assert list(r.get_state_dict(dtype=torch.float16).keys()) == list(n.get_state_dict(dtype=torch.float16).keys())
+
+
+def test_optimizer_state_interchange_with_torch_adamw():
+    """B200AdamW state <-> torch.optim.AdamW state dict layout (what the reference stores in optimizer.pt)."""
+    from ai_toolkit_b200.optimizer import B200AdamW
+    model, net = _net()
+    opt = B200AdamW(net, lr=3e-4, eps=1e-6, weight_decay=1e-2)
+    opt.exp_avg.normal_()
+    opt.exp_avg_sq.uniform_()
+    opt.state_buf[0] = 7
+    sd = opt.torch_state_dict()
+    ref = torch.optim.AdamW(net.prepare_optimizer_params(None, 3e-4, 3e-4), lr=3e-4, eps=1e-6)
+    ref.load_state_dict(sd)  # torch accepts it
+    some = next(iter(ref.state.values()))
+    assert float(some["step"]) == 7.0 and ref.param_groups[0]["eps"] == 1e-6
+    opt2 = B200AdamW(net, lr=1e-4)
+    opt2.load_torch_state_dict(ref.state_dict())
+    assert torch.equal(opt2.exp_avg, opt.exp_avg) and torch.equal(opt2.exp_avg_sq, opt.exp_avg_sq)
+    assert int(opt2.state_buf[0]) == 7 and opt2.param_groups[0]["lr"] == 3e-4
