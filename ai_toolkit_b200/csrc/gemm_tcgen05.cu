@@ -721,9 +721,12 @@ extern "C" int b200_gemm_bf16(b200_ctx* ctx, const b200_gemm_desc* d, void* stre
     // stay in L2 while B streams past once per group.  DRAM traffic ~ A + B * (m_tiles / group_m): make the group as
     // tall as ~30 MB of A allows (the whole M for the K = 3072 layers, where A is the 28 MB activation).
     const long long row_tile_bytes = 128LL * cg * (static_cast<long long>(d->K0) + d->K1) * 2;
-    long long gm = (30LL << 20) / (row_tile_bytes > 0 ? row_tile_bytes : 1);
     const int m_tiles_h = (d->M + 128 * cg - 1) / (128 * cg);
-    if (gm < 1) gm = 1;
+    // measured sweep (tools/sweep_group_m.py): if all of A fits (<= 32 MB: the K = 3072 layers) keep every tile-row in one
+    // group; otherwise ~16 MB of A per group (2 tile-rows at K = 12288 .. 21504) is the best or within 0.5 % of it
+    long long gm = m_tiles_h;
+    if (row_tile_bytes * m_tiles_h > (32LL << 20)) gm = (16LL << 20) / (row_tile_bytes > 0 ? row_tile_bytes : 1);
+    if (gm < 2) gm = 2;
     if (gm > m_tiles_h) gm = m_tiles_h;
     a.group_m = static_cast<int>(gm);
     const char* e = getenv("B200_GEMM_GROUP_M");

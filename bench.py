@@ -316,7 +316,7 @@ def run_b200(args):
         "loss_last": last["loss"] if last else None,
         "setup_s": setup_s,
     }
-    if not args.skip_cpu_baseline:
+    if not args.skip_cpu_baseline and world == 1:  # rank 0 at N = 1 only (a bounded CPU sample of the same workload)
         sec, f_sample, desc = cpu_reference_sample(steps=1, warmup=0)
         v = 1.0 / (sec * f_step / f_sample)
         out["cpu_baseline"] = {"value": v, "unit": "steps/s", "cores": os.cpu_count(), "kind": "port", "sample": desc}
