@@ -15,49 +15,13 @@ import torch
 from . import cabi
 
 
-import os
-
-# Bring-up aid ONLY (never the default, never used by bench.py / tests of the product path): route the
-# attention core through torch SDPA to bisect engine bugs from attention-kernel bugs.
-_DEBUG_TORCH = os.environ.get("B200_ATTN_DEBUG_TORCH", "0") == "1"
-
-
 def _p(t):
     return None if t is None else c_void_p(t.data_ptr())
-
-
-def _dbg_gather(o0, o1, B, H, L, split):
-    D = H * 128
-    parts = []
-    if split > 0:
-        parts.append(o0[:, :D].reshape(B, split, D))
-    parts.append(o1[:, :D].reshape(B, L - split, D))
-    return torch.cat(parts, 1)
-
-
-def _dbg_fwd(Q, K, V, o0, o1, split):
-    B, H, L, Dh = Q.shape
-    o = torch.nn.functional.scaled_dot_product_attention(Q, K, V).transpose(1, 2).reshape(B, L, H * Dh)
-    if split > 0:
-        o0[:, :H * Dh].copy_(o[:, :split].reshape(-1, H * Dh))
-    o1[:, :H * Dh].copy_(o[:, split:].reshape(-1, H * Dh))
-    return torch.zeros((B, H, L), device=Q.device, dtype=torch.float32)
-
-
-def _dbg_bwd(Q, K, V, do0, do1, split):
-    B, H, L, Dh = Q.shape
-    do = _dbg_gather(do0, do1, B, H, L, split).reshape(B, L, H, Dh).transpose(1, 2)
-    q, k, v = (t.detach().clone().requires_grad_(True) for t in (Q, K, V))
-    with torch.enable_grad():
-        o = torch.nn.functional.scaled_dot_product_attention(q, k, v)
-    return torch.autograd.grad(o, (q, k, v), do)
 
 
 def fwd(Q, K, V, o0, o1, split):
     """-> lse [B, H, L] fp32 (natural log).  o0 [B*split, ld0] / o1 [B*(L-split), ld1] bf16 views (first H*128 cols)."""
     B, H, L, Dh = Q.shape
-    if _DEBUG_TORCH:
-        return _dbg_fwd(Q, K, V, o0, o1, split)
     lse = torch.empty((B, H, L), device=Q.device, dtype=torch.float32)
     ld0 = int(o0.stride(0)) if o0 is not None else 0
     ld1 = int(o1.stride(0))
@@ -69,8 +33,6 @@ def fwd(Q, K, V, o0, o1, split):
 def bwd(Q, K, V, o0, o1, do0, do1, lse, split):
     """-> dQ, dK, dV [B, H, L, 128] bf16."""
     B, H, L, Dh = Q.shape
-    if _DEBUG_TORCH:
-        return _dbg_bwd(Q, K, V, do0, do1, split)
     dQ = torch.empty_like(Q)
     dK = torch.empty_like(K)
     dV = torch.empty_like(V)
