@@ -638,6 +638,8 @@ __global__ void __launch_bounds__(256) attn_delta_kernel(const bf16* __restrict_
 struct AttnBwdArgs {
   const float* lse;
   const float* delta;
+  const bf16* r0;  // MODE_Q: Q  [B,H,L,128] (the stationary operands are read straight into TMEM)
+  const bf16* r1;  // MODE_Q: dO [B,H,L,128]
   bf16* out0;  // MODE_KV: dV ; MODE_Q: dQ
   bf16* out1;  // MODE_KV: dK
   int L;
@@ -690,7 +692,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmR0, const __grid_constant_
       }
       for (int s = 0; s < 2; ++s) {
         mbar_init(&x_full[s], 1);
-        mbar_init(&x_empty[s], 256);
+        mbar_init(&x_empty[s], 256);  // [0] doubles as 'stationary operands are in TMEM' (MODE_Q)
       }
       mbar_init(&pb_full[0], 128);
       mbar_init(&pb_full[1], 128);
@@ -707,15 +709,21 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmR0, const __grid_constant_
   const uint32_t tX0[2] = {tmem_base, tmem_base + 64u};
   const uint32_t tX1[2] = {tmem_base + 128u, tmem_base + 192u};
   const uint32_t tA0 = tmem_base + 256u, tA1 = tmem_base + 384u;
+  // MODE_Q: only one accumulator (dQ), so columns 384..511 hold the stationary A operands Q_i / dO_i as bf16 pairs:
+  // phase A then reads A from TMEM and only the 64-row streamed tile from shared memory (the N = 64 SS form needs
+  // 6 KB of smem reads per 32-cycle MMA, i.e. it is shared-memory-bandwidth bound)
+  const uint32_t tR0 = tmem_base + 384u, tR1 = tmem_base + 448u;
 
   if (warp == 0) {
     if (lane == 0) {
       const int rrow = static_cast<int>(row_base + r0);
-      mbar_arrive_expect_tx(r_full, 65536);
-      tma_load_2d(sR0, &tmR0, r_full, 0, rrow);
-      tma_load_2d(sR0 + 16384, &tmR0, r_full, 64, rrow);
-      tma_load_2d(sR1, &tmR1, r_full, 0, rrow);
-      tma_load_2d(sR1 + 16384, &tmR1, r_full, 64, rrow);
+      if (MODE_KV) {
+        mbar_arrive_expect_tx(r_full, 65536);
+        tma_load_2d(sR0, &tmR0, r_full, 0, rrow);
+        tma_load_2d(sR0 + 16384, &tmR0, r_full, 64, rrow);
+        tma_load_2d(sR1, &tmR1, r_full, 0, rrow);
+        tma_load_2d(sR1 + 16384, &tmR1, r_full, 64, rrow);
+      }
       for (int i = 0; i < n_t; ++i) {
         const int st = i % kBwdStages;
         const uint32_t ph = (i / kBwdStages) & 1;
@@ -733,7 +741,12 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmR0, const __grid_constant_
     {  // converged MMA warp, elected issue (see common.cuh)
       constexpr uint32_t idA = umma_idesc_bf16(128, 64, 0, 0);
       constexpr uint32_t idB = umma_idesc_bf16(128, 128, 0, 1);
-      mbar_wait(r_full, 0, 21);
+      const uint32_t tR0u = tR0, tR1u = tR1;
+      if (MODE_KV)
+        mbar_wait(r_full, 0, 21);
+      else
+        mbar_wait(&x_empty[0], 0, 21);  // the softmax warps have stored Q_i / dO_i into TMEM
+      tc_fence_after();
       const uint64_t dR0 = umma_desc_sw128(smem_u32(sR0), 1024, 16);
       const uint64_t dR1 = umma_desc_sw128(smem_u32(sR1), 1024, 16);
       const uint64_t dTk = umma_desc_sw128(smem_u32(sT), 1024, 16);     // streamed tiles read K-major (phase A)
@@ -751,13 +764,19 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmR0, const __grid_constant_
         for (int kk = 0; kk < 8; ++kk) {
           const uint32_t offa = (kk >> 2) * (16384 >> 4) + 2u * (kk & 3);
           const uint32_t offb = (kk >> 2) * (8192 >> 4) + 2u * (kk & 3);
-          umma_bf16_ss_w(tX0[xb], dR0 + offa, d0 + offb, idA, kk > 0 ? 1u : 0u);
+          if (MODE_KV)
+            umma_bf16_ss_w(tX0[xb], dR0 + offa, d0 + offb, idA, kk > 0 ? 1u : 0u);
+          else
+            umma_bf16_ts_w(tX0[xb], tR0u + kk * 8, d0 + offb, idA, kk > 0 ? 1u : 0u);
         }
 #pragma unroll
         for (int kk = 0; kk < 8; ++kk) {
           const uint32_t offa = (kk >> 2) * (16384 >> 4) + 2u * (kk & 3);
           const uint32_t offb = (kk >> 2) * (8192 >> 4) + 2u * (kk & 3);
-          umma_bf16_ss_w(tX1[xb], dR1 + offa, d1 + offb, idA, kk > 0 ? 1u : 0u);
+          if (MODE_KV)
+            umma_bf16_ss_w(tX1[xb], dR1 + offa, d1 + offb, idA, kk > 0 ? 1u : 0u);
+          else
+            umma_bf16_ts_w(tX1[xb], tR1u + kk * 8, d1 + offb, idA, kk > 0 ? 1u : 0u);
         }
         umma_commit_w(&x_full[xb]);
       };
@@ -809,6 +828,28 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmR0, const __grid_constant_
     if (!MODE_KV && ri < g.L) {
       my_lse2 = lse_bh[ri] * kLog2e;
       my_dls = delta_bh[ri] * g.scale;
+    }
+    if (!MODE_KV) {
+      // group 0 stores Q_i, group 1 stores dO_i: one 256-byte row per thread, bf16 pairs as they lie in memory
+      const bf16* src = (gq == 0 ? g.r0 : g.r1) + (row_base + ri) * 128;
+      const uint32_t dst = (gq == 0 ? tR0 : tR1) + lane_off;
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        uint32_t w[32];
+#pragma unroll
+        for (int k4 = 0; k4 < 8; ++k4) {
+          uint4 u = make_uint4(0u, 0u, 0u, 0u);
+          if (ri < g.L) u = *reinterpret_cast<const uint4*>(src + c * 64 + k4 * 8);
+          w[k4 * 4 + 0] = u.x;
+          w[k4 * 4 + 1] = u.y;
+          w[k4 * 4 + 2] = u.z;
+          w[k4 * 4 + 3] = u.w;
+        }
+        tmem_st_32x32(dst + c * 32, w);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(&x_empty[0]);
     }
     // software prefetch of the per-column statistics (MODE_KV): registers for the group's next tile
     float nl0 = 0.f, nl1 = 0.f, nd0 = 0.f, nd1 = 0.f;
@@ -984,10 +1025,10 @@ extern "C" int b200_attn_bwd(b200_ctx* ctx, const void* Q, const void* K, const 
     configured = true;
   }
   dim3 grid((L + 127) / 128, B * H);
-  AttnBwdArgs akv{(const float*)lse, (const float*)delta, (bf16*)dV, (bf16*)dK, L, scale};
+  AttnBwdArgs akv{(const float*)lse, (const float*)delta, nullptr, nullptr, (bf16*)dV, (bf16*)dK, L, scale};
   attn_bwd_kernel<1><<<grid, kAttnThreads, kBwdSmem, st>>>(k128, v128, q64, d64, akv);
   B200_CUDA_CHECK(cudaGetLastError());
-  AttnBwdArgs aq{(const float*)lse, (const float*)delta, (bf16*)dQ, nullptr, L, scale};
+  AttnBwdArgs aq{(const float*)lse, (const float*)delta, (const bf16*)Q, (const bf16*)dOh, (bf16*)dQ, nullptr, L, scale};
   attn_bwd_kernel<0><<<grid, kAttnThreads, kBwdSmem, st>>>(q128, d128, k64, v64, aq);
   B200_CUDA_CHECK(cudaGetLastError());
   ctx->launches.fetch_add(3);
