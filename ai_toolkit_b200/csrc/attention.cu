@@ -711,7 +711,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmR0, const __grid_constant_
   const uint32_t tA0 = tmem_base + 256u, tA1 = tmem_base + 384u;
   // MODE_Q: only one accumulator (dQ), so columns 384..511 hold the stationary A operands Q_i / dO_i as bf16 pairs:
   // phase A then reads A from TMEM and only the 64-row streamed tile from shared memory (the N = 64 SS form needs
-  // 6 KB of smem reads per 32-cycle MMA, i.e. it is shared-memory-bandwidth bound)
+  // 6 KB of smem reads per 32-cycle MMA).  Measured: correct, but end-to-end neutral (886 vs ~870 us backward), so
+  // shared-memory bandwidth is not what holds this kernel at ~52 % tensor-pipe activity.
   const uint32_t tR0 = tmem_base + 384u, tR1 = tmem_base + 448u;
 
   if (warp == 0) {
