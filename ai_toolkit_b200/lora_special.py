@@ -456,14 +456,14 @@ class LoRASpecialNetwork(nn.Module):
 
     def _apply(self, fn, recurse=True):
         out = super()._apply(fn, recurse)
-        # .to()/.cuda()/.float() replaced every parameter tensor: rebuild the flat views there.
-        if self.flat_params is not None or any(True for _ in self.get_all_modules()):
-            registered = all(m.lora_name in self._modules for m in self.get_all_modules())
-            if registered and self.get_all_modules():
-                for m in self.get_all_modules():
-                    if m.lora_down.weight.dtype != torch.float32:
-                        raise NotImplementedError("LoRA master weights must be fp32 (BaseSDTrainProcess.py:1983)")
-                self._flatten()
+        # .to() / .cuda() / .float() replaced every parameter tensor: rebuild the flat views on the new device.  Before
+        # apply_to() the adapters are not registered sub-modules yet (force_to moves them itself), so nothing to do.
+        mods = self.get_all_modules()
+        if mods and all(m.lora_name in self._modules for m in mods):
+            for m in mods:
+                if m.lora_down.weight.dtype != torch.float32:
+                    raise NotImplementedError("LoRA master weights must be fp32 (BaseSDTrainProcess.py:1983)")
+            self._flatten()
         return out
 
     def ensure_grad_views(self):

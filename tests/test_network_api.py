@@ -157,3 +157,25 @@ def test_optimizer_state_interchange_with_torch_adamw():
     opt2.load_torch_state_dict(ref.state_dict())
     assert torch.equal(opt2.exp_avg, opt.exp_avg) and torch.equal(opt2.exp_avg_sq, opt.exp_avg_sq)
     assert int(opt2.state_buf[0]) == 7 and opt2.param_groups[0]["lr"] == 3e-4
+
+
+def test_flux_container_matches_oracle_parameter_names():
+    """The parameter container has exactly the oracle's (= diffusers') parameter names and shapes, so checkpoints load."""
+    from oracle import flux_ref
+
+    cfg = dict(CFG)
+    o = flux_ref.FluxTransformer2DModel(flux_ref.FluxConfig(**cfg))
+    m = FluxTransformer2DModel(FluxConfig(**cfg), dtype=torch.float32)
+    so, sm = o.state_dict(), m.state_dict()
+    assert set(so.keys()) == set(sm.keys())
+    for k in so:
+        assert so[k].shape == sm[k].shape, k
+    m.load_state_dict(so, strict=True)
+
+
+def test_to_rebuilds_flat_views():
+    model, net = _net()
+    w_before = net.unet_loras[0].lora_down.weight.detach().clone()
+    net.to(torch.float32)  # a no-op move still goes through _apply -> _flatten
+    assert torch.equal(net.unet_loras[0].lora_down.weight, w_before)
+    assert net.unet_loras[0].lora_down.weight.data_ptr() == net.flat_params.data_ptr()
