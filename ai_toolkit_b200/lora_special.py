@@ -35,6 +35,8 @@ from . import cabi
 LINEAR_MODULES = ["Linear", "LoRACompatibleLinear", "QLinear", "OstrisLinear"]  # lora_special.py:29-35
 CONV_MODULES = ["Conv2d", "LoRACompatibleConv", "QConv2d"]  # lora_special.py:36-40
 RANK_PAD = 64
+KOHYA_UNET_TARGET_REPLACE_MODULE = ["Transformer2DModel"]  # kohya_lora.py:750
+KOHYA_UNET_TARGET_REPLACE_MODULE_CONV2D_3X3 = ["ResnetBlock2D", "Downsample2D", "Upsample2D"]  # :751
 
 
 class LoRAModule(nn.Module):
@@ -245,8 +247,10 @@ class LoRASpecialNetwork(nn.Module):
             conv_alpha = self.conv_alpha
         if conv_lora_dim is not None and conv_lora_dim > 0:
             raise NotImplementedError("conv_lora_dim (3x3 conv LoRA) is not implemented")
+        # the reference's defaults are kohya's class attributes, not this class's (lora_special.py:331-332,
+        # kohya_lora.py:750-751): LoRA goes on the Linear / 1x1-conv layers inside `Transformer2DModel` blocks
         if target_lin_modules is None:
-            target_lin_modules = list(self.UNET_TARGET_REPLACE_MODULE)
+            target_lin_modules = list(KOHYA_UNET_TARGET_REPLACE_MODULE)
 
         def create_modules(is_unet, text_encoder_idx, root_module, target_replace_modules):
             unet_prefix = self.PEFT_PREFIX_UNET if self.peft_format else self.LORA_PREFIX_UNET
@@ -321,7 +325,7 @@ class LoRASpecialNetwork(nn.Module):
                 self.text_encoder_loras.extend(te_loras)
         target_modules = list(target_lin_modules)
         if modules_dim is not None:
-            target_modules += list(target_conv_modules or self.UNET_TARGET_REPLACE_MODULE_CONV2D_3X3)
+            target_modules += list(target_conv_modules or KOHYA_UNET_TARGET_REPLACE_MODULE_CONV2D_3X3)
         if is_v3:
             target_modules = ["SD3Transformer2DModel"]
         if is_pixart:

@@ -179,3 +179,62 @@ def test_to_rebuilds_flat_views():
     net.to(torch.float32)  # a no-op move still goes through _apply -> _flatten
     assert torch.equal(net.unet_loras[0].lora_down.weight, w_before)
     assert net.unet_loras[0].lora_down.weight.data_ptr() == net.flat_params.data_ptr()
+
+
+class Transformer2DModel(torch.nn.Module):  # the class name the reference targets inside a UNet (kohya_lora.py:750)
+    def __init__(self):
+        super().__init__()
+        self.proj_in = torch.nn.Conv2d(8, 16, 1)
+        self.to_q = torch.nn.Linear(16, 16, bias=False)
+        self.ff = torch.nn.Linear(16, 32)
+        self.conv3 = torch.nn.Conv2d(16, 16, 3, padding=1)
+
+
+def _toy_unet():
+    cls = type("UNet2DConditionModel", (torch.nn.Module,), {})
+
+    def init(self):
+        torch.nn.Module.__init__(self)
+        self.down_blocks = torch.nn.ModuleList([Transformer2DModel(), Transformer2DModel()])
+        self.conv_in = torch.nn.Conv2d(4, 8, 3, padding=1)      # outside Transformer2DModel: never wrapped
+        self.time_proj = torch.nn.Linear(8, 8)
+
+    cls.__init__ = init
+    return cls()
+
+
+def test_kohya_format_unet_naming_alpha_and_scale():
+    """SD1.5 / SDXL path (BASELINE configs[0], [1], plumbing): kohya names `lora_unet_<path_with_underscores>`, alpha saved,
+    scale = alpha / rank, Linear + 1x1 Conv wrapped, 3x3 Conv skipped when conv_lora_dim is None (lora_special.py:456-640)."""
+    unet = _toy_unet()
+    net = LoRASpecialNetwork(text_encoder=None, unet=unet, lora_dim=4, alpha=2, train_unet=True, train_text_encoder=False)
+    net.force_to("cpu", torch.float32)
+    net._update_torch_multiplier()
+    net.apply_to(None, unet, False, True)
+    names = [l.lora_name for l in net.unet_loras]
+    assert names == ["lora_unet_down_blocks_0_proj_in", "lora_unet_down_blocks_0_to_q", "lora_unet_down_blocks_0_ff",
+                     "lora_unet_down_blocks_1_proj_in", "lora_unet_down_blocks_1_to_q", "lora_unet_down_blocks_1_ff"]
+    assert not net.peft_format and all(abs(l.scale - 0.5) < 1e-9 for l in net.unet_loras)
+    sd = net.get_state_dict(dtype=torch.float32)
+    assert "lora_unet_down_blocks_0_to_q.alpha" in sd and float(sd["lora_unet_down_blocks_0_to_q.alpha"]) == 2.0
+    assert sd["lora_unet_down_blocks_0_proj_in.lora_down.weight"].shape == (4, 8, 1, 1)
+    assert sd["lora_unet_down_blocks_0_ff.lora_up.weight"].shape == (32, 4)
+
+
+@pytest.mark.skipif(not ref_import.available(), reason="reference tree not present (GPU box)")
+def test_kohya_format_identical_to_live_reference():
+    RefNet, _ = ref_import.reference_lora()
+    u1, u2 = _toy_unet(), _toy_unet()
+    kw = dict(text_encoder=None, lora_dim=4, alpha=2, train_unet=True, train_text_encoder=False)
+    torch.manual_seed(2)
+    r = RefNet(unet=u1, **kw)
+    r.force_to("cpu", torch.float32); r._update_torch_multiplier(); r.apply_to(None, u1, False, True)
+    torch.manual_seed(2)
+    n = LoRASpecialNetwork(unet=u2, **kw)
+    n.force_to("cpu", torch.float32); n._update_torch_multiplier(); n.apply_to(None, u2, False, True)
+    assert [l.lora_name for l in r.unet_loras] == [l.lora_name for l in n.unet_loras]
+    sr, sn = r.get_state_dict(dtype=torch.float32), n.get_state_dict(dtype=torch.float32)
+    assert list(sr.keys()) == list(sn.keys())
+    for k in sr:
+        assert torch.equal(sr[k], sn[k]), k
+    assert [l.scale for l in r.unet_loras] == [l.scale for l in n.unet_loras]
