@@ -15,72 +15,13 @@
 //
 // Reference semantics: torch SDPA as called by diffusers' FLUX attention processor (in-tree equivalent
 // extensions_built_in/diffusion_models/chroma/src/math.py:13-30); backward = its autograd.
-#include "common.cuh"
-#include "ctx.h"
+#include "attn_common.cuh"
 
 namespace b200 {
-
-__device__ __forceinline__ float ex2(float x) {
-  float y;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
-// 2^x on the FMA pipe (Cody-Waite split + degree-3 minimax polynomial, rel. error ~1e-4, plenty for a bf16 P):
-// the softmax is MUFU-bound (16 ex2 / clk / SM = the same 1024 cycles per 128 x 128 tile as the two MMAs), so a share
-// of the exponentials is computed here instead.  Valid for x in [-126, 127].
-__device__ __forceinline__ float ex2_poly(float x) {
-  x = fmaxf(x, -126.0f);
-  const float xr = __fadd_rd(x, 12582912.0f);       // 1.5 * 2^23: the integer part lands in the low mantissa bits
-  const float f = x - (xr - 12582912.0f);           // fractional part in [0, 1)
-  float p = fmaf(f, 0.077119089663028717f, 0.227564394474029541f);
-  p = fmaf(p, f, 0.695146143436431885f);
-  p = fmaf(p, f, 1.0f);
-  return __int_as_float(__float_as_int(p) + (__float_as_int(xr) << 23));
-}
-__device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t (&r)[32]) {
-  asm volatile(
-      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
-      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
-      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
-      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
-      "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]),
-      "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]),
-      "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
-      : "memory");
-}
-__device__ __forceinline__ void tmem_st_32x16(uint32_t taddr, const uint32_t (&r)[16]) {
-  asm volatile(
-      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
-      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
-      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
-      "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
-      : "memory");
-}
-// 16-byte store of 8 bf16 into a [rows x 128 B] SWIZZLE_128B tile (row r, 16-byte chunk c of 8)
-__device__ __forceinline__ void st_sw128(uint8_t* tile, int r, int c, uint4 v) {
-  *reinterpret_cast<uint4*>(tile + r * 128 + ((c ^ (r & 7)) << 4)) = v;
-}
-
-#ifndef B200_ATTN_POLY
-#define B200_ATTN_POLY 1
-#endif
-constexpr int kPolyPairsOf4 = B200_ATTN_POLY;  // of every 4 column pairs, how many use ex2_poly (0 = all MUFU)
-constexpr float kLog2e = 1.4426950408889634f;
-constexpr float kLn2 = 0.6931471805599453f;
 
 // =================================================================================================
 // forward
 // =================================================================================================
-struct AttnFwdArgs {
-  bf16* o0;
-  int ld0;
-  bf16* o1;
-  int ld1;
-  float* lse;
-  int B, H, L, split;
-  float scale;
-};
-
 constexpr int kFwdSmem = 1024 + 32768 + 2 * 32768 + 2 * 32768 + 16 * 8 + 16 + 2 * 2 * 128 * 4;
 constexpr int kAttnThreads = 320;  // TMA warp, MMA warp, 8 softmax warps (two per TMEM sub-partition)
 
@@ -635,17 +576,6 @@ __global__ void __launch_bounds__(256) attn_delta_kernel(const bf16* __restrict_
   *reinterpret_cast<uint2*>(dOh + hm * 128 + lane * 4) = ud;
 }
 
-struct AttnBwdArgs {
-  const float* lse;
-  const float* delta;
-  const bf16* r0;  // MODE_Q: Q  [B,H,L,128] (the stationary operands are read straight into TMEM)
-  const bf16* r1;  // MODE_Q: dO [B,H,L,128]
-  bf16* out0;  // MODE_KV: dV ; MODE_Q: dQ
-  bf16* out1;  // MODE_KV: dK
-  int L;
-  float scale;
-};
-
 constexpr int kBwdStages = 3;
 constexpr int kBwdSmem = 1024 + 2 * 32768 + kBwdStages * 32768 + 16 * 8 + 16 + 8 * 128 * 4;
 
@@ -979,10 +909,15 @@ extern "C" int b200_attn_fwd(b200_ctx* ctx, const void* Q, const void* K, const 
     B200_CUDA_CHECK(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwdSmem));
     B200_CUDA_CHECK(cudaFuncSetAttribute(attn_fwd2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwdSmem));
     const char* e = getenv("B200_ATTN_FWD");
-    if (e) variant = atoi(e) == 2 ? 2 : 1;
+    if (e) variant = (atoi(e) >= 2 && atoi(e) <= 4) ? atoi(e) : 1;  // 3, 4: opt-in round-2 candidates (attention_r2.cu)
     configured = true;
   }
   AttnFwdArgs a{(bf16*)o0, ld0, (bf16*)o1, ld1, (float*)lse, B, H, L, split, scale};
+  if (variant >= 3) {
+    if ((rc = attn_fwd_r2_launch(variant, tq, tk, tv, a, reinterpret_cast<cudaStream_t>(stream)))) return rc;
+    ctx->launches.fetch_add(1);
+    return B200_OK;
+  }
   dim3 grid((L + 127) / 128, B * H);
   if (variant == 1)
     attn_fwd_kernel<<<grid, kAttnThreads, kFwdSmem, reinterpret_cast<cudaStream_t>(stream)>>>(tq, tk, tv, a);
@@ -1020,16 +955,24 @@ extern "C" int b200_attn_bwd(b200_ctx* ctx, const void* Q, const void* K, const 
   if ((rc = attn_maps(ctx, V, rows, 64, &v64))) return rc;
   if ((rc = attn_maps(ctx, dOh, rows, 64, &d64))) return rc;
   static bool configured = false;
+  static int variant = 1;
   if (!configured) {
     B200_CUDA_CHECK(cudaFuncSetAttribute(attn_bwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdSmem));
     B200_CUDA_CHECK(cudaFuncSetAttribute(attn_bwd_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdSmem));
+    const char* e = getenv("B200_ATTN_BWD");
+    if (e && (atoi(e) == 2 || atoi(e) == 3)) variant = atoi(e);  // opt-in round-2 candidates (attention_r2.cu)
     configured = true;
   }
   dim3 grid((L + 127) / 128, B * H);
   AttnBwdArgs akv{(const float*)lse, (const float*)delta, nullptr, nullptr, (bf16*)dV, (bf16*)dK, L, scale};
+  AttnBwdArgs aq{(const float*)lse, (const float*)delta, (const bf16*)Q, (const bf16*)dOh, (bf16*)dQ, nullptr, L, scale};
+  if (variant >= 2) {
+    if ((rc = attn_bwd_r2_launch(variant, k128, v128, q64, d64, q128, d128, k64, v64, akv, aq, B, H, st))) return rc;
+    ctx->launches.fetch_add(3);
+    return B200_OK;
+  }
   attn_bwd_kernel<1><<<grid, kAttnThreads, kBwdSmem, st>>>(k128, v128, q64, d64, akv);
   B200_CUDA_CHECK(cudaGetLastError());
-  AttnBwdArgs aq{(const float*)lse, (const float*)delta, (const bf16*)Q, (const bf16*)dOh, (bf16*)dQ, nullptr, L, scale};
   attn_bwd_kernel<0><<<grid, kAttnThreads, kBwdSmem, st>>>(q128, d128, k64, v64, aq);
   B200_CUDA_CHECK(cudaGetLastError());
   ctx->launches.fetch_add(3);

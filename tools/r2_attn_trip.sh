@@ -1,0 +1,26 @@
+#!/bin/bash
+# Round-2, first GPU trip: parity + same-box timing of the opt-in attention candidates (csrc/attention_r2.cu).
+#   gpurun --timeout 1500 -- 'bash tools/r2_attn_trip.sh'
+# Every process runs under its own `timeout` (a barrier-protocol mistake ends in the 2.5 s mbarrier watchdog trap, not
+# in a hung box).  Output: gpurun_out/r2_attn_trip.log.  Promote a candidate to the default only if parity=OK on every
+# shape, tests/test_gpu_attention.py passes with it, and it is faster than variant 1 in THIS log.
+mkdir -p gpurun_out
+LOG=gpurun_out/r2_attn_trip.log
+: > $LOG
+run() { echo "== $*" >> $LOG; timeout 300 env "$@" >> $LOG 2>&1; echo "exit $?" >> $LOG; }
+# 1. baseline + each candidate alone: parity on ragged/short/long shapes, timing at the FLUX shape
+for v in "B200_ATTN_FWD=1 B200_ATTN_BWD=1" "B200_ATTN_FWD=3 B200_ATTN_BWD=1" "B200_ATTN_FWD=4 B200_ATTN_BWD=1" \
+         "B200_ATTN_FWD=1 B200_ATTN_BWD=3" "B200_ATTN_FWD=1 B200_ATTN_BWD=2"; do
+  run $v python tools/time_attn_variants.py 88 320 1000 4608
+done
+# 2. the unit tests (ragged tails, split = 0, large scores that force the lazy rescale) with each candidate
+for v in "B200_ATTN_FWD=3 B200_ATTN_BWD=3" "B200_ATTN_FWD=4 B200_ATTN_BWD=2"; do
+  run $v python -m pytest tests/test_gpu_attention.py -x -q -p no:cacheprovider
+done
+# 3. best-looking pairs through the whole step (parity of the engine + bench line)
+for v in "B200_ATTN_FWD=3 B200_ATTN_BWD=3" "B200_ATTN_FWD=4 B200_ATTN_BWD=2"; do
+  run $v python -m pytest tests/test_gpu_flux_engine.py -x -q -p no:cacheprovider -k "golden or parity or rank"
+  run $v python bench.py --steps 10 --warmup 3
+done
+run B200_ATTN_FWD=1 B200_ATTN_BWD=1 python bench.py --steps 10 --warmup 3
+grep -E "^\[|exit|passed|failed|\"value\"" $LOG | cut -c1-260
