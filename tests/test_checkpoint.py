@@ -1,0 +1,127 @@
+"""Save / resume conventions: file naming, metadata, optimizer.pt, pruning of old saves, latest-path
+selection — and interchange with the LIVE reference (its metadata reader, its network loader, torch AdamW)."""
+import os
+import time
+
+import pytest
+import torch
+
+from ai_toolkit_b200 import LoRASpecialNetwork, checkpoint as ck
+from ai_toolkit_b200.flux import FluxConfig, FluxTransformer2DModel
+from ai_toolkit_b200.optimizer import B200AdamW
+from oracle import ref_import
+
+CFG = dict(num_layers=1, num_single_layers=1, num_attention_heads=2, joint_attention_dim=64, pooled_projection_dim=32)
+KW = dict(text_encoder=None, alpha=None, train_unet=True, train_text_encoder=False, is_flux=True, network_type="lora",
+          transformer_only=True)
+
+
+def _net(rank=4, seed=0):
+    torch.manual_seed(seed)
+    model = FluxTransformer2DModel(FluxConfig(**CFG), dtype=torch.float32)
+    kw = dict(KW, alpha=rank)
+    net = LoRASpecialNetwork(unet=model, lora_dim=rank, **kw)
+    net.force_to("cpu", torch.float32)
+    net._update_torch_multiplier()
+    net.apply_to(None, model, False, True)
+    with torch.no_grad():
+        for l in net.unet_loras:
+            l.lora_up.weight.normal_(0, 0.1)
+    return model, net
+
+
+def test_save_naming_metadata_pruning_and_latest(tmp_path):
+    root = str(tmp_path / "out")
+    _, net = _net()
+    opt = B200AdamW(net, lr=2e-4)
+    opt.state_buf[0] = 3
+    net.multiplier = 0.5
+    paths = []
+    for step in (100, 200, 300):
+        paths.append(ck.save_checkpoint(net, opt, root, "my_lora", step=step, epoch=1, dtype=torch.float16,
+                                        max_step_saves_to_keep=2))
+        time.sleep(0.02)  # distinct ctimes
+    assert net.multiplier == 0.5  # restored after saving at 1.0 (BaseSDTrainProcess.py:544-556)
+    assert os.path.basename(paths[0]) == "my_lora_000000100.safetensors"
+    assert sorted(os.listdir(root)) == ["my_lora_000000200.safetensors", "my_lora_000000300.safetensors", "optimizer.pt"]
+    meta = ck.load_metadata_from_safetensors(paths[2])
+    assert meta["training_info"] == {"step": 300, "epoch": 1} and meta["ss_output_name"] == "my_lora"
+    assert meta["format"] == "pt" and meta["software"]["name"] and len(meta["sshs_legacy_hash"]) == 8
+    assert ck.get_latest_save_path(root, "my_lora") == paths[2]
+    assert ck.load_training_state_from_metadata(paths[2]) == (300, 1)
+    # false positives: another run's `_LoRA` files share the prefix and must not be picked up (:843-851)
+    final = ck.save_checkpoint(net, None, root, "my_lora", step=None, named_lora=True)
+    assert os.path.basename(final) == "my_lora_LoRA.safetensors"
+    assert ck.get_latest_save_path(root, "my_lora") == paths[2]
+    assert ck.get_latest_save_path(root, "my_lora_LoRA") == final
+    # nothing saved yet -> the pretrained LoRA is the start point, and its metadata is NOT a resume state (:868-872)
+    empty = str(tmp_path / "empty")
+    assert ck.get_latest_save_path(empty, "x") is None
+    assert ck.get_latest_save_path(empty, "x", pretrained_lora_path=paths[2]) == paths[2]
+    assert ck.load_training_state_from_metadata(paths[2], pretrained_lora_path=paths[2]) is None
+
+
+def test_resume_restores_weights_step_and_optimizer_but_keeps_configured_lr(tmp_path):
+    root = str(tmp_path / "run")
+    _, net = _net(seed=1)
+    opt = B200AdamW(net, lr=2e-4)
+    opt.exp_avg.normal_()
+    opt.exp_avg_sq.uniform_()
+    opt.state_buf[0] = 41
+    ck.save_checkpoint(net, opt, root, "r", step=41, epoch=2, dtype=torch.float32)
+    _, net2 = _net(seed=2)
+    opt2 = B200AdamW(net2, lr=5e-5)
+    path, step, epoch = ck.resume(net2, opt2, root, "r")
+    assert (step, epoch) == (41, 2) and path.endswith("r_000000041.safetensors")
+    for a, b in zip(net.unet_loras, net2.unet_loras):
+        assert torch.equal(a.lora_up.weight, b.lora_up.weight) and torch.equal(a.lora_down.weight, b.lora_down.weight)
+    assert torch.equal(opt2.exp_avg, opt.exp_avg) and int(opt2.state_buf[0]) == 41
+    assert opt2.param_groups[0]["lr"] == 5e-5 and abs(float(opt2.hyper[0]) - 5e-5) < 1e-11  # :2215-2218
+    # a rank change on load invalidates the optimizer state: it must not be loaded (:2200-2205)
+    _, net3 = _net(rank=8, seed=3)
+    opt3 = B200AdamW(net3, lr=1e-4)
+    _, step3, _ = ck.resume(net3, opt3, root, "r")
+    assert net3.did_change_weights and step3 == 41 and float(opt3.exp_avg.abs().sum()) == 0.0
+
+
+@pytest.mark.skipif(not ref_import.available(), reason="reference tree not present (GPU box)")
+def test_checkpoint_interchange_with_live_reference(tmp_path):
+    from oracle import flux_ref
+
+    ref_import.install()
+    from toolkit.metadata import load_metadata_from_safetensors as ref_load_meta  # the reference's own reader
+
+    RefNet, _ = ref_import.reference_lora()
+    root = str(tmp_path / "x")
+    _, net = _net(seed=5)
+    opt = B200AdamW(net, lr=1e-4, eps=1e-6)
+    opt.exp_avg.normal_()
+    opt.exp_avg_sq.uniform_()
+    opt.state_buf[0] = 9
+    path = ck.save_checkpoint(net, opt, root, "job", step=9, dtype=torch.float32)
+    # 1. the reference reads our metadata the way load_training_state_from_metadata does (:883-889)
+    meta = ref_load_meta(path)
+    assert meta["training_info"]["step"] == 9 and dict(meta) == dict(ck.load_metadata_from_safetensors(path))
+    # 2. the reference network loads our file
+    m1 = flux_ref.FluxTransformer2DModel(flux_ref.FluxConfig(**CFG))
+    r = RefNet(unet=m1, lora_dim=4, **dict(KW, alpha=4))
+    r.force_to("cpu", torch.float32); r._update_torch_multiplier(); r.apply_to(None, m1, False, True)
+    r.load_weights(path)
+    for a, b in zip(net.unet_loras, r.unet_loras):
+        assert a.lora_name == b.lora_name
+        assert torch.equal(a.lora_up.weight, b.lora_up.weight) and torch.equal(a.lora_down.weight, b.lora_down.weight)
+    # 3. torch.optim.AdamW over the reference network's parameter groups loads our optimizer.pt (:2209-2211)
+    ref_opt = torch.optim.AdamW(r.prepare_optimizer_params(1e-4, 1e-4, 1e-4), lr=1e-4, eps=1e-6)
+    ref_opt.load_state_dict(torch.load(os.path.join(root, "optimizer.pt"), weights_only=True))
+    p0 = ref_opt.param_groups[0]["params"][0]
+    assert float(ref_opt.state[p0]["step"]) == 9.0
+    assert torch.equal(ref_opt.state[p0]["exp_avg"].reshape(-1), opt.exp_avg[:p0.numel()])
+    # 4. and back: a file written by the reference network resumes here
+    r.save_weights(os.path.join(root, "job_000000010.safetensors"), dtype=torch.float32,
+                   metadata=ck.get_meta_for_safetensors(ck.training_metadata("job", 10), "job"))
+    time.sleep(0.02)
+    _, net2 = _net(seed=6)
+    p, step, _ = ck.resume(net2, None, root, "job")
+    assert p.endswith("job_000000010.safetensors") and step == 10
+    for a, b in zip(net2.unet_loras, r.unet_loras):
+        assert torch.equal(a.lora_up.weight, b.lora_up.weight)
