@@ -102,7 +102,8 @@ __global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ g,
 
 // hyper: [0] lr, [1] beta1, [2] beta2, [3] eps, [4] weight_decay, [5] max_norm (<=0: no clipping),
 //        [6] ema_decay (<=0: no EMA), [7] grad_prescale (e.g. 1/world when the all-reduce summed)
-// state: 64 bytes; int64 [0] = optimizer steps taken so far; floats at byte 16: derived per-step scalars
+// state: 64 bytes; int64 [0] = optimizer steps taken so far; int64 [1] != 0: EMA warm-up (use_num_updates); floats at
+//        byte 16: derived per-step scalars
 //        d[0] grad scale (clip * prescale), d[1] step_size = lr / (1 - b1^t), d[2] sqrt(1 - b2^t),
 //        d[3] EMA decay of this step, d[4] total grad norm (after prescale, before clipping)
 __global__ void adamw_prepare_kernel(const double* __restrict__ sumsq, const float* __restrict__ hyper, long long* state,
@@ -118,8 +119,11 @@ __global__ void adamw_prepare_kernel(const double* __restrict__ sumsq, const flo
   d[0] = clip * pre;
   d[1] = static_cast<float>(lr / (1.0 - pow(b1, static_cast<double>(step))));
   d[2] = static_cast<float>(sqrt(1.0 - pow(b2, static_cast<double>(step))));
-  const float nn = static_cast<float>(step);  // num_updates after its increment (toolkit/ema.py:108-111)
-  d[3] = ema_decay > 0.f ? fminf(ema_decay, (1.0f + nn) / (10.0f + nn)) : 0.f;
+  // toolkit/ema.py:121-128: the warm-up min(decay, (1 + n) / (10 + n)) exists only with `use_num_updates=True`; the
+  // trainer builds its EMA without it (BaseSDTrainProcess.py:798-803), so the default (state[1] == 0) is a constant decay
+  const float nn = static_cast<float>(step);  // num_updates after its increment
+  const bool warm_up = state[1] != 0;
+  d[3] = ema_decay > 0.f ? (warm_up ? fminf(ema_decay, (1.0f + nn) / (10.0f + nn)) : ema_decay) : 0.f;
   d[4] = total_norm;
   if (norm_out) *norm_out = total_norm;
 }

@@ -16,7 +16,7 @@ from . import ops
 
 class B200AdamW(torch.optim.Optimizer):
     def __init__(self, network, lr=1e-4, betas=(0.9, 0.999), eps=1e-6, weight_decay=1e-2, max_grad_norm=1.0,
-                 ema_decay=0.0, grad_prescale=1.0):
+                 ema_decay=0.0, grad_prescale=1.0, ema_use_num_updates=False):
         if network.flat_params is None:
             network._flatten()
         self.network = network
@@ -32,6 +32,10 @@ class B200AdamW(torch.optim.Optimizer):
         self.grad_prescale = float(grad_prescale)
         self.hyper = torch.zeros(8, device=dev, dtype=torch.float32)
         self.state_buf = torch.zeros(8, device=dev, dtype=torch.int64)  # 64 bytes: step counter + derived scalars
+        # ExponentialMovingAverage(use_num_updates=...): the trainer leaves it False = constant decay
+        # (BaseSDTrainProcess.py:798-803); True = warm-up min(decay, (1 + n) / (10 + n)) (toolkit/ema.py:121-128)
+        self.ema_use_num_updates = bool(ema_use_num_updates)
+        self.state_buf[1] = int(self.ema_use_num_updates)
         self.sumsq = torch.zeros(1, device=dev, dtype=torch.float64)
         self.grad_norm = torch.zeros(1, device=dev, dtype=torch.float32)
         self._hyper_host = None
@@ -93,6 +97,7 @@ class B200AdamW(torch.optim.Optimizer):
             off += n
         self.state_buf.zero_()
         self.state_buf[0] = step
+        self.state_buf[1] = int(self.ema_use_num_updates)
         g = sd["param_groups"][0]
         self.param_groups[0].update({k: g[k] for k in ("lr", "betas", "eps", "weight_decay") if k in g})
         self._hyper_host = None
@@ -113,6 +118,7 @@ class B200AdamW(torch.optim.Optimizer):
             self.ema.copy_(sd["ema"])
         self.state_buf.zero_()
         self.state_buf[0] = int(sd["step"])
+        self.state_buf[1] = int(self.ema_use_num_updates)
         for g, saved in zip(self.param_groups, sd["param_groups"]):
             g.update(saved)
         self._hyper_host = None

@@ -211,10 +211,12 @@ int b200_flow_loss(b200_ctx* ctx, const void* pred, const void* latents, const v
  * b200_grad_sumsq: *sumsq_f64 = sum g^2.
  * b200_clip_adamw: total_norm = sqrt(sumsq) * hyper[7]; g *= min(1, max_norm / (total_norm + 1e-6))
  *   (accelerator.clip_grad_norm_, SDTrainer.py:2278-2283); torch.optim.AdamW update with decoupled weight
- *   decay (toolkit/optimizer.py:78-79); optional EMA shadow -= (1 - decay_t)(shadow - p) with
- *   decay_t = min(decay, (1 + n) / (10 + n)) (toolkit/ema.py:100-152).
+ *   decay (toolkit/optimizer.py:78-79); optional EMA shadow -= (1 - decay_t)(shadow - p) (toolkit/ema.py:100-152)
+ *   with decay_t = decay, as the trainer builds it (BaseSDTrainProcess.py:798-803), or
+ *   decay_t = min(decay, (1 + n) / (10 + n)) when state int64[1] != 0 (`use_num_updates=True`).
  *   hyper fp32[8] (device): lr, beta1, beta2, eps, weight_decay, max_norm, ema_decay, grad_prescale.
- *   state (device, 64 bytes, zero-initialised): int64 step counter + per-step derived scalars.
+ *   state (device, 64 bytes, zero-initialised): int64[0] step counter, int64[1] EMA warm-up flag, then per-step
+ *   derived scalars.
  *   28 bytes per parameter (36 with EMA).
  * b200_repack_lora: bf16 padded operand copies of the fp32 masters; table = n_entries x
  *   {int64 src_off, int64 dst_off, int32 rows, cols, dst_ld, pad}.
