@@ -125,3 +125,29 @@ def test_checkpoint_interchange_with_live_reference(tmp_path):
     assert p.endswith("job_000000010.safetensors") and step == 10
     for a, b in zip(net2.unet_loras, r.unet_loras):
         assert torch.equal(a.lora_up.weight, b.lora_up.weight)
+
+
+@pytest.mark.skipif(not ref_import.available(), reason="reference tree not present (GPU box)")
+def test_metadata_and_hashes_identical_to_live_reference():
+    """`get_meta_for_safetensors` flattening and the sshs hashes (toolkit/metadata.py:13-46, train_tools.py:162-185)
+    computed by the reference's own functions on the same state dict."""
+    import copy
+    from collections import OrderedDict
+
+    ref_import.install()
+    from toolkit import metadata as ref_meta
+
+    from ai_toolkit_b200 import metadata as my_meta
+
+    torch.manual_seed(0)
+    sd = OrderedDict((f"transformer.blocks.{i}.q.lora_{ab}.weight", torch.randn(*shape).half())
+                     for i in range(3) for ab, shape in (("A", (4, 4096)), ("B", (4096, 4))))  # > 1 MiB: legacy hash window
+    meta = OrderedDict(training_info=OrderedDict(step=7, epoch=1), ss_output_name="[name]_v1", ss_base_model_version="flux.1",
+                       nested=dict(a=[1, 2], b="x"))
+    want = ref_meta.get_meta_for_safetensors(copy.deepcopy(meta), name="job", add_software_info=False)
+    got = my_meta.get_meta_for_safetensors(copy.deepcopy(meta), name="job", add_software_info=False)
+    assert got == want and got["ss_output_name"] == "job_v1" and got["format"] == "pt"
+    want = ref_meta.add_model_hash_to_meta(sd, copy.deepcopy(want))
+    got = my_meta.add_model_hash_to_meta(sd, copy.deepcopy(got))
+    assert got["sshs_model_hash"] == want["sshs_model_hash"] and got["sshs_legacy_hash"] == want["sshs_legacy_hash"]
+    assert ck.parse_metadata_from_safetensors(got) == ref_meta.parse_metadata_from_safetensors(want)

@@ -238,3 +238,61 @@ def test_kohya_format_identical_to_live_reference():
     for k in sr:
         assert torch.equal(sr[k], sn[k]), k
     assert [l.scale for l in r.unet_loras] == [l.scale for l in n.unet_loras]
+
+
+@pytest.mark.skipif(not ref_import.available(), reason="reference tree not present (GPU box)")
+def test_rank_change_merge_and_multiplier_identical_to_live_reference(tmp_path):
+    """Numbers, not just shapes: a rank-4 file loaded into rank-8 / rank-2 networks, merge_in / merge_out of the frozen
+    weights, and the multiplier tensor, next to the UNMODIFIED reference network doing the same
+    (toolkit/network_mixins.py:737-775, :370-462, :790-846)."""
+    from oracle import flux_ref
+
+    RefNet, _ = ref_import.reference_lora()
+    kw = dict(text_encoder=None, train_unet=True, train_text_encoder=False, is_flux=True, network_type="lora",
+              transformer_only=True)
+
+    def pair(rank, seed):
+        torch.manual_seed(seed)
+        m1 = flux_ref.FluxTransformer2DModel(flux_ref.FluxConfig(**CFG))
+        m2 = FluxTransformer2DModel(FluxConfig(**CFG), dtype=torch.float32)
+        m2.load_state_dict(m1.state_dict())
+        torch.manual_seed(seed + 1)
+        r = RefNet(unet=m1, lora_dim=rank, alpha=rank, **kw)
+        r.force_to("cpu", torch.float32); r._update_torch_multiplier(); r.apply_to(None, m1, False, True)
+        torch.manual_seed(seed + 1)
+        n = LoRASpecialNetwork(unet=m2, lora_dim=rank, alpha=rank, **kw)
+        n.force_to("cpu", torch.float32); n._update_torch_multiplier(); n.apply_to(None, m2, False, True)
+        return m1, r, m2, n
+
+    _, r4, _, n4 = pair(4, 10)
+    with torch.no_grad():
+        for a, b in zip(r4.unet_loras, n4.unet_loras):
+            a.lora_up.weight.normal_(0, 0.1)
+            b.lora_up.weight.copy_(a.lora_up.weight)
+    f = str(tmp_path / "r4.safetensors")
+    r4.save_weights(f, dtype=torch.float32)
+    for rank in (8, 2):  # expand with zero rows / columns, shrink by truncation
+        m1, r, m2, n = pair(rank, 20 + rank)
+        r.load_weights(f)
+        n.load_weights(f)
+        assert r.did_change_weights and n.did_change_weights
+        for a, b in zip(r.unet_loras, n.unet_loras):
+            assert torch.equal(a.lora_down.weight, b.lora_down.weight) and torch.equal(a.lora_up.weight, b.lora_up.weight)
+        # merge into the frozen weights and back out
+        for mw in (1.0, 0.35):
+            r.merge_in(mw)
+            n.merge_in(mw)
+            assert r.is_merged_in and n.is_merged_in
+            sd1, sd2 = m1.state_dict(), m2.state_dict()
+            for k in sd1:
+                assert torch.equal(sd1[k], sd2[k]), (rank, mw, k)
+            r.merge_out(mw)
+            n.merge_out(mw)
+            sd1, sd2 = m1.state_dict(), m2.state_dict()
+            for k in sd1:
+                assert torch.equal(sd1[k], sd2[k]), (rank, mw, k)
+        # multiplier -> tensor
+        for val in (0.5, [1.0, -1.0, 0.25], torch.tensor([2.0, 0.0])):
+            r.multiplier = val
+            n.multiplier = val
+            assert torch.equal(r.torch_multiplier, n.torch_multiplier) and r.torch_multiplier.dtype == n.torch_multiplier.dtype
