@@ -1,0 +1,14 @@
+#!/bin/bash
+# Round-2 profile set.  Same as tools/gpu_profile_trip.sh plus a WARM-cache launch list: ncu flushes the caches before
+# every kernel by default, which makes each memory-bound kernel look as if its input came from HBM although the
+# producer has just written it into the 126 MB L2.  Shares in the two lists bracket the real in-graph share.
+mkdir -p gpurun_out
+timeout 900 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --cache-control none --csv \
+    --log-file gpurun_out/r2_step_launches_warm.csv python tools/profile_step.py > gpurun_out/profile_step_warm.log 2>&1
+echo "warm launch list exit $?"
+timeout 900 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv \
+    --log-file gpurun_out/r2_step_launches.csv python tools/profile_step.py > gpurun_out/profile_step.log 2>&1
+echo "cold launch list exit $?"
+python tools/summarize_launches.py gpurun_out/r2_step_launches_warm.csv > gpurun_out/r2_step_launches_warm.md
+python tools/summarize_launches.py gpurun_out/r2_step_launches.csv > gpurun_out/r2_step_launches.md
+head -20 gpurun_out/r2_step_launches_warm.md
