@@ -218,7 +218,7 @@ attn_fwd_nt_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       mx *= c2;  // c2 > 0: max and rounding commute
       float* xm = xch + (j & 1) * (NT * 128);
       xm[h * 128 + r] = mx;
-      named_bar_sync<128 * NT>(1);
+      named_bar_sync<32 * NT>(1 + q);  // only the NT warps that share these 32 rows (one named barrier per lane quarter)
       float m_new = m_used;
 #pragma unroll
       for (int t = 0; t < NT; ++t) m_new = fmaxf(m_new, xm[t * 128 + r]);
@@ -277,7 +277,7 @@ attn_fwd_nt_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     // combine the partial row sums
     float* xl = xch + (n_kv & 1) * (NT * 128);
     xl[h * 128 + r] = l_sum;
-    named_bar_sync<128 * NT>(1);
+    named_bar_sync<32 * NT>(1 + q);
     l_sum = 0.f;
 #pragma unroll
     for (int t = 0; t < NT; ++t) l_sum += xl[t * 128 + r];

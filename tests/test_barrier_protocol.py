@@ -17,6 +17,8 @@ def test_forward_lazy_pv_protocol(n_kv, n_soft, rescale):
     """attention_r2.cu `attn_fwd_nt_kernel`: per-buffer p_full / pv_done, lazy waits."""
     for seed in range(400):
         m.run_fwd(seed, n_kv=n_kv, n_soft=n_soft, lazy=True, double_p_full=True, rescale_prob=rescale)
+    for seed in range(400):  # the row-max exchange synchronises only the warps sharing a lane quarter (groups of 2)
+        m.run_fwd(seed, n_kv=n_kv, n_soft=4, lazy=True, double_p_full=True, rescale_prob=rescale, sync_group=2)
 
 
 def test_forward_round1_protocol():

@@ -146,7 +146,9 @@ class Sim:
 # ---------------------------------------------------------------------------------------------------------------------
 # forward: attention_r2.cu attn_fwd_nt_kernel (lazy P V waits) and its single-p_full variant (the bug it avoids)
 # ---------------------------------------------------------------------------------------------------------------------
-def run_fwd(seed, n_kv=7, n_soft=3, lazy=True, double_p_full=True, rescale_prob=0.3):
+def run_fwd(seed, n_kv=7, n_soft=3, lazy=True, double_p_full=True, rescale_prob=0.3, sync_group=None):
+    """`sync_group`: size of the groups that exchange the row maximum through a named barrier (None = all softmax agents,
+    as in attention.cu; attention_r2.cu synchronises only the NT warps that share a lane quarter)."""
     sim = Sim(seed)
     B = lambda n, c: Barrier(n, c)  # noqa: E731
     k_full, k_empty = [B(f"k_full{s}", 1) for s in (0, 1)], [B(f"k_empty{s}", 1) for s in (0, 1)]
@@ -221,7 +223,8 @@ def run_fwd(seed, n_kv=7, n_soft=3, lazy=True, double_p_full=True, rescale_prob=
                 st["S_read"][s].add(w)
             yield ("do", load_S)
             yield ("arrive", s_empty[s])
-            yield ("sync", ("max", j), n_soft)  # bar.sync: row-max exchange
+            g = sync_group or n_soft
+            yield ("sync", ("max", j, w // g), min(g, n_soft - (w // g) * g))  # bar.sync: row-max exchange
             if not lazy and j > 0:
                 yield ("wait", pv_done[0], (j - 1) & 1, j - 1)
             if j > 0 and lazy and rng.random() < rescale_prob:
