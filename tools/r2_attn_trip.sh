@@ -19,7 +19,7 @@ for v in "B200_ATTN_FWD=3 B200_ATTN_BWD=3" "B200_ATTN_FWD=4 B200_ATTN_BWD=2"; do
 done
 # 3. best-looking pairs through the whole step (parity of the engine + bench line)
 for v in "B200_ATTN_FWD=3 B200_ATTN_BWD=3" "B200_ATTN_FWD=4 B200_ATTN_BWD=2"; do
-  run $v python -m pytest tests/test_gpu_flux_engine.py -x -q -p no:cacheprovider -k "golden or parity or rank"
+  run $v python -m pytest tests/test_gpu_flux_engine.py -x -q -p no:cacheprovider -k "oracle or golden"
   run $v python bench.py --steps 10 --warmup 3
 done
 run B200_ATTN_FWD=1 B200_ATTN_BWD=1 python bench.py --steps 10 --warmup 3
