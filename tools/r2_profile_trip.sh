@@ -12,3 +12,6 @@ echo "cold launch list exit $?"
 python tools/summarize_launches.py gpurun_out/r2_step_launches_warm.csv > gpurun_out/r2_step_launches_warm.md
 python tools/summarize_launches.py gpurun_out/r2_step_launches.csv > gpurun_out/r2_step_launches.md
 head -20 gpurun_out/r2_step_launches_warm.md
+# decision input for folding dQ into the dK/dV kernel: L2 reduction throughput (see the header of the .cu file)
+nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o gpurun_out/bulk_reduce tools/microbench/bulk_reduce.cu \
+  && timeout 120 gpurun_out/bulk_reduce > gpurun_out/r2_bulk_reduce.log 2>&1; echo "bulk_reduce exit $?"; cat gpurun_out/r2_bulk_reduce.log
