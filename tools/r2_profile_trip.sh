@@ -15,3 +15,5 @@ head -20 gpurun_out/r2_step_launches_warm.md
 # decision input for folding dQ into the dK/dV kernel: L2 reduction throughput (see the header of the .cu file)
 nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o gpurun_out/bulk_reduce tools/microbench/bulk_reduce.cu \
   && timeout 120 gpurun_out/bulk_reduce > gpurun_out/r2_bulk_reduce.log 2>&1; echo "bulk_reduce exit $?"; cat gpurun_out/r2_bulk_reduce.log
+# rank-side (N = 64) GEMMs with a hot L2, persistent vs cluster split-K: the cold-cache launch list overstates them
+timeout 300 python tools/time_skinny.py > gpurun_out/r2_time_skinny.log 2>&1; echo "time_skinny exit $?"; cat gpurun_out/r2_time_skinny.log
