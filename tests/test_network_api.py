@@ -296,3 +296,58 @@ def test_rank_change_merge_and_multiplier_identical_to_live_reference(tmp_path):
             r.multiplier = val
             n.multiplier = val
             assert torch.equal(r.torch_multiplier, n.torch_multiplier) and r.torch_multiplier.dtype == n.torch_multiplier.dtype
+
+
+@pytest.mark.skipif(not ref_import.available(), reason="reference tree not present (GPU box)")
+def test_text_encoder_and_unet_construction_identical_to_live_reference():
+    """CLIP text encoder(s) + UNet with DEFAULT target lists (the reference takes kohya's: CLIPAttention / CLIPMLP,
+    Transformer2DModel): adapter names (`lora_te_`, `lora_te1_/te2_`, `lora_unet_`), kaiming draws, scale = alpha / rank,
+    optimizer parameter groups with their learning rates (toolkit/lora_special.py:346-470, :644-700)."""
+    from transformers import CLIPTextConfig, CLIPTextModel
+
+    RefNet, _ = ref_import.reference_lora()
+    cfg = CLIPTextConfig(hidden_size=32, intermediate_size=64, num_hidden_layers=2, num_attention_heads=2, vocab_size=100,
+                         max_position_embeddings=16)
+    kw = dict(lora_dim=4, alpha=2, train_unet=True, train_text_encoder=True)
+
+    def build(cls, n_te):
+        torch.manual_seed(0)
+        tes = [CLIPTextModel(cfg) for _ in range(n_te)]
+        unet = _toy_unet()
+        torch.manual_seed(1)
+        return cls(text_encoder=tes[0] if n_te == 1 else tes, unet=unet, **kw)
+
+    for n_te in (1, 2):
+        r, n = build(RefNet, n_te), build(LoRASpecialNetwork, n_te)
+        ra, na = r.text_encoder_loras + r.unet_loras, n.text_encoder_loras + n.unet_loras
+        assert [l.lora_name for l in ra] == [l.lora_name for l in na] and len(r.text_encoder_loras) == 12 * n_te
+        assert na[0].lora_name.startswith("lora_te_" if n_te == 1 else "lora_te1_")
+        for a, b in zip(ra, na):
+            assert torch.equal(a.lora_down.weight, b.lora_down.weight) and a.scale == b.scale == 0.5
+        g1, g2 = r.prepare_optimizer_params(1e-5, 2e-4, 1e-4), n.prepare_optimizer_params(1e-5, 2e-4, 1e-4)
+        assert [(g["lr"], len(g["params"])) for g in g1] == [(g["lr"], len(g["params"])) for g in g2]
+
+
+@pytest.mark.skipif(not ref_import.available(), reason="reference tree not present (GPU box)")
+@pytest.mark.parametrize("opts", [
+    dict(transformer_only=True), dict(transformer_only=False), dict(transformer_only=True, attn_only=True),
+    dict(transformer_only=True, only_if_contains=["transformer_blocks.1.", "single_transformer_blocks.0."]),
+    dict(transformer_only=True, ignore_if_contains=["norm", "ff"]), dict(transformer_only=True, parameter_threshold=5000.0),
+    dict(transformer_only=False, only_if_contains=["x_embedder", "proj_out"]),
+    dict(transformer_only=True, target_lin_modules=["FluxTransformerBlock"]), dict(transformer_only=True, is_transformer=True),
+    dict(transformer_only=True, peft_format=False)], ids=lambda o: ",".join(f"{k}" for k in o))
+def test_module_selection_options_identical_to_live_reference(opts):
+    """Which Linear layers get an adapter, in which order, under the selection options of the constructor
+    (toolkit/lora_special.py:346-470): identical name lists, format flag and scales next to the live reference."""
+    from oracle import flux_ref
+
+    RefNet, _ = ref_import.reference_lora()
+    cfg = dict(CFG, num_layers=2, num_single_layers=2)
+    base = dict(text_encoder=None, lora_dim=4, alpha=4, train_unet=True, train_text_encoder=False, is_flux=True,
+                network_type="lora")
+    torch.manual_seed(0)
+    r = RefNet(unet=flux_ref.FluxTransformer2DModel(flux_ref.FluxConfig(**cfg)), **base, **opts)
+    torch.manual_seed(0)
+    n = LoRASpecialNetwork(unet=FluxTransformer2DModel(FluxConfig(**cfg), dtype=torch.float32), **base, **opts)
+    assert [l.lora_name for l in r.unet_loras] == [l.lora_name for l in n.unet_loras]
+    assert r.peft_format == n.peft_format and [float(l.scale) for l in r.unet_loras] == [float(l.scale) for l in n.unet_loras]
