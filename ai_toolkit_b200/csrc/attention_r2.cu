@@ -22,6 +22,8 @@
 //        * S / dP read in 16-column chunks, the next chunk in flight while the current one is computed;
 //        * NH = 2: thread (row, hh) owns columns [32 hh, 32 hh + 32) and writes its bf16 P / dS pairs inside its own
 //          range (columns 48 hh ...), so no thread overwrites what another still reads.
+#include <type_traits>
+
 #include "attn_common.cuh"
 
 namespace b200 {
@@ -559,17 +561,11 @@ attn_bwd_r2_kernel(const __grid_constant__ CUtensorMap tmR0, const __grid_consta
       uint32_t pp[CW / 2], dd[CW / 2];             // packed bf16 pairs of my columns: P and dS
       uint32_t sv[2][16], dv[2][16];               // two chunks in flight (ping-pong)
       const uint32_t cs = X0(gq) + lane_off + hh * CW, cd = X1(gq) + lane_off + hh * CW;
-      tmem_ld_32x16(cs, sv[0]);
-      tmem_ld_32x16(cd, dv[0]);
-#pragma unroll
-      for (int ch = 0; ch < NCH; ++ch) {
-        tmem_ld_wait();  // chunk ch has arrived
-        if (ch + 1 < NCH) {  // next chunk in flight while this one is computed (tcgen05.ld is asynchronous until wait::ld)
-          tmem_ld_32x16(cs + (ch + 1) * 16, sv[(ch + 1) & 1]);
-          tmem_ld_32x16(cd + (ch + 1) * 16, dv[(ch + 1) & 1]);
-        }
-        const uint32_t(&s16)[16] = sv[ch & 1];
-        const uint32_t(&d16)[16] = dv[ch & 1];
+      // P = exp2(S c2 - lse2), dS = P (dP scale - delta scale) for 16 columns, as packed fp32 pairs (FFMA2 / FMUL2).
+      // MASKED is only instantiated for the ragged last tile: the selects cost 20 % of the loop when always executed.
+      const float2 c22 = make_float2(c2, c2), sc2 = make_float2(g.scale, g.scale);
+      auto chunk = [&](auto masked_tag, const uint32_t(&s16)[16], const uint32_t(&d16)[16], int ch) {
+        constexpr bool MASKED = decltype(masked_tag)::value;
 #pragma unroll
         for (int k = 0; k < 16; k += 4) {
           float l4[4], d4[4];
@@ -583,20 +579,40 @@ attn_bwd_r2_kernel(const __grid_constant__ CUtensorMap tmR0, const __grid_consta
               d4[e] = my_dls;
             }
           }
-          float p4[4], s4[4];
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            float p = ex2(__uint_as_float(s16[k + e]) * c2 - l4[e]);
-            if (nvalid < CW) p = (ch * 16 + k + e < nvalid) ? p : 0.f;  // only the last tile has missing columns
-            p4[e] = p;
-            s4[e] = p * (__uint_as_float(d16[k + e]) * g.scale - d4[e]);
+          for (int e = 0; e < 4; e += 2) {
+            const float2 a = ffma2(make_float2(__uint_as_float(s16[k + e]), __uint_as_float(s16[k + e + 1])), c22,
+                                   make_float2(-l4[e], -l4[e + 1]));
+            float2 pr = make_float2(ex2(a.x), ex2(a.y));
+            if (MASKED) {
+              pr.x = (ch * 16 + k + e < nvalid) ? pr.x : 0.f;
+              pr.y = (ch * 16 + k + e + 1 < nvalid) ? pr.y : 0.f;
+            }
+            const float2 t = ffma2(make_float2(__uint_as_float(d16[k + e]), __uint_as_float(d16[k + e + 1])), sc2,
+                                   make_float2(-d4[e], -d4[e + 1]));
+            const float2 ds = fmul2(pr, t);
+            pp[ch * 8 + (k + e) / 2] = pack_bf16x2(pr.x, pr.y);
+            dd[ch * 8 + (k + e) / 2] = pack_bf16x2(ds.x, ds.y);
           }
-          pp[ch * 8 + k / 2] = pack_bf16x2(p4[0], p4[1]);
-          pp[ch * 8 + k / 2 + 1] = pack_bf16x2(p4[2], p4[3]);
-          dd[ch * 8 + k / 2] = pack_bf16x2(s4[0], s4[1]);
-          dd[ch * 8 + k / 2 + 1] = pack_bf16x2(s4[2], s4[3]);
         }
-      }
+      };
+      auto tile = [&](auto masked_tag) {
+        tmem_ld_32x16(cs, sv[0]);
+        tmem_ld_32x16(cd, dv[0]);
+#pragma unroll
+        for (int ch = 0; ch < NCH; ++ch) {
+          tmem_ld_wait();  // chunk ch has arrived
+          if (ch + 1 < NCH) {  // next chunk in flight while this one is computed (tcgen05.ld is asynchronous until wait::ld)
+            tmem_ld_32x16(cs + (ch + 1) * 16, sv[(ch + 1) & 1]);
+            tmem_ld_32x16(cd + (ch + 1) * 16, dv[(ch + 1) & 1]);
+          }
+          chunk(masked_tag, sv[ch & 1], dv[ch & 1], ch);
+        }
+      };
+      if (nvalid >= CW)  // warp-uniform
+        tile(std::false_type{});
+      else
+        tile(std::true_type{});
       // bf16 pairs back into TMEM INSIDE this thread's own column range (all of its loads have completed):
       //   NH = 1: columns 0..31        NH = 2: columns 48 hh .. 48 hh + 15
       const uint32_t wcol = hh * (64 - CW / 2);
