@@ -206,14 +206,12 @@ attn_fwd_nt_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       tc_fence_before();
       mbar_arrive(&s_empty[s]);  // S is in registers: the tensor core may overwrite this buffer
       const int nvalid = g.L - (j * 128 + h * CW);  // columns of my part that exist
-      float x[CW];                                  // RAW scores (masked columns = -inf); scaled inside the FFMA2 below
-      if (nvalid >= CW) {
+      if (nvalid < CW) {  // ragged last tile only: missing columns become -inf IN PLACE (no second copy of the row)
 #pragma unroll
-        for (int i = 0; i < CW; ++i) x[i] = __uint_as_float(v[i]);
-      } else {
-#pragma unroll
-        for (int i = 0; i < CW; ++i) x[i] = i < nvalid ? __uint_as_float(v[i]) : -INFINITY;
+        for (int i = 0; i < CW; ++i)
+          if (i >= nvalid) v[i] = 0xff800000u;
       }
+      const float* x = reinterpret_cast<const float*>(v);  // RAW scores; scaled inside the FFMA2 below
       float mx = -INFINITY;
 #pragma unroll
       for (int i = 0; i < CW; ++i) mx = fmaxf(mx, x[i]);
@@ -257,9 +255,7 @@ attn_fwd_nt_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       for (int k2 = 0; k2 < CW / 2; ++k2) {
         const bool poly = (k2 % 4) < kPolyPairsOf4R2;
         const float2 a = ffma2(make_float2(x[2 * k2], x[2 * k2 + 1]), c22, nm2);
-        float2 p2;
-        p2.x = poly ? ex2_poly(a.x) : ex2(a.x);
-        p2.y = poly ? ex2_poly(a.y) : ex2(a.y);
+        const float2 p2 = poly ? ex2_poly2(a) : make_float2(ex2(a.x), ex2(a.y));
         ls[k2 & 1] = fadd2(ls[k2 & 1], p2);
         pk[k2] = pack_bf16x2(p2.x, p2.y);
       }

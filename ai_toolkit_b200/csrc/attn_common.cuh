@@ -63,6 +63,14 @@ __device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
       : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
   return d;
 }
+__device__ __forceinline__ float2 fadd2_rm(float2 a, float2 b) {  // both lanes rounded towards -inf
+  float2 d;
+  asm("{\n\t.reg .b64 ra, rb, rd;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\t"
+      "add.rm.f32x2 rd, ra, rb;\n\tmov.b64 {%0, %1}, rd;\n\t}"
+      : "=f"(d.x), "=f"(d.y)
+      : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+  return d;
+}
 __device__ __forceinline__ float2 fmul2(float2 a, float2 b) {
   float2 d;
   asm("{\n\t.reg .b64 ra, rb, rd;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\t"
@@ -102,6 +110,21 @@ struct AttnBwdArgs {
   float scale;
 };
 
+
+// ex2_poly for a pair (same split and polynomial, packed instructions: 10 issue slots per pair instead of 16)
+__device__ __forceinline__ float2 ex2_poly2(float2 x) {
+  const float2 magic = make_float2(12582912.0f, 12582912.0f);
+  x.x = fmaxf(x.x, -126.0f);
+  x.y = fmaxf(x.y, -126.0f);
+  const float2 xr = fadd2_rm(x, magic);
+  const float2 f = fadd2(x, fadd2(magic, make_float2(-xr.x, -xr.y)));  // x - (xr - magic), both roundings exact
+  float2 p = ffma2(f, make_float2(0.077119089663028717f, 0.077119089663028717f),
+                   make_float2(0.227564394474029541f, 0.227564394474029541f));
+  p = ffma2(p, f, make_float2(0.695146143436431885f, 0.695146143436431885f));
+  p = ffma2(p, f, make_float2(1.0f, 1.0f));
+  return make_float2(__int_as_float(__float_as_int(p.x) + (__float_as_int(xr.x) << 23)),
+                     __int_as_float(__float_as_int(p.y) + (__float_as_int(xr.y) << 23)));
+}
 
 // opt-in round-2 candidates (attention_r2.cu); variant numbers are the values of B200_ATTN_FWD / B200_ATTN_BWD
 int attn_fwd_r2_launch(int variant, const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnFwdArgs& a,
