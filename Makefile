@@ -6,7 +6,22 @@ SRC := $(wildcard ai_toolkit_b200/csrc/*.cu)
 OBJ := $(patsubst ai_toolkit_b200/csrc/%.cu,build/%.o,$(SRC))
 LIB := ai_toolkit_b200/lib/libb200lora.so
 
-all: $(LIB)
+LIB_PDL := ai_toolkit_b200/lib/libb200lora_pdl.so
+OBJ_PDL := $(patsubst ai_toolkit_b200/csrc/%.cu,build_pdl/%.o,$(SRC))
+
+all: $(LIB) $(LIB_PDL)
+
+# opt-in variant: every launch carries the programmatic-stream-serialization attribute and every kernel waits with
+# griddepcontrol (common.cuh).  Not the default: select with B200_LIB=ai_toolkit_b200/lib/libb200lora_pdl.so
+pdl: $(LIB_PDL)
+
+build_pdl/%.o: ai_toolkit_b200/csrc/%.cu $(wildcard ai_toolkit_b200/csrc/*.cuh) $(wildcard ai_toolkit_b200/csrc/*.h) include/b200_lora.h
+	@mkdir -p build_pdl
+	$(NVCC) $(NVCCFLAGS) -DB200_PDL=1 -c $< -o $@ 2> build_pdl/$*.ptxas.log || (cat build_pdl/$*.ptxas.log; exit 1)
+
+$(LIB_PDL): $(OBJ_PDL)
+	@mkdir -p ai_toolkit_b200/lib
+	$(NVCC) $(ARCH) -shared -o $@ $(OBJ_PDL) -lcudart_static -ldl -lpthread -lrt
 
 build/%.o: ai_toolkit_b200/csrc/%.cu $(wildcard ai_toolkit_b200/csrc/*.cuh) $(wildcard ai_toolkit_b200/csrc/*.h) include/b200_lora.h
 	@mkdir -p build
@@ -17,5 +32,5 @@ $(LIB): $(OBJ)
 	$(NVCC) $(ARCH) -shared -o $@ $(OBJ) -lcudart_static -ldl -lpthread -lrt
 
 clean:
-	rm -rf build $(LIB)
-.PHONY: all clean
+	rm -rf build build_pdl $(LIB) $(LIB_PDL)
+.PHONY: all pdl clean

@@ -28,6 +28,7 @@ constexpr int kAttnThreads = 320;  // TMA warp, MMA warp, 8 softmax warps (two p
 __global__ void __launch_bounds__(kAttnThreads, 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                 const __grid_constant__ CUtensorMap tmV, const AttnFwdArgs g) {
+  pdl_launch_dependents();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sQ = smem;
@@ -78,6 +79,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_wait();  // everything above touched only shared / tensor memory
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
   const uint32_t tS[2] = {tmem_base, tmem_base + 128u};
   const uint32_t tO = tmem_base + 256u;
@@ -287,6 +289,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 __global__ void __launch_bounds__(kAttnThreads, 1)
 attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                  const __grid_constant__ CUtensorMap tmV, const AttnFwdArgs g) {
+  pdl_launch_dependents();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sQ = smem;
@@ -335,6 +338,7 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_wait();  // everything above touched only shared / tensor memory
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
   const uint32_t tS[2] = {tmem_base, tmem_base + 128u};         // S of stream g; P (bf16 pairs) overwrites its first 64 columns
   const uint32_t tO[2] = {tmem_base + 256u, tmem_base + 384u};  // O accumulator of stream g
@@ -551,6 +555,7 @@ __global__ void __launch_bounds__(256) attn_delta_kernel(const bf16* __restrict_
                                                          const bf16* __restrict__ do0, int ldd0,
                                                          const bf16* __restrict__ do1, int ldd1, float* __restrict__ delta,
                                                          bf16* __restrict__ dOh, int B, int H, int L, int split) {
+  pdl_grid_sync();
   const long long w = static_cast<long long>(blockIdx.x) * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (w >= static_cast<long long>(B) * L * H) return;
@@ -585,6 +590,7 @@ template <int MODE_KV>
 __global__ void __launch_bounds__(kAttnThreads, 1)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tmR0, const __grid_constant__ CUtensorMap tmR1,
                 const __grid_constant__ CUtensorMap tmT0, const __grid_constant__ CUtensorMap tmT1, const AttnBwdArgs g) {
+  pdl_launch_dependents();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sR0 = smem;
@@ -635,6 +641,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmR0, const __grid_constant_
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_wait();  // everything above touched only shared / tensor memory
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
   const uint32_t tX0[2] = {tmem_base, tmem_base + 64u};
   const uint32_t tX1[2] = {tmem_base + 128u, tmem_base + 192u};
@@ -920,9 +927,9 @@ extern "C" int b200_attn_fwd(b200_ctx* ctx, const void* Q, const void* K, const 
   }
   dim3 grid((L + 127) / 128, B * H);
   if (variant == 1)
-    attn_fwd_kernel<<<grid, kAttnThreads, kFwdSmem, reinterpret_cast<cudaStream_t>(stream)>>>(tq, tk, tv, a);
+    B200_KLAUNCH(attn_fwd_kernel, grid, kAttnThreads, kFwdSmem, reinterpret_cast<cudaStream_t>(stream), tq, tk, tv, a);
   else
-    attn_fwd2_kernel<<<grid, kAttnThreads, kFwdSmem, reinterpret_cast<cudaStream_t>(stream)>>>(tq, tk, tv, a);
+    B200_KLAUNCH(attn_fwd2_kernel, grid, kAttnThreads, kFwdSmem, reinterpret_cast<cudaStream_t>(stream), tq, tk, tv, a);
   B200_CUDA_CHECK(cudaGetLastError());
   ctx->launches.fetch_add(1);
   return B200_OK;
@@ -941,7 +948,7 @@ extern "C" int b200_attn_bwd(b200_ctx* ctx, const void* Q, const void* K, const 
   const uint64_t rows = static_cast<uint64_t>(B) * H * L;
   B200_REQUIRE(rows < (1ull << 31), "b200_attn_bwd: too many rows");
   const long long warps = static_cast<long long>(B) * L * H;
-  attn_delta_kernel<<<static_cast<unsigned>((warps + 7) / 8), 256, 0, st>>>((const bf16*)o0, ld0, (const bf16*)o1, ld1,
+  B200_KLAUNCH(attn_delta_kernel, static_cast<unsigned>((warps + 7) / 8), 256, 0, st, (const bf16*)o0, ld0, (const bf16*)o1, ld1,
                                                                             (const bf16*)do0, ldd0, (const bf16*)do1, ldd1,
                                                                             (float*)delta, (bf16*)dOh, B, H, L, split);
   B200_CUDA_CHECK(cudaGetLastError());
@@ -971,9 +978,9 @@ extern "C" int b200_attn_bwd(b200_ctx* ctx, const void* Q, const void* K, const 
     ctx->launches.fetch_add(3);
     return B200_OK;
   }
-  attn_bwd_kernel<1><<<grid, kAttnThreads, kBwdSmem, st>>>(k128, v128, q64, d64, akv);
+  B200_KLAUNCH(attn_bwd_kernel<1>, grid, kAttnThreads, kBwdSmem, st, k128, v128, q64, d64, akv);
   B200_CUDA_CHECK(cudaGetLastError());
-  attn_bwd_kernel<0><<<grid, kAttnThreads, kBwdSmem, st>>>(q128, d128, k64, v64, aq);
+  B200_KLAUNCH(attn_bwd_kernel<0>, grid, kAttnThreads, kBwdSmem, st, q128, d128, k64, v64, aq);
   B200_CUDA_CHECK(cudaGetLastError());
   ctx->launches.fetch_add(3);
   return B200_OK;

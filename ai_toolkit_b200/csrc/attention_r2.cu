@@ -58,6 +58,7 @@ template <int NT>
 __global__ void __launch_bounds__(FwdR2<NT>::kThreads, 1)
 attn_fwd_nt_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                    const __grid_constant__ CUtensorMap tmV, const AttnFwdArgs g) {
+  pdl_launch_dependents();
   using C = FwdR2<NT>;
   constexpr int CW = C::kCW;
   extern __shared__ uint8_t smem_raw[];
@@ -111,6 +112,7 @@ attn_fwd_nt_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_wait();  // everything above touched only shared / tensor memory
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
   const uint32_t tO = tmem_base + 256u;
   auto S_at = [&](int b) -> uint32_t { return tmem_base + static_cast<uint32_t>(b) * 128u; };
@@ -328,6 +330,7 @@ template <int MODE_KV, int NH>
 __global__ void __launch_bounds__(64 + 256 * NH, 1)
 attn_bwd_r2_kernel(const __grid_constant__ CUtensorMap tmR0, const __grid_constant__ CUtensorMap tmR1,
                    const __grid_constant__ CUtensorMap tmT0, const __grid_constant__ CUtensorMap tmT1, const AttnBwdArgs g) {
+  pdl_launch_dependents();
   constexpr int kStages = kBwdR2Stages;
   constexpr int CW = 64 / NH;       // S / dP columns per thread
   constexpr int NCH = CW / 16;      // 16-column chunks per thread
@@ -380,6 +383,7 @@ attn_bwd_r2_kernel(const __grid_constant__ CUtensorMap tmR0, const __grid_consta
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_wait();  // everything above touched only shared / tensor memory
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
   auto X0 = [&](int b) -> uint32_t { return tmem_base + static_cast<uint32_t>(b) * 64u; };          // S  -> P
   auto X1 = [&](int b) -> uint32_t { return tmem_base + 128u + static_cast<uint32_t>(b) * 64u; };   // dP -> dS
@@ -671,7 +675,7 @@ static int launch_fwd_nt(const CUtensorMap& tq, const CUtensorMap& tk, const CUt
     configured = true;
   }
   dim3 grid((a.L + 127) / 128, a.B * a.H);
-  kern<<<grid, FwdR2<NT>::kThreads, FwdR2<NT>::kSmem, stream>>>(tq, tk, tv, a);
+  B200_KLAUNCH(kern, grid, FwdR2<NT>::kThreads, FwdR2<NT>::kSmem, stream, tq, tk, tv, a);
   B200_CUDA_CHECK(cudaGetLastError());
   return B200_OK;
 }
@@ -694,9 +698,9 @@ static int launch_bwd_nh(const CUtensorMap& k128, const CUtensorMap& v128, const
     configured = true;
   }
   dim3 grid((akv.L + 127) / 128, B * H);
-  kkv<<<grid, 64 + 256 * NH, kBwdR2Smem, stream>>>(k128, v128, q64, d64, akv);
+  B200_KLAUNCH(kkv, grid, 64 + 256 * NH, kBwdR2Smem, stream, k128, v128, q64, d64, akv);
   B200_CUDA_CHECK(cudaGetLastError());
-  kq<<<grid, 64 + 256 * NH, kBwdR2Smem, stream>>>(q128, d128, k64, v64, aq);
+  B200_KLAUNCH(kq, grid, 64 + 256 * NH, kBwdR2Smem, stream, q128, d128, k64, v64, aq);
   B200_CUDA_CHECK(cudaGetLastError());
   return B200_OK;
 }

@@ -8,7 +8,57 @@
 #include <stdint.h>
 #include <stdio.h>
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Programmatic dependent launch (opt-in build: `make pdl` -> lib/libb200lora_pdl.so, -DB200_PDL=1; select it with B200_LIB).
+// Every kernel calls pdl_launch_dependents() first thing (the next grid of the stream may be scheduled as soon as ALL
+// CTAs of this one have started) and pdl_wait() before it touches global memory (blocks until the previous grid has
+// completed and its writes are visible); the tcgen05 kernels put the wait AFTER their barrier-init / TMEM-alloc prologue,
+// which thereby overlaps the tail of the previous kernel.  In the default build both are empty and B200_KLAUNCH is the
+// plain <<<>>> launch: the validated library is byte-identical.
+// ---------------------------------------------------------------------------------------------------------------------
+#ifndef B200_PDL
+#define B200_PDL 0
+#endif
+#if B200_PDL
+#define B200_KLAUNCH(kern, grid, block, smem, stream, ...) ::b200::launch_pdl(kern, grid, block, smem, stream, __VA_ARGS__)
+#else
+#define B200_KLAUNCH(kern, grid, block, smem, stream, ...) kern<<<grid, block, smem, stream>>>(__VA_ARGS__)
+#endif
+
 namespace b200 {
+
+__device__ __forceinline__ void pdl_launch_dependents() {
+#if B200_PDL
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#endif
+}
+__device__ __forceinline__ void pdl_wait() {
+#if B200_PDL
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+#endif
+}
+__device__ __forceinline__ void pdl_grid_sync() {  // kernels without a prologue worth overlapping
+  pdl_launch_dependents();
+  pdl_wait();
+}
+#if B200_PDL
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                                     Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+#endif
+
 
 typedef __nv_bfloat16 bf16;
 

@@ -40,6 +40,7 @@ __global__ void __launch_bounds__(256) ln_modulate_fwd_kernel(const bf16* __rest
                                                               int rows_per_sample, bf16* __restrict__ out, int ldo,
                                                               float* __restrict__ mean_out, float* __restrict__ rstd_out,
                                                               int M, float eps) {
+  pdl_grid_sync();
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= M) return;
@@ -98,6 +99,7 @@ __global__ void __launch_bounds__(256) ln_modulate_bwd_kernel(const bf16* __rest
                                                               const bf16* __restrict__ scale, int ldmod,
                                                               int rows_per_sample, const bf16* __restrict__ dres, int lddres,
                                                               bf16* __restrict__ out, int ldo, int M) {
+  pdl_grid_sync();
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= M) return;
@@ -151,6 +153,7 @@ __global__ void __launch_bounds__(256) col_reduce_kernel(const bf16* __restrict_
                                                          const bf16* __restrict__ g, int ldg, bf16* __restrict__ mul_out,
                                                          int ldmul, float* __restrict__ sum_a, float* __restrict__ sum_ab,
                                                          int ldsum, int rows_per_sample, int M, int D) {
+  pdl_grid_sync();
   const int col = (blockIdx.x * 256 + threadIdx.x) * 2;
   if (col >= D) return;
   const int chunks_per_sample = (rows_per_sample + kColRows - 1) / kColRows;
@@ -210,6 +213,7 @@ __global__ void __launch_bounds__(256) qk_norm_rope_fwd_kernel(const bf16* __res
                                                                const float* __restrict__ sin_t, bf16* __restrict__ Q,
                                                                bf16* __restrict__ K, bf16* __restrict__ V, int B, int Lseg,
                                                                int seq_off, int Ltot, int H, float eps) {
+  pdl_grid_sync();
   const long long w = static_cast<long long>(blockIdx.x) * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   const long long total = static_cast<long long>(B) * Lseg * H;
@@ -254,6 +258,7 @@ __global__ void __launch_bounds__(256) qk_norm_rope_bwd_kernel(const bf16* __res
                                                                const float* __restrict__ sin_t, bf16* __restrict__ dq,
                                                                bf16* __restrict__ dk, bf16* __restrict__ dv, int ldd, int B,
                                                                int Lseg, int seq_off, int Ltot, int H, float eps) {
+  pdl_grid_sync();
   const long long w = static_cast<long long>(blockIdx.x) * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   const long long total = static_cast<long long>(B) * Lseg * H;
@@ -306,6 +311,7 @@ __global__ void __launch_bounds__(256) qk_norm_rope_bwd_kernel(const bf16* __res
 
 // ------------------------------------------------------------------------------------------------
 __global__ void silu_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, long long n) {
+  pdl_grid_sync();
   const long long i = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) * 2;
   if (i + 1 < n) {
     float2 v = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(x + i));
@@ -319,6 +325,7 @@ __global__ void silu_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, lo
 // (the trainer passes timestep / 1000 in fp32, the bf16 model multiplies by 1000 in bf16)
 __global__ void timestep_embed_kernel(const float* __restrict__ t_in, bf16* __restrict__ out, int B, int dim, float max_period,
                                       float div, float mult) {
+  pdl_grid_sync();
   const int b = blockIdx.x;
   const int half = dim / 2;
   const float t = bf16_round(bf16_round(t_in[b] / div) * mult);
@@ -333,6 +340,7 @@ __global__ void timestep_embed_kernel(const float* __restrict__ t_in, bf16* __re
 // out = bf16(a + b) (+ c)
 __global__ void add_kernel(const bf16* __restrict__ a, const bf16* __restrict__ b, const bf16* __restrict__ c,
                            bf16* __restrict__ y, long long n) {
+  pdl_grid_sync();
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= n) return;
   float v = bf16_round(__bfloat162float(a[i]) + __bfloat162float(b[i]));
@@ -369,7 +377,7 @@ extern "C" int b200_ln_modulate_fwd(b200_ctx* ctx, const void* x, int ldx, const
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const int grid = (M + 7) / 8;
 #define CALL(N_)                                                                                                         \
-  ln_modulate_fwd_kernel<N_><<<grid, 256, 0, st>>>((const bf16*)x, ldx, (const bf16*)shift, (const bf16*)scale, ldmod, \
+  B200_KLAUNCH(ln_modulate_fwd_kernel<N_>, grid, 256, 0, st, (const bf16*)x, ldx, (const bf16*)shift, (const bf16*)scale, ldmod, \
                                                    rows_per_sample, (bf16*)out, ldo, (float*)mean, (float*)rstd, M, eps)
   B200_LN_DISPATCH(D, CALL)
 #undef CALL
@@ -388,7 +396,7 @@ extern "C" int b200_ln_modulate_bwd(b200_ctx* ctx, const void* dy, int lddy, con
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const int grid = (M + 7) / 8;
 #define CALL(N_)                                                                                                      \
-  ln_modulate_bwd_kernel<N_><<<grid, 256, 0, st>>>((const bf16*)dy, lddy, (const bf16*)x, ldx, (const float*)mean,  \
+  B200_KLAUNCH(ln_modulate_bwd_kernel<N_>, grid, 256, 0, st, (const bf16*)dy, lddy, (const bf16*)x, ldx, (const float*)mean,  \
                                                    (const float*)rstd, (const bf16*)scale, ldmod, rows_per_sample,  \
                                                    (const bf16*)dres, lddres, (bf16*)out, ldo, M)
   B200_LN_DISPATCH(D, CALL)
@@ -410,7 +418,7 @@ extern "C" int b200_col_reduce(b200_ctx* ctx, const void* a, int lda, const void
   const int samples = (M + rows_per_sample - 1) / rows_per_sample;
   const int chunks = (rows_per_sample + kColRows - 1) / kColRows;
   dim3 grid((D / 2 + 255) / 256, samples * chunks);
-  col_reduce_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+  B200_KLAUNCH(col_reduce_kernel, grid, 256, 0, reinterpret_cast<cudaStream_t>(stream), 
       (const bf16*)a, lda, (const bf16*)b, ldb, (const float*)mean, (const float*)rstd, (const bf16*)g, ldg, (bf16*)mul_out,
       ldmul, (float*)sum_a, (float*)sum_ab, ldsum, rows_per_sample, M, D);
   B200_CUDA_CHECK(cudaGetLastError());
@@ -428,7 +436,7 @@ extern "C" int b200_qk_norm_rope_fwd(b200_ctx* ctx, const void* q, const void* k
   B200_REQUIRE(seq_off >= 0 && seq_off + Lseg <= Ltot, "b200_qk_norm_rope_fwd: segment out of range");
   const long long warps = static_cast<long long>(B) * Lseg * H;
   const unsigned grid = static_cast<unsigned>((warps + 7) / 8);
-  qk_norm_rope_fwd_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+  B200_KLAUNCH(qk_norm_rope_fwd_kernel, grid, 256, 0, reinterpret_cast<cudaStream_t>(stream), 
       (const bf16*)q, (const bf16*)k, (const bf16*)v, ld, (const bf16*)wq, (const bf16*)wk, (const float*)cos_t,
       (const float*)sin_t, (bf16*)Q, (bf16*)K, (bf16*)V, B, Lseg, seq_off, Ltot, H, eps);
   B200_CUDA_CHECK(cudaGetLastError());
@@ -447,7 +455,7 @@ extern "C" int b200_qk_norm_rope_bwd(b200_ctx* ctx, const void* dQ, const void* 
                "b200_qk_norm_rope_bwd: bad args");
   const long long warps = static_cast<long long>(B) * Lseg * H;
   const unsigned grid = static_cast<unsigned>((warps + 7) / 8);
-  qk_norm_rope_bwd_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+  B200_KLAUNCH(qk_norm_rope_bwd_kernel, grid, 256, 0, reinterpret_cast<cudaStream_t>(stream), 
       (const bf16*)dQ, (const bf16*)dK, (const bf16*)dV, (const bf16*)q, (const bf16*)k, ld, (const bf16*)wq,
       (const bf16*)wk, (const float*)cos_t, (const float*)sin_t, (bf16*)dq, (bf16*)dk, (bf16*)dv, ldd, B, Lseg, seq_off,
       Ltot, H, eps);
@@ -461,7 +469,7 @@ extern "C" int b200_silu(b200_ctx* ctx, const void* x, void* y, int64_t n, void*
   if (rc) return rc;
   B200_REQUIRE(x && y && n > 0, "b200_silu: bad args");
   const unsigned grid = static_cast<unsigned>(((n + 1) / 2 + 255) / 256);
-  silu_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>((const bf16*)x, (bf16*)y, n);
+  B200_KLAUNCH(silu_kernel, grid, 256, 0, reinterpret_cast<cudaStream_t>(stream), (const bf16*)x, (bf16*)y, n);
   B200_CUDA_CHECK(cudaGetLastError());
   ctx->launches.fetch_add(1);
   return B200_OK;
@@ -472,7 +480,7 @@ extern "C" int b200_timestep_embed(b200_ctx* ctx, const void* t01, void* out, in
   int rc = check_ctx(ctx);
   if (rc) return rc;
   B200_REQUIRE(t01 && out && B > 0 && dim > 0 && dim % 2 == 0 && div != 0.f, "b200_timestep_embed: bad args");
-  timestep_embed_kernel<<<B, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>((const float*)t01, (bf16*)out, B, dim,
+  B200_KLAUNCH(timestep_embed_kernel, B, 128, 0, reinterpret_cast<cudaStream_t>(stream), (const float*)t01, (bf16*)out, B, dim,
                                                                                max_period, div, mult);
   B200_CUDA_CHECK(cudaGetLastError());
   ctx->launches.fetch_add(1);
@@ -484,7 +492,7 @@ extern "C" int b200_add_bf16(b200_ctx* ctx, const void* a, const void* b, const 
   if (rc) return rc;
   B200_REQUIRE(a && b && y && n > 0, "b200_add_bf16: bad args");
   const unsigned grid = static_cast<unsigned>((n + 255) / 256);
-  add_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>((const bf16*)a, (const bf16*)b, (const bf16*)c,
+  B200_KLAUNCH(add_kernel, grid, 256, 0, reinterpret_cast<cudaStream_t>(stream), (const bf16*)a, (const bf16*)b, (const bf16*)c,
                                                                        (bf16*)y, n);
   B200_CUDA_CHECK(cudaGetLastError());
   ctx->launches.fetch_add(1);

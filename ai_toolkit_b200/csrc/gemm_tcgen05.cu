@@ -327,6 +327,7 @@ __global__ void __launch_bounds__(320, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmB0,
                  const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmB1,
                  const GemmArgs g) {
+  pdl_launch_dependents();
   using C = GemmCfg<CG, BN, STAGES, A_MN, B_MN>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -378,6 +379,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
   else
     __syncthreads();
   tc_fence_after();
+  pdl_wait();  // everything above touched only shared / tensor memory
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
 
   const int m_tiles = (g.M + C::BM * CG - 1) / (C::BM * CG);
@@ -598,13 +600,22 @@ static int launch_gemm(b200_ctx* ctx, const CUtensorMap& a0, const CUtensorMap& 
   cfg.blockDim = dim3(320, 1, 1);
   cfg.dynamicSmemBytes = C::SMEM_BYTES;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = CG;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
+  cudaLaunchAttribute attr[2];
+  int n_attr = 0;
+  if (CG == 2) {
+    attr[n_attr].id = cudaLaunchAttributeClusterDimension;
+    attr[n_attr].val.clusterDim.x = CG;
+    attr[n_attr].val.clusterDim.y = 1;
+    attr[n_attr].val.clusterDim.z = 1;
+    ++n_attr;
+  }
+#if B200_PDL
+  attr[n_attr].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[n_attr].val.programmaticStreamSerializationAllowed = 1;
+  ++n_attr;
+#endif
   cfg.attrs = attr;
-  cfg.numAttrs = (CG == 2) ? 1 : 0;
+  cfg.numAttrs = n_attr;
   B200_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, a0, b0, a1, b1, args));
   ctx->launches.fetch_add(1);
   return B200_OK;

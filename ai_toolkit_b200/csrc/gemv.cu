@@ -18,6 +18,7 @@ constexpr int kMaxRank = 128;
 // z[b, j] = c * sum_k x[b,k] A[j,k]          one warp per (b, j)
 __global__ void __launch_bounds__(256) lora_gemv_down_kernel(const bf16* __restrict__ x, int ldx, const float* __restrict__ A,
                                                              float c, float* __restrict__ z, int Bm, int r, int K) {
+  pdl_grid_sync();
   const int w = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (w >= Bm * r) return;
@@ -36,6 +37,7 @@ __global__ void __launch_bounds__(256) lora_gemv_fwd_kernel(const bf16* __restri
                                                             int ldw, const bf16* __restrict__ bias, const float* __restrict__ z,
                                                             const float* __restrict__ Bw, int r, bf16* __restrict__ y, int ldy,
                                                             int N, int K) {
+  pdl_grid_sync();
   extern __shared__ uint8_t smem_raw[];
   bf16* xs = reinterpret_cast<bf16*>(smem_raw);  // [BM][K]
   for (int i = threadIdx.x * 8; i < BM * K; i += blockDim.x * 8) {
@@ -86,6 +88,7 @@ __global__ void __launch_bounds__(256) lora_gemv_fwd_kernel(const bf16* __restri
 __global__ void __launch_bounds__(256) lora_gemv_bwd1_kernel(const float* __restrict__ dy, int lddy, const float* __restrict__ z,
                                                              const float* __restrict__ Bw, float c, float* __restrict__ dBw,
                                                              float* __restrict__ t, int Bm, int r, int N, int nb_db) {
+  pdl_grid_sync();
   if (static_cast<int>(blockIdx.x) < nb_db) {
     const long long idx = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x;
     if (idx >= static_cast<long long>(N) * r) return;
@@ -117,6 +120,7 @@ __global__ void __launch_bounds__(256) lora_gemv_bwd1_kernel(const float* __rest
 // dA[j, k] += sum_b t[b,j] x[b,k]
 __global__ void __launch_bounds__(256) lora_gemv_bwd2_kernel(const float* __restrict__ t, const bf16* __restrict__ x, int ldx,
                                                              float* __restrict__ dA, int Bm, int r, int K) {
+  pdl_grid_sync();
   const long long idx = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x;
   if (idx >= static_cast<long long>(r) * K) return;
   const int j = static_cast<int>(idx / K), k = static_cast<int>(idx % K);
@@ -141,7 +145,7 @@ extern "C" int b200_lora_gemv_fwd(b200_ctx* ctx, const void* x, int ldx, const v
   if (r > 0) B200_REQUIRE(A && Bw && z, "b200_lora_gemv_fwd: rank > 0 needs A, B and z");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (r > 0) {
-    lora_gemv_down_kernel<<<(Bm * r + 7) / 8, 256, 0, st>>>((const bf16*)x, ldx, (const float*)A, c, (float*)z, Bm, r, K);
+    B200_KLAUNCH(lora_gemv_down_kernel, (Bm * r + 7) / 8, 256, 0, st, (const bf16*)x, ldx, (const float*)A, c, (float*)z, Bm, r, K);
     B200_CUDA_CHECK(cudaGetLastError());
     ctx->launches.fetch_add(1);
   }
@@ -152,7 +156,7 @@ extern "C" int b200_lora_gemv_fwd(b200_ctx* ctx, const void* x, int ldx, const v
   case BM_: {                                                                                                          \
     auto kern = lora_gemv_fwd_kernel<BM_>;                                                                             \
     if (smem > 48 * 1024) B200_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    kern<<<grid, 256, smem, st>>>((const bf16*)x, ldx, (const bf16*)W, ldw, (const bf16*)bias, (const float*)z,       \
+    B200_KLAUNCH(kern, grid, 256, smem, st, (const bf16*)x, ldx, (const bf16*)W, ldw, (const bf16*)bias, (const float*)z,       \
                                   (const float*)Bw, r, (bf16*)y, ldy, N, K);                                           \
   } break;
   switch (Bm) {
@@ -175,11 +179,11 @@ extern "C" int b200_lora_gemv_bwd(b200_ctx* ctx, const void* dy, int lddy, const
   const int nb_db = static_cast<int>((static_cast<long long>(N) * r + 255) / 256);
   const int nb_t = (N + 255) / 256;
   B200_CUDA_CHECK(cudaMemsetAsync(t_ws, 0, sizeof(float) * Bm * r, st));
-  lora_gemv_bwd1_kernel<<<nb_db + nb_t, 256, 0, st>>>((const float*)dy, lddy, (const float*)z, (const float*)Bw, c,
+  B200_KLAUNCH(lora_gemv_bwd1_kernel, nb_db + nb_t, 256, 0, st, (const float*)dy, lddy, (const float*)z, (const float*)Bw, c,
                                                       (float*)dBw, (float*)t_ws, Bm, r, N, nb_db);
   B200_CUDA_CHECK(cudaGetLastError());
   const int nb_da = static_cast<int>((static_cast<long long>(r) * K + 255) / 256);
-  lora_gemv_bwd2_kernel<<<nb_da, 256, 0, st>>>((const float*)t_ws, (const bf16*)x, ldx, (float*)dA, Bm, r, K);
+  B200_KLAUNCH(lora_gemv_bwd2_kernel, nb_da, 256, 0, st, (const float*)t_ws, (const bf16*)x, ldx, (float*)dA, Bm, r, K);
   B200_CUDA_CHECK(cudaGetLastError());
   ctx->launches.fetch_add(2);
   return B200_OK;

@@ -20,6 +20,7 @@ __device__ __forceinline__ size_t packed_index(int b, int c, int h, int w, int C
 // noisy = bf16( (1 - t/1000) * x0 + (t/1000) * noise )   [fp32 math, as the fp32 timestep tensor promotes it]
 __global__ void flow_add_noise_kernel(const bf16* __restrict__ x0, const bf16* __restrict__ noise, const float* __restrict__ t,
                                       bf16* __restrict__ out, int B, int C, int H, int W, int pack) {
+  pdl_grid_sync();
   const long long i2 = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;  // pair index
   const long long per = static_cast<long long>(C) * H * W;
   if (i2 * 2 >= per * B) return;
@@ -43,6 +44,7 @@ __global__ void __launch_bounds__(256) flow_loss_kernel(const bf16* __restrict__
                                                         const bf16* __restrict__ noise, bf16* __restrict__ dpred,
                                                         float* __restrict__ loss_per_sample, float* __restrict__ loss_total,
                                                         int B, int C, int H, int W, int pack, float gscale) {
+  pdl_grid_sync();
   const long long i2 = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   const long long per = static_cast<long long>(C) * H * W;
   const int b = blockIdx.y;
@@ -79,6 +81,7 @@ __global__ void __launch_bounds__(256) flow_loss_kernel(const bf16* __restrict__
 
 // sum of squares of an fp32 vector -> double accumulator (caller zeroes it)
 __global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ g, long long n, double* __restrict__ out) {
+  pdl_grid_sync();
   float acc = 0.f;
   const long long stride = static_cast<long long>(gridDim.x) * blockDim.x * 4;
   for (long long i = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) * 4; i < n; i += stride) {
@@ -108,6 +111,7 @@ __global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ g,
 //        d[3] EMA decay of this step, d[4] total grad norm (after prescale, before clipping)
 __global__ void adamw_prepare_kernel(const double* __restrict__ sumsq, const float* __restrict__ hyper, long long* state,
                                      float* __restrict__ norm_out) {
+  pdl_grid_sync();
   float* d = reinterpret_cast<float*>(reinterpret_cast<char*>(state) + 16);
   const long long step = state[0] + 1;  // 1-based index of this step, as torch.optim.AdamW counts
   state[0] = step;
@@ -132,6 +136,7 @@ __global__ void __launch_bounds__(256) clip_adamw_kernel(float* __restrict__ p, 
                                                          float* __restrict__ m, float* __restrict__ v,
                                                          float* __restrict__ ema, const float* __restrict__ hyper,
                                                          const long long* __restrict__ state, long long n) {
+  pdl_grid_sync();
   const float* d = reinterpret_cast<const float*>(reinterpret_cast<const char*>(state) + 16);
   const float lr = hyper[0], b1 = hyper[1], b2 = hyper[2], eps = hyper[3], wd = hyper[4];
   const float gs = d[0], step_size = d[1], bc2_sqrt = d[2], ema_d = d[3];
@@ -162,6 +167,7 @@ struct RepackEntry {
 
 __global__ void __launch_bounds__(256) repack_kernel(const float* __restrict__ flat, bf16* __restrict__ pack,
                                                      const RepackEntry* __restrict__ tab) {
+  pdl_grid_sync();
   const RepackEntry e = tab[blockIdx.y];
   const long long n = static_cast<long long>(e.rows) * e.cols;
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
@@ -182,7 +188,7 @@ extern "C" int b200_flow_add_noise(b200_ctx* ctx, const void* latents, const voi
   B200_REQUIRE(latents && noise && t && out && B > 0 && C > 0 && H > 0 && W > 0, "b200_flow_add_noise: bad args");
   B200_REQUIRE(W % 2 == 0 && (!pack || H % 2 == 0), "b200_flow_add_noise: H/W must be even");
   const long long pairs = static_cast<long long>(B) * C * H * W / 2;
-  flow_add_noise_kernel<<<static_cast<unsigned>((pairs + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+  B200_KLAUNCH(flow_add_noise_kernel, static_cast<unsigned>((pairs + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream), 
       (const bf16*)latents, (const bf16*)noise, (const float*)t, (bf16*)out, B, C, H, W, pack);
   B200_CUDA_CHECK(cudaGetLastError());
   ctx->launches.fetch_add(1);
@@ -201,7 +207,7 @@ extern "C" int b200_flow_loss(b200_ctx* ctx, const void* pred, const void* laten
   B200_CUDA_CHECK(cudaMemsetAsync(loss_total, 0, sizeof(float), st));
   const long long pairs = static_cast<long long>(C) * H * W / 2;
   dim3 grid(static_cast<unsigned>((pairs + 255) / 256), B);
-  flow_loss_kernel<<<grid, 256, 0, st>>>((const bf16*)pred, (const bf16*)latents, (const bf16*)noise, (bf16*)dpred,
+  B200_KLAUNCH(flow_loss_kernel, grid, 256, 0, st, (const bf16*)pred, (const bf16*)latents, (const bf16*)noise, (bf16*)dpred,
                                          (float*)loss_per_sample, (float*)loss_total, B, C, H, W, pack, gscale);
   B200_CUDA_CHECK(cudaGetLastError());
   ctx->launches.fetch_add(1);
@@ -219,7 +225,7 @@ extern "C" int b200_grad_sumsq(b200_ctx* ctx, const void* g, int64_t n, void* su
   const long long cap = static_cast<long long>(ctx->sm_count) * 8;
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
-  sumsq_kernel<<<static_cast<unsigned>(blocks), 256, 0, st>>>((const float*)g, n, (double*)sumsq_f64);
+  B200_KLAUNCH(sumsq_kernel, static_cast<unsigned>(blocks), 256, 0, st, (const float*)g, n, (double*)sumsq_f64);
   B200_CUDA_CHECK(cudaGetLastError());
   ctx->launches.fetch_add(1);
   return B200_OK;
@@ -231,9 +237,9 @@ extern "C" int b200_clip_adamw(b200_ctx* ctx, void* p, void* g, void* m, void* v
   if (rc) return rc;
   B200_REQUIRE(p && g && m && v && sumsq_f64 && hyper && state && n > 0, "b200_clip_adamw: bad args");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  adamw_prepare_kernel<<<1, 1, 0, st>>>((const double*)sumsq_f64, (const float*)hyper, (long long*)state, (float*)norm_out);
+  B200_KLAUNCH(adamw_prepare_kernel, 1, 1, 0, st, (const double*)sumsq_f64, (const float*)hyper, (long long*)state, (float*)norm_out);
   B200_CUDA_CHECK(cudaGetLastError());
-  clip_adamw_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(
+  B200_KLAUNCH(clip_adamw_kernel, static_cast<unsigned>((n + 255) / 256), 256, 0, st, 
       (float*)p, (const float*)g, (float*)m, (float*)v, (float*)ema, (const float*)hyper, (const long long*)state, n);
   B200_CUDA_CHECK(cudaGetLastError());
   ctx->launches.fetch_add(2);
@@ -247,7 +253,7 @@ extern "C" int b200_repack_lora(b200_ctx* ctx, const void* flat_f32, void* pack_
   B200_REQUIRE(flat_f32 && pack_bf16 && table && n_entries > 0, "b200_repack_lora: bad args");
   static_assert(sizeof(RepackEntry) == 32, "RepackEntry layout is part of the C ABI");
   dim3 grid(16, n_entries);
-  repack_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>((const float*)flat_f32, (bf16*)pack_bf16,
+  B200_KLAUNCH(repack_kernel, grid, 256, 0, reinterpret_cast<cudaStream_t>(stream), (const float*)flat_f32, (bf16*)pack_bf16,
                                                                           (const RepackEntry*)table);
   B200_CUDA_CHECK(cudaGetLastError());
   ctx->launches.fetch_add(1);

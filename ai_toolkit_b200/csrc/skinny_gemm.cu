@@ -43,6 +43,7 @@ __device__ __forceinline__ float ld_dsmem_f32(uint32_t local_addr, uint32_t rank
 template <int B_MN>
 __global__ void __launch_bounds__(192, 1)
 skinny_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const SkinnyArgs g) {
+  pdl_launch_dependents();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   float* partial = reinterpret_cast<float*>(smem + kSkStages * (kSkA + kSkB));  // [64 cols][128 rows]
@@ -78,6 +79,7 @@ skinny_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_wait();  // everything above touched only shared / tensor memory
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
 
   if (warp == 0) {
@@ -191,13 +193,18 @@ static int launch_skinny(b200_ctx* ctx, const CUtensorMap& ta, const CUtensorMap
   cfg.blockDim = dim3(192, 1, 1);
   cfg.dynamicSmemBytes = kSkSmem;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = a.S;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
+#if B200_PDL
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.numAttrs = 2;
+#endif
   B200_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, ta, tb, a));
   ctx->launches.fetch_add(1);
   return B200_OK;

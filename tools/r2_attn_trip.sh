@@ -24,3 +24,9 @@ for v in "B200_ATTN_FWD=3 B200_ATTN_BWD=3" "B200_ATTN_FWD=4 B200_ATTN_BWD=2"; do
 done
 run B200_ATTN_FWD=1 B200_ATTN_BWD=1 python bench.py --steps 10 --warmup 3
 grep -E "^\[|exit|passed|failed|\"value\"" $LOG | cut -c1-260
+# 4. programmatic dependent launch build (same kernels + griddepcontrol, every launch with the PDL attribute)
+PDL=ai_toolkit_b200/lib/libb200lora_pdl.so
+run B200_LIB=$PDL python -m pytest tests/test_gpu_gemm.py tests/test_gpu_ops.py tests/test_gpu_attention.py -x -q -p no:cacheprovider
+run B200_LIB=$PDL python -m pytest tests/test_gpu_flux_engine.py -x -q -p no:cacheprovider
+run B200_LIB=$PDL python bench.py --steps 10 --warmup 3
+grep -E "exit|passed|failed|\"value\"" $LOG | tail -8 | cut -c1-260
