@@ -31,6 +31,14 @@ $(LIB): $(OBJ)
 	@mkdir -p ai_toolkit_b200/lib
 	$(NVCC) $(ARCH) -shared -o $@ $(OBJ) -lcudart_static -ldl -lpthread -lrt
 
+# tuning variants for same-box A/B runs:  make variant NAME=poly0 DEFS="-DB200_ATTN_POLY_R2=0"
+#   -> ai_toolkit_b200/lib/libb200lora_poly0.so (select with B200_LIB)
+variant:
+	@test -n "$(NAME)" || (echo "usage: make variant NAME=<tag> DEFS=\"-D...\""; exit 1)
+	@mkdir -p build_$(NAME) ai_toolkit_b200/lib
+	for f in $(SRC); do $(NVCC) $(NVCCFLAGS) $(DEFS) -c $$f -o build_$(NAME)/$$(basename $$f .cu).o 2> build_$(NAME)/$$(basename $$f .cu).ptxas.log || exit 1; done
+	$(NVCC) $(ARCH) -shared -o ai_toolkit_b200/lib/libb200lora_$(NAME).so build_$(NAME)/*.o -lcudart_static -ldl -lpthread -lrt
+
 clean:
 	rm -rf build build_pdl $(LIB) $(LIB_PDL)
-.PHONY: all pdl clean
+.PHONY: all pdl variant clean

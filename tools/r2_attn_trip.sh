@@ -13,6 +13,12 @@ for v in "B200_ATTN_FWD=1 B200_ATTN_BWD=1" "B200_ATTN_FWD=3 B200_ATTN_BWD=1" "B2
          "B200_ATTN_FWD=1 B200_ATTN_BWD=3" "B200_ATTN_FWD=1 B200_ATTN_BWD=2"; do
   run $v python tools/time_attn_variants.py 88 320 1000 4608
 done
+# 1b. share of the exponentials computed by the FMA-pipe polynomial in the r2 forward (default 1 of 4 pairs): 0 and 2
+for n in 0 2; do
+  make variant NAME=poly$n DEFS="-DB200_ATTN_POLY_R2=$n" > /dev/null 2>&1
+  run B200_LIB=ai_toolkit_b200/lib/libb200lora_poly$n.so B200_ATTN_FWD=3 B200_ATTN_BWD=1 python tools/time_attn_variants.py 4608
+  run B200_LIB=ai_toolkit_b200/lib/libb200lora_poly$n.so B200_ATTN_FWD=4 B200_ATTN_BWD=1 python tools/time_attn_variants.py 4608
+done
 # 2. the unit tests (ragged tails, split = 0, large scores that force the lazy rescale) with each candidate
 for v in "B200_ATTN_FWD=3 B200_ATTN_BWD=3" "B200_ATTN_FWD=4 B200_ATTN_BWD=2"; do
   run $v python -m pytest tests/test_gpu_attention.py -x -q -p no:cacheprovider
