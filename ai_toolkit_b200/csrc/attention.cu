@@ -30,7 +30,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                 const __grid_constant__ CUtensorMap tmV, const AttnFwdArgs g) {
   pdl_launch_dependents();
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_base_1024(smem_raw);
   uint8_t* sQ = smem;
   uint8_t* sK = sQ + 32768;
   uint8_t* sV = sK + 2 * 32768;
@@ -291,7 +291,7 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
                  const __grid_constant__ CUtensorMap tmV, const AttnFwdArgs g) {
   pdl_launch_dependents();
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_base_1024(smem_raw);
   uint8_t* sQ = smem;
   uint8_t* sK = sQ + 32768;
   uint8_t* sV = sK + 2 * 32768;
@@ -592,7 +592,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmR0, const __grid_constant_
                 const __grid_constant__ CUtensorMap tmT0, const __grid_constant__ CUtensorMap tmT1, const AttnBwdArgs g) {
   pdl_launch_dependents();
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_base_1024(smem_raw);
   uint8_t* sR0 = smem;
   uint8_t* sR1 = sR0 + 32768;
   uint8_t* sT = sR1 + 32768;  // stage st: T0 at sT + st*32768, T1 at +16384

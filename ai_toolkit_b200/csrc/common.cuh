@@ -27,6 +27,21 @@
 
 namespace b200 {
 
+// 1024-byte alignment of the dynamic shared-memory window (SWIZZLE_128B tiles).  Default: round the generic address up
+// (validated round 1) — the compiler then loses the shared address space and every later shared access through a
+// derived pointer is a generic LD / ST.  -DB200_SMEM_SHARED_ADDR=1 (tuning variant): offset arithmetic on the __shared__
+// array, which keeps LDS / STS (used unconditionally by the round-2 candidates in attention_r2.cu).
+#ifndef B200_SMEM_SHARED_ADDR
+#define B200_SMEM_SHARED_ADDR 0
+#endif
+__device__ __forceinline__ uint8_t* smem_base_1024(uint8_t* raw) {
+#if B200_SMEM_SHARED_ADDR
+  return raw + ((1024u - (static_cast<uint32_t>(__cvta_generic_to_shared(raw)) & 1023u)) & 1023u);
+#else
+  return reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~uintptr_t(1023));
+#endif
+}
+
 __device__ __forceinline__ void pdl_launch_dependents() {
 #if B200_PDL
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");

@@ -330,7 +330,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
   pdl_launch_dependents();
   using C = GemmCfg<CG, BN, STAGES, A_MN, B_MN>;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_base_1024(smem_raw);
   uint8_t* epi_scratch = smem + STAGES * C::STAGE_BYTES;
   uint64_t* full = reinterpret_cast<uint64_t*>(epi_scratch + C::EPI_SCRATCH);
   uint64_t* empty = full + STAGES;

@@ -45,7 +45,7 @@ __global__ void __launch_bounds__(192, 1)
 skinny_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const SkinnyArgs g) {
   pdl_launch_dependents();
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_base_1024(smem_raw);
   float* partial = reinterpret_cast<float*>(smem + kSkStages * (kSkA + kSkB));  // [64 cols][128 rows]
   uint64_t* full = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(partial) + 128 * 64 * 4);
   uint64_t* empty = full + kSkStages;

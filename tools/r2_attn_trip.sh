@@ -36,3 +36,12 @@ run B200_LIB=$PDL python -m pytest tests/test_gpu_gemm.py tests/test_gpu_ops.py 
 run B200_LIB=$PDL python -m pytest tests/test_gpu_flux_engine.py -x -q -p no:cacheprovider
 run B200_LIB=$PDL python bench.py --steps 10 --warmup 3
 grep -E "exit|passed|failed|\"value\"" $LOG | tail -8 | cut -c1-260
+# 5. shared-address-space variant of the VALIDATED kernels (LDS/STS instead of generic LD/ST in the GEMM epilogue
+#    transposes and the attention statistics): parity + sustained GEMM rate + bench
+make variant NAME=lds DEFS="-DB200_SMEM_SHARED_ADDR=1" > /dev/null 2>&1
+LDS=ai_toolkit_b200/lib/libb200lora_lds.so
+run B200_LIB=$LDS python -m pytest tests/test_gpu_gemm.py tests/test_gpu_attention.py -x -q -p no:cacheprovider
+run B200_LIB=$LDS python tools/sustained.py
+run python tools/sustained.py
+run B200_LIB=$LDS python bench.py --steps 10 --warmup 3
+grep -E "exit|passed|failed|\"value\"|TF" $LOG | tail -12 | cut -c1-260
