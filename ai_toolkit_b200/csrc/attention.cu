@@ -967,7 +967,7 @@ extern "C" int b200_attn_bwd(b200_ctx* ctx, const void* Q, const void* K, const 
     B200_CUDA_CHECK(cudaFuncSetAttribute(attn_bwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdSmem));
     B200_CUDA_CHECK(cudaFuncSetAttribute(attn_bwd_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdSmem));
     const char* e = getenv("B200_ATTN_BWD");
-    if (e && (atoi(e) == 2 || atoi(e) == 3)) variant = atoi(e);  // opt-in round-2 candidates (attention_r2.cu)
+    if (e && atoi(e) >= 2 && atoi(e) <= 5) variant = atoi(e);  // opt-in round-2 candidates (attention_r2.cu)
     configured = true;
   }
   dim3 grid((L + 127) / 128, B * H);

@@ -1,4 +1,4 @@
-// Round-2 CANDIDATE attention kernels (opt-in: B200_ATTN_FWD=3|4, B200_ATTN_BWD=2|3).  They compile and their SASS
+// Round-2 CANDIDATE attention kernels (opt-in: B200_ATTN_FWD=3|4, B200_ATTN_BWD=2|3|4|5).  They compile and their SASS
 // has been read, but they have NOT run on a B200 yet; the default path stays the validated kernels of attention.cu
 // until tools/r2_attn_trip.sh has shown parity and a speed-up on the GPU box.
 //
@@ -22,6 +22,8 @@
 //        * S / dP read in 16-column chunks, the next chunk in flight while the current one is computed;
 //        * NH = 2: thread (row, hh) owns columns [32 hh, 32 hh + 32) and writes its bf16 P / dS pairs inside its own
 //          range (columns 48 hh ...), so no thread overwrites what another still reads.
+//   bwd  variant 4 (NH = 2) / 5 (NH = 1): the dK/dV pass of variant 2 / 3 plus a dQ pass whose next S / dP MMA is
+//        issued as soon as the softmax has LOADED the current one (dS in its own TMEM region): see attn_bwd_q2_kernel.
 #include <type_traits>
 
 #include "attn_common.cuh"
@@ -663,6 +665,255 @@ attn_bwd_r2_kernel(const __grid_constant__ CUtensorMap tmR0, const __grid_consta
 }
 
 // =================================================================================================
+// backward, dQ pass with EARLY issue of the next S / dP MMA (variant 4; the dK/dV pass is variant 2's kernel).
+// In attn_bwd_r2_kernel<0> the group's chain is  A(i) -> softmax(i) -> B(i) -> A(i+2)  because dS is written over dP inside
+// X[g].  The dQ pass has only ONE accumulator, so 128 TMEM columns are free: dS goes to its own region D[g], A(i+2) may
+// overwrite X[g] as soon as softmax(i) has LOADED S / dP (x_free), and the tensor pipe works on it while softmax(i) still
+// computes.  Q_i / dO_i stay in shared memory (SS MMAs, as in the dK/dV pass; the TMEM-resident form measured neutral).
+// Protocol checked by tools/mbar_model.py::run_bwd_q2 (softmax(i) must wait d_free = B(i-2) before it rewrites D[g]).
+// =================================================================================================
+constexpr int kBwdQ2Stages = 4;
+constexpr int kBwdQ2Smem = 1024 + 2 * 32768 + kBwdQ2Stages * 32768 + 24 * 8;
+
+template <int NH>
+__global__ void __launch_bounds__(64 + 256 * NH, 1)
+attn_bwd_q2_kernel(const __grid_constant__ CUtensorMap tmR0, const __grid_constant__ CUtensorMap tmR1,
+                   const __grid_constant__ CUtensorMap tmT0, const __grid_constant__ CUtensorMap tmT1, const AttnBwdArgs g) {
+  pdl_launch_dependents();
+  constexpr int kStages = kBwdQ2Stages;
+  constexpr int CW = 64 / NH;   // S / dP columns per thread
+  constexpr int NCH = CW / 16;  // 16-column chunks per thread
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_align1024(smem_raw);
+  uint8_t* sR0 = smem;          // Q_i  [128 x 128] bf16, two 64-column SWIZZLE_128B halves
+  uint8_t* sR1 = sR0 + 32768;   // dO_i
+  uint8_t* sT = sR1 + 32768;    // stage st: K_j tile at sT + st*32768, V_j tile at +16384 (64 rows each)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sT + kStages * 32768);
+  uint64_t* r_full = bars;
+  uint64_t* t_full = bars + 1;    // [4]
+  uint64_t* t_empty = bars + 5;   // [4]
+  uint64_t* x_full = bars + 9;    // [2] S / dP of the group's tile are in TMEM
+  uint64_t* x_free = bars + 11;   // [2] the group has loaded them: X[g] may be overwritten
+  uint64_t* pb_full = bars + 13;  // [2] dS of the group's tile is in D[g]
+  uint64_t* d_free = bars + 15;   // [2] the dQ MMA has read D[g]
+  uint64_t* done_bar = bars + 17;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
+
+  const int warp = warp_id_uniform(), lane = threadIdx.x & 31;
+  const int bh = blockIdx.y;
+  const int r0 = blockIdx.x * 128;
+  const int n_t = (g.L + 63) / 64;
+  const long long row_base = static_cast<long long>(bh) * g.L;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmR0);
+    tma_prefetch_desc(&tmR1);
+    tma_prefetch_desc(&tmT0);
+    tma_prefetch_desc(&tmT1);
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      mbar_init(r_full, 1);
+      for (int s = 0; s < kStages; ++s) {
+        mbar_init(&t_full[s], 1);
+        mbar_init(&t_empty[s], 1);
+      }
+      for (int s = 0; s < 2; ++s) {
+        mbar_init(&x_full[s], 1);
+        mbar_init(&x_free[s], 128 * NH);
+        mbar_init(&pb_full[s], 128 * NH);
+        mbar_init(&d_free[s], 1);
+      }
+      mbar_init(done_bar, 1);
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc<512>(tmem_slot);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  pdl_wait();  // everything above touched only shared / tensor memory
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
+  auto X0 = [&](int b) -> uint32_t { return tmem_base + static_cast<uint32_t>(b) * 64u; };         // S
+  auto X1 = [&](int b) -> uint32_t { return tmem_base + 128u + static_cast<uint32_t>(b) * 64u; };  // dP
+  auto Dg = [&](int b) -> uint32_t { return tmem_base + 384u + static_cast<uint32_t>(b) * 32u; };  // dS, bf16 pairs
+  const uint32_t tA0 = tmem_base + 256u;                                                            // dQ accumulator
+
+  if (warp == 0) {
+    if (lane == 0) {
+      const int rrow = static_cast<int>(row_base + r0);
+      mbar_arrive_expect_tx(r_full, 65536);
+      tma_load_2d(sR0, &tmR0, r_full, 0, rrow);
+      tma_load_2d(sR0 + 16384, &tmR0, r_full, 64, rrow);
+      tma_load_2d(sR1, &tmR1, r_full, 0, rrow);
+      tma_load_2d(sR1 + 16384, &tmR1, r_full, 64, rrow);
+      for (int i = 0; i < n_t; ++i) {
+        const int st = i % kStages;
+        const uint32_t ph = (i / kStages) & 1;
+        const int trow = static_cast<int>(row_base + i * 64);
+        mbar_wait(&t_empty[st], ph ^ 1u, 20000 + i);
+        mbar_arrive_expect_tx(&t_full[st], 32768);
+        uint8_t* d = sT + st * 32768;
+        tma_load_2d(d, &tmT0, &t_full[st], 0, trow);
+        tma_load_2d(d + 8192, &tmT0, &t_full[st], 64, trow);
+        tma_load_2d(d + 16384, &tmT1, &t_full[st], 0, trow);
+        tma_load_2d(d + 16384 + 8192, &tmT1, &t_full[st], 64, trow);
+      }
+    }
+  } else if (warp == 1) {
+    // converged MMA warp, elected issue (common.cuh)
+    constexpr uint32_t idA = umma_idesc_bf16(128, 64, 0, 0);
+    constexpr uint32_t idB = umma_idesc_bf16(128, 128, 0, 1);
+    mbar_wait(r_full, 0, 21);
+    tc_fence_after();
+    const uint64_t dR0 = umma_desc_sw128(smem_u32(sR0), 1024, 16);
+    const uint64_t dR1 = umma_desc_sw128(smem_u32(sR1), 1024, 16);
+    const uint64_t dTk = umma_desc_sw128(smem_u32(sT), 1024, 16);    // K_j / V_j read K-major (S, dP)
+    const uint64_t dTm = umma_desc_sw128(smem_u32(sT), 1024, 8192);  // K_j read MN-major (dQ += dS K_j)
+    auto issue_A = [&](int i) {  // S = Q_i K_j^T -> X0[g], dP = dO_i V_j^T -> X1[g]
+      const int st = i % kStages;
+      const uint32_t ph = (i / kStages) & 1;
+      const int xb = i & 1;
+      mbar_wait(&t_full[st], ph, 22000 + i);
+      tc_fence_after();
+      const uint64_t d0 = dTk + static_cast<uint64_t>(st * (32768 >> 4));
+      const uint64_t d1 = d0 + (16384 >> 4);
+#pragma unroll
+      for (int kk = 0; kk < 8; ++kk) {
+        const uint32_t offa = (kk >> 2) * (16384 >> 4) + 2u * (kk & 3);
+        const uint32_t offb = (kk >> 2) * (8192 >> 4) + 2u * (kk & 3);
+        umma_bf16_ss_w(X0(xb), dR0 + offa, d0 + offb, idA, kk > 0 ? 1u : 0u);
+      }
+#pragma unroll
+      for (int kk = 0; kk < 8; ++kk) {
+        const uint32_t offa = (kk >> 2) * (16384 >> 4) + 2u * (kk & 3);
+        const uint32_t offb = (kk >> 2) * (8192 >> 4) + 2u * (kk & 3);
+        umma_bf16_ss_w(X1(xb), dR1 + offa, d1 + offb, idA, kk > 0 ? 1u : 0u);
+      }
+      umma_commit_w(&x_full[xb]);
+    };
+    issue_A(0);
+    if (n_t > 1) issue_A(1);
+    for (int i = 0; i < n_t; ++i) {
+      const int xb = i & 1;
+      const uint32_t gph = (i >> 1) & 1;
+      if (i + 2 < n_t) {  // X[xb] is free as soon as the group has its S / dP in registers
+        mbar_wait(&x_free[xb], gph, 23000 + i);
+        issue_A(i + 2);
+      }
+      mbar_wait(&pb_full[xb], gph, 24000 + i);
+      tc_fence_after();
+      const int st = i % kStages;
+      const uint64_t m0 = dTm + static_cast<uint64_t>(st * (32768 >> 4));  // K_j tile, MN-major view
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk)  // dQ += dS K_j   (A = dS from TMEM: 64 kv = 4 K steps of 8 columns)
+        umma_bf16_ts_w(tA0, Dg(xb) + kk * 8, m0 + kk * (2048 >> 4), idB, (kk > 0 || i > 0) ? 1u : 0u);
+      umma_commit_w(&t_empty[st]);
+      umma_commit_w(&d_free[xb]);
+    }
+    umma_commit_w(done_bar);
+  } else {
+    const int q = warp & 3;
+    const int gq = ((warp - 2) >> 2) & 1;
+    const int hh = (warp - 2) >> 3;  // 0 for NH = 1
+    const int r = q * 32 + lane;
+    const int ri = r0 + r;  // q index
+    const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
+    const float c2 = g.scale * kLog2e;
+    float my_lse2 = 0.f, my_dls = 0.f;
+    if (ri < g.L) {
+      my_lse2 = (g.lse + row_base)[ri] * kLog2e;
+      my_dls = (g.delta + row_base)[ri] * g.scale;
+    }
+    const float2 c22 = make_float2(c2, c2), sc2 = make_float2(g.scale, g.scale);
+    const float2 nl2 = make_float2(-my_lse2, -my_lse2), nd2 = make_float2(-my_dls, -my_dls);
+    for (int i = gq; i < n_t; i += 2) {
+      const uint32_t gph = (i >> 1) & 1;
+      mbar_wait(&x_full[gq], gph, 25000 + i);
+      tc_fence_after();
+      const int nvalid = g.L - (i * 64 + hh * CW);  // kv columns of my part that exist (<= 0: none)
+      uint32_t dd[CW / 2];
+      uint32_t sv[2][16], dv[2][16];
+      const uint32_t cs = X0(gq) + lane_off + hh * CW, cd = X1(gq) + lane_off + hh * CW;
+      auto chunk = [&](auto masked_tag, const uint32_t(&s16)[16], const uint32_t(&d16)[16], int ch) {
+        constexpr bool MASKED = decltype(masked_tag)::value;
+#pragma unroll
+        for (int k = 0; k < 16; k += 2) {
+          const float2 a = ffma2(make_float2(__uint_as_float(s16[k]), __uint_as_float(s16[k + 1])), c22, nl2);
+          float2 pr = make_float2(ex2(a.x), ex2(a.y));
+          if (MASKED) {
+            pr.x = (ch * 16 + k < nvalid) ? pr.x : 0.f;
+            pr.y = (ch * 16 + k + 1 < nvalid) ? pr.y : 0.f;
+          }
+          const float2 t = ffma2(make_float2(__uint_as_float(d16[k]), __uint_as_float(d16[k + 1])), sc2, nd2);
+          const float2 ds = fmul2(pr, t);
+          dd[ch * 8 + k / 2] = pack_bf16x2(ds.x, ds.y);
+        }
+      };
+      auto tile = [&](auto masked_tag) {
+        tmem_ld_32x16(cs, sv[0]);
+        tmem_ld_32x16(cd, dv[0]);
+#pragma unroll
+        for (int ch = 0; ch < NCH; ++ch) {
+          tmem_ld_wait();  // chunk ch has arrived
+          if (ch + 1 < NCH) {
+            tmem_ld_32x16(cs + (ch + 1) * 16, sv[(ch + 1) & 1]);
+            tmem_ld_32x16(cd + (ch + 1) * 16, dv[(ch + 1) & 1]);
+          } else {
+            tc_fence_before();
+            mbar_arrive(&x_free[gq]);  // all of my S / dP are in registers: the next S / dP MMA may overwrite X[gq]
+          }
+          chunk(masked_tag, sv[ch & 1], dv[ch & 1], ch);
+        }
+      };
+      if (nvalid >= CW)  // warp-uniform
+        tile(std::false_type{});
+      else
+        tile(std::true_type{});
+      if (i >= 2) {  // the dQ MMA of tile i-2 has read D[gq]
+        mbar_wait(&d_free[gq], ((i >> 1) - 1) & 1, 26000 + i);
+        tc_fence_after();
+      }
+      if constexpr (CW == 64)
+        tmem_st_32x32(Dg(gq) + lane_off, dd);
+      else
+        tmem_st_32x16(Dg(gq) + lane_off + hh * 16, dd);
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(&pb_full[gq]);
+    }
+    mbar_wait(done_bar, 0, 27);
+    tc_fence_after();
+    // epilogue: 8 NH warps = 4 lane quarters x 2 NH column blocks of the dQ accumulator
+    constexpr int CB = 128 / (2 * NH);
+    const int cb = (warp - 2) >> 2;
+#pragma unroll 1
+    for (int c = 0; c < CB / 32; ++c) {
+      uint32_t v[32];
+      tmem_ld_32x32(tA0 + lane_off + cb * CB + c * 32, v);
+      tmem_ld_wait();
+      if (ri < g.L) {
+        bf16* orow = g.out0 + (row_base + ri) * 128 + cb * CB + c * 32;
+#pragma unroll
+        for (int k8 = 0; k8 < 4; ++k8) {
+          uint4 u;
+          u.x = pack_bf16x2(__uint_as_float(v[k8 * 8 + 0]), __uint_as_float(v[k8 * 8 + 1]));
+          u.y = pack_bf16x2(__uint_as_float(v[k8 * 8 + 2]), __uint_as_float(v[k8 * 8 + 3]));
+          u.z = pack_bf16x2(__uint_as_float(v[k8 * 8 + 4]), __uint_as_float(v[k8 * 8 + 5]));
+          u.w = pack_bf16x2(__uint_as_float(v[k8 * 8 + 6]), __uint_as_float(v[k8 * 8 + 7]));
+          *reinterpret_cast<uint4*>(orow + k8 * 8) = u;
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (warp == 1) tmem_dealloc<512>(tmem_base);
+}
+
+// =================================================================================================
 // host-side launchers (called from b200_attn_fwd / b200_attn_bwd when the environment selects a candidate)
 // =================================================================================================
 template <int NT>
@@ -705,10 +956,32 @@ static int launch_bwd_nh(const CUtensorMap& k128, const CUtensorMap& v128, const
   return B200_OK;
 }
 
+template <int NH>
+static int launch_bwd_q2(const CUtensorMap& k128, const CUtensorMap& v128, const CUtensorMap& q64, const CUtensorMap& d64,
+                         const CUtensorMap& q128, const CUtensorMap& d128, const CUtensorMap& k64, const CUtensorMap& v64,
+                         const AttnBwdArgs& akv, const AttnBwdArgs& aq, int B, int H, cudaStream_t stream) {
+  auto kkv = attn_bwd_r2_kernel<1, NH>;
+  auto kq = attn_bwd_q2_kernel<NH>;
+  static bool configured = false;
+  if (!configured) {
+    B200_CUDA_CHECK(cudaFuncSetAttribute(kkv, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdR2Smem));
+    B200_CUDA_CHECK(cudaFuncSetAttribute(kq, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdQ2Smem));
+    configured = true;
+  }
+  dim3 grid((akv.L + 127) / 128, B * H);
+  B200_KLAUNCH(kkv, grid, 64 + 256 * NH, kBwdR2Smem, stream, k128, v128, q64, d64, akv);
+  B200_CUDA_CHECK(cudaGetLastError());
+  B200_KLAUNCH(kq, grid, 64 + 256 * NH, kBwdQ2Smem, stream, q128, d128, k64, v64, aq);
+  B200_CUDA_CHECK(cudaGetLastError());
+  return B200_OK;
+}
+
 int attn_bwd_r2_launch(int variant, const CUtensorMap& k128, const CUtensorMap& v128, const CUtensorMap& q64,
                        const CUtensorMap& d64, const CUtensorMap& q128, const CUtensorMap& d128, const CUtensorMap& k64,
                        const CUtensorMap& v64, const AttnBwdArgs& akv, const AttnBwdArgs& aq, int B, int H,
                        cudaStream_t stream) {
+  if (variant == 4) return launch_bwd_q2<2>(k128, v128, q64, d64, q128, d128, k64, v64, akv, aq, B, H, stream);
+  if (variant == 5) return launch_bwd_q2<1>(k128, v128, q64, d64, q128, d128, k64, v64, akv, aq, B, H, stream);
   if (variant == 2) return launch_bwd_nh<2>(k128, v128, q64, d64, q128, d128, k64, v64, akv, aq, B, H, stream);
   return launch_bwd_nh<1>(k128, v128, q64, d64, q128, d128, k64, v64, akv, aq, B, H, stream);
 }

@@ -51,3 +51,22 @@ def test_backward_shared_arrival_barrier_is_caught():
     for seed in range(20):
         with pytest.raises(m.ProtocolError):
             m.run_bwd(seed, shared_pb_full=True)
+
+
+@pytest.mark.parametrize("n_t,group_size,stages", [(9, 2, 4), (6, 3, 3), (1, 2, 4), (2, 2, 4), (3, 2, 4), (72, 1, 4)])
+def test_backward_dq_early_issue_protocol(n_t, group_size, stages):
+    """attention_r2.cu `attn_bwd_q2_kernel`: A(i+2) is issued on x_free (the group has loaded S / dP), dS lives in D[g],
+    softmax(i) waits d_free = B(i-2) before rewriting D[g]."""
+    for seed in range(60 if n_t > 20 else 400):
+        m.run_bwd_q2(seed, n_t=n_t, group_size=group_size, stages=stages)
+
+
+def test_backward_dq_without_d_free_wait_is_caught():
+    hits = 0
+    for seed in range(200):
+        try:
+            m.run_bwd_q2(seed, wait_d_free=False)
+        except m.ProtocolError as e:
+            assert "overwrites dS" in str(e)
+            hits += 1
+    assert hits > 0

@@ -341,3 +341,99 @@ def run_bwd(seed, n_t=9, group_size=2, stages=3, shared_pb_full=False):
             sim.add(f"soft{g}_{w}", softmax(g, w))
     sim.run()
     return sim.steps
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# backward dQ pass with EARLY issue of the next S/dP MMA (attention_r2.cu attn_bwd_q2_kernel): dS goes to its own TMEM
+# region D[g], so A(i+2) may overwrite X[g] as soon as softmax(i) has LOADED S/dP (x_free) instead of after B(i)
+# ---------------------------------------------------------------------------------------------------------------------
+def run_bwd_q2(seed, n_t=9, group_size=2, stages=4, wait_d_free=True):
+    sim = Sim(seed)
+    r_full = Barrier("r_full", 1)
+    t_full = [Barrier(f"t_full{s}", 1) for s in range(stages)]
+    t_empty = [Barrier(f"t_empty{s}", 1) for s in range(stages)]
+    x_full = [Barrier(f"x_full{g}", 1) for g in (0, 1)]
+    x_free = [Barrier(f"x_free{g}", group_size) for g in (0, 1)]
+    pb_full = [Barrier(f"pb_full{g}", group_size) for g in (0, 1)]
+    d_free = [Barrier(f"d_free{g}", 1) for g in (0, 1)]
+    done_bar = Barrier("done", 1)
+    st = dict(T=[None] * stages, X=[None, None], X_loaded=[set(), set()], D=[None, None], D_written=[set(), set()], b_exec=-1,
+              R=False)
+
+    def tma():
+        yield ("do", lambda: st.__setitem__("R", True))
+        yield ("arrive", r_full)
+        for i in range(n_t):
+            s = i % stages
+            yield ("wait", t_empty[s], ((i // stages) & 1) ^ 1, i // stages - 1)
+            yield ("do", lambda i=i, s=s: st["T"].__setitem__(s, i))
+            yield ("arrive", t_full[s])
+
+    def mma():
+        def exec_A(i):
+            g = i & 1
+            if not st["R"] or st["T"][i % stages] != i:
+                raise ProtocolError(f"A({i}) reads stage holding {st['T'][i % stages]}")
+            if st["X"][g] is not None and len(st["X_loaded"][g]) != group_size:
+                raise ProtocolError(f"A({i}) overwrites X[{g}] (tile {st['X'][g]}) before the group loaded it")
+            st["X"][g], st["X_loaded"][g] = i, set()
+
+        def exec_B(i):
+            g = i & 1
+            if st["T"][i % stages] != i:
+                raise ProtocolError(f"B({i}) reads stage holding {st['T'][i % stages]}")
+            if st["D"][g] != i or len(st["D_written"][g]) != group_size:
+                raise ProtocolError(f"B({i}) reads D[{g}] = tile {st['D'][g]} with {len(st['D_written'][g])}/{group_size} rows")
+            st["b_exec"] = i
+
+        def issue_A(i):
+            s = i % stages
+            yield ("wait", t_full[s], (i // stages) & 1, i // stages)
+            yield ("push", ("mma", lambda i=i: exec_A(i)))
+            yield ("push", ("commit", x_full[i & 1]))
+
+        yield ("wait", r_full, 0, 0)
+        yield from issue_A(0)
+        if n_t > 1:
+            yield from issue_A(1)
+        for i in range(n_t):
+            g = i & 1
+            if i + 2 < n_t:
+                yield ("wait", x_free[g], (i >> 1) & 1, i >> 1)
+                yield from issue_A(i + 2)
+            yield ("wait", pb_full[g], (i >> 1) & 1, i >> 1)
+            yield ("push", ("mma", lambda i=i: exec_B(i)))
+            yield ("push", ("commit", t_empty[i % stages]))
+            yield ("push", ("commit", d_free[g]))
+        yield ("push", ("commit", done_bar))
+
+    def softmax(g, w):
+        for i in range(g, n_t, 2):
+            yield ("wait", x_full[g], (i >> 1) & 1, i >> 1)
+
+            def load(i=i):
+                if st["X"][g] != i:
+                    raise ProtocolError(f"group {g} loads X holding tile {st['X'][g]} instead of {i}")
+                st["X_loaded"][g].add(w)
+            yield ("do", load)
+            yield ("arrive", x_free[g])
+            if wait_d_free and i >= 2:
+                yield ("wait", d_free[g], ((i >> 1) - 1) & 1, (i >> 1) - 1)
+
+            def write(i=i):
+                if st["b_exec"] < i - 2:
+                    raise ProtocolError(f"group {g} overwrites dS({i - 2}) before B({i - 2}) read it")
+                if st["D"][g] != i:
+                    st["D"][g], st["D_written"][g] = i, set()
+                st["D_written"][g].add(w)
+            yield ("do", write)
+            yield ("arrive", pb_full[g])
+        yield ("wait", done_bar, 0, 0)
+
+    sim.add("tma", tma())
+    sim.add("mma", mma())
+    for g in (0, 1):
+        for w in range(group_size):
+            sim.add(f"soft{g}_{w}", softmax(g, w))
+    sim.run()
+    return sim.steps

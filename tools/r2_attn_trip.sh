@@ -20,7 +20,8 @@ want() { case " $SECTIONS " in *" $1 "*) return 0;; *) return 1;; esac; }
 
 if want attn; then
   for v in "B200_ATTN_FWD=1 B200_ATTN_BWD=1" "B200_ATTN_FWD=3 B200_ATTN_BWD=1" "B200_ATTN_FWD=4 B200_ATTN_BWD=1" \
-           "B200_ATTN_FWD=1 B200_ATTN_BWD=3" "B200_ATTN_FWD=1 B200_ATTN_BWD=2"; do
+           "B200_ATTN_FWD=1 B200_ATTN_BWD=3" "B200_ATTN_FWD=1 B200_ATTN_BWD=2" "B200_ATTN_FWD=1 B200_ATTN_BWD=5" \
+           "B200_ATTN_FWD=1 B200_ATTN_BWD=4"; do
     run $v python tools/time_attn_variants.py 88 320 1000 4608
   done
 fi
@@ -32,7 +33,8 @@ if want poly; then
   done
 fi
 if want unit; then
-  for v in "B200_ATTN_FWD=3 B200_ATTN_BWD=3" "B200_ATTN_FWD=4 B200_ATTN_BWD=2"; do
+  for v in "B200_ATTN_FWD=3 B200_ATTN_BWD=3" "B200_ATTN_FWD=4 B200_ATTN_BWD=2" "B200_ATTN_FWD=3 B200_ATTN_BWD=5" \
+           "B200_ATTN_FWD=4 B200_ATTN_BWD=4"; do
     run $v python -m pytest tests/test_gpu_attention.py -x -q -p no:cacheprovider
   done
 fi
