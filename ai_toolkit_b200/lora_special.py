@@ -759,11 +759,18 @@ def get_network(unet, text_encoder=None, *, network_config=None, model_config=No
         transformer_only=g(network_config, "transformer_only", True), is_transformer=g(base_model, "is_transformer", False),
         base_model=base_model)
     kw.update(g(network_config, "network_kwargs", {}) or {})
+    if base_model is not None and hasattr(base_model, "target_lora_modules"):  # :1945-1946
+        kw["target_lin_modules"] = base_model.target_lora_modules
     kw.update(network_kwargs)
     net = LoRASpecialNetwork(**kw)
     if device is None:
         device = next(unet.parameters()).device
     net.force_to(device, dtype=torch.float32)
+    if base_model is not None:  # "give network to sd so it can use it" (:1984)
+        try:
+            base_model.network = net
+        except AttributeError:
+            pass
     net._update_torch_multiplier()
     net.apply_to(text_encoder, unet, kw["train_text_encoder"], kw["train_unet"])
     return net
