@@ -663,7 +663,12 @@ extern "C" int b200_gemm_bf16(b200_ctx* ctx, const b200_gemm_desc* d, void* stre
   //   M 4608, K 3072: 16 vs 18.5 us | K 9216: 35 vs 27 | K 21504: 71 vs 58 | M 4096, K 12288: 43 vs 21 | M 512, K 9216: 33 vs 11
   // -> the cluster variant wins as soon as the contraction is long or the row tiles are few.
   const int sk_mtiles = (d->M + 127) / 128;
-  const bool sk_cluster = plain_bf16 && (d->K0 >= 6144 || sk_mtiles <= 16) && d->K0 >= 512;
+  static int sk_always = -1;  // B200_SKINNY_ALWAYS=1 (tuning): cluster kernel for every plain rank-side GEMM
+  if (sk_always < 0) {
+    const char* e = getenv("B200_SKINNY_ALWAYS");
+    sk_always = (e && atoi(e) == 1) ? 1 : 0;
+  }
+  const bool sk_cluster = plain_bf16 && (d->K0 >= 6144 || sk_mtiles <= 16 || sk_always) && d->K0 >= 512;
   if ((config == B200_GEMM_AUTO && sk_cluster) || config == B200_GEMM_SKINNY_CLUSTER) {
     B200_REQUIRE(plain_bf16, "b200_gemm_bf16: SKINNY_CLUSTER needs N <= 64, bf16 output, one segment and no fused epilogue");
     return skinny_gemm_dispatch(ctx, d, stream);

@@ -5,6 +5,8 @@
 // CLUSTER: S CTAs each run the TMA -> tcgen05 pipeline over K/S, park their fp32 partial tile in shared memory,
 // and the partials are reduced through distributed shared memory (ld.shared::cluster) — no fp32 round trip
 // through HBM, no second kernel, bf16 result written once.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "ctx.h"
 
@@ -40,7 +42,19 @@ __device__ __forceinline__ float ld_dsmem_f32(uint32_t local_addr, uint32_t rank
   return v;
 }
 
-template <int B_MN>
+__device__ __forceinline__ void st_dsmem_f32(uint32_t local_addr, uint32_t rank, float v) {
+  uint32_t remote;
+  asm("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local_addr), "r"(rank));
+  asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(remote), "f"(v) : "memory");
+}
+
+// PUSH = 0: validated round-1 reduction (every CTA parks its whole partial tile locally, the owner of a row block PULLS the
+//   S partials with ld.shared::cluster — 64 dependent remote loads per thread, latency-bound: the cluster kernel measured
+//   18.5 us against 16 us for the persistent kernel at K = 3072 although it uses 4x the SMs).
+// PUSH = 1 (round-2 candidate, B200_SKINNY_PUSH=1): every CTA PUSHES each row block of its partial tile straight into the
+//   owner's receive buffer with st.shared::cluster (fire and forget), one cluster barrier, then the owner sums S local
+//   slices with ordinary LDS.
+template <int B_MN, int PUSH = 0>
 __global__ void __launch_bounds__(192, 1)
 skinny_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const SkinnyArgs g) {
   pdl_launch_dependents();
@@ -130,14 +144,50 @@ skinny_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
 #pragma unroll
         for (int i = 0; i < 32; ++i) v[i] = 0u;
       }
+      if (PUSH) {
+        // receive buffer of the owner: [source rank][64 cols][rows_per]; lanes = consecutive rows -> contiguous remote stores
+        const int rows_per = 128 / g.S;
+        const uint32_t owner = static_cast<uint32_t>(row / rows_per);
+        const uint32_t base = smem_u32(partial) + ((rank * 64u + c * 32u) * rows_per + (row % rows_per)) * 4u;
 #pragma unroll
-      for (int i = 0; i < 32; ++i) partial[(c * 32 + i) * 128 + row] = __uint_as_float(v[i]);
+        for (int i = 0; i < 32; ++i) st_dsmem_f32(base + static_cast<uint32_t>(i * rows_per) * 4u, owner, __uint_as_float(v[i]));
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) partial[(c * 32 + i) * 128 + row] = __uint_as_float(v[i]);
+      }
     }
   }
   tc_fence_before();
   __syncthreads();
   cluster_barrier();  // every CTA's partial tile is complete and visible cluster-wide
-  if (warp >= 2) {
+  if (PUSH) {
+    if (warp >= 2) {  // sum the S slices that arrived in MY receive buffer: rows [rank * rows_per, +rows_per)
+      const int rows_per = 128 / g.S;
+      const int t = (warp - 2) * 32 + lane;
+      const int rl = t % rows_per;
+      const int cgrp = t / rows_per;
+      const int ncg = 128 / rows_per;
+      const int cols_per = 64 / ncg;
+      const int grow = m_blk * 128 + static_cast<int>(rank) * rows_per + rl;
+      if (grow < g.M) {
+        float a = g.alpha;
+        if (g.row_alpha) a *= g.row_alpha[grow / g.rows_per_sample];
+        for (int c = 0; c < cols_per; c += 2) {
+          const int col = cgrp * cols_per + c;
+          float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+          for (int p = 0; p < 8; ++p) {
+            if (p < g.S) {
+              s0 += partial[(p * 64 + col) * rows_per + rl];
+              s1 += partial[(p * 64 + col + 1) * rows_per + rl];
+            }
+          }
+          if (col < g.n_store)
+            *reinterpret_cast<uint32_t*>(g.out + static_cast<size_t>(grow) * g.ldo + col) = pack_bf16x2(s0 * a, s1 * a);
+        }
+      }
+    }
+  } else if (warp >= 2) {
     // CTA `rank` reduces rows [rank * 128 / S, ...) over all S partial tiles; 128 threads: lane -> row, warp -> 16 columns
     const int rows_per = 128 / g.S;  // S in {1, 2, 4, 8}
     const int t = (warp - 2) * 32 + lane;
@@ -179,9 +229,9 @@ skinny_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   if (warp == 1) tmem_dealloc<64>(tmem_base);
 }
 
-template <int B_MN>
+template <int B_MN, int PUSH = 0>
 static int launch_skinny(b200_ctx* ctx, const CUtensorMap& ta, const CUtensorMap& tb, const SkinnyArgs& a, cudaStream_t stream) {
-  auto kern = skinny_gemm_kernel<B_MN>;
+  auto kern = skinny_gemm_kernel<B_MN, PUSH>;
   static bool configured = false;
   if (!configured) {
     B200_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSkSmem));
@@ -233,6 +283,12 @@ int skinny_gemm_dispatch(b200_ctx* ctx, const b200_gemm_desc* d, cudaStream_t st
   else
     rc = make_tmap_bf16_2d(ctx, &tb, d->B0, d->N, d->K0, d->ldb0, 64, 64);
   if (rc) return rc;
+  static int push = -1;  // B200_SKINNY_PUSH=1: round-2 candidate reduction (opt-in)
+  if (push < 0) {
+    const char* e = getenv("B200_SKINNY_PUSH");
+    push = (e && atoi(e) == 1) ? 1 : 0;
+  }
+  if (push) return d->trans_b ? launch_skinny<1, 1>(ctx, ta, tb, a, stream) : launch_skinny<0, 1>(ctx, ta, tb, a, stream);
   return d->trans_b ? launch_skinny<1>(ctx, ta, tb, a, stream) : launch_skinny<0>(ctx, ta, tb, a, stream);
 }
 

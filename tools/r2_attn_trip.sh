@@ -7,13 +7,15 @@
 #  unit  tests/test_gpu_attention.py with the candidates (ragged tails, split = 0, big scores -> lazy rescale)
 #  step  the candidate pairs through the whole step: engine parity tests + bench line, baseline bench beside it
 #  pdl   programmatic-dependent-launch build: GPU test suite + bench
+#  skinny  cluster split-K rank-side GEMM with the PUSH reduction (B200_SKINNY_PUSH=1): tests, hot-L2 timing vs the pull
+#          reduction and the persistent kernel, bench with it forced for every rank-side GEMM (B200_SKINNY_ALWAYS=1)
 #  lds   shared-address-space variant of the VALIDATED kernels: tests + sustained GEMM rate + bench
 # Every process runs under its own `timeout` (a barrier-protocol mistake ends in the 2.5 s mbarrier watchdog trap, not in
 # a hung box).  Output: gpurun_out/r2_trip.log.  Promote a candidate to the default only if parity = OK on every shape,
 # the unit tests pass with it, and it is faster than the baseline IN THE SAME LOG (box-to-box spread is +-2 %).
 mkdir -p gpurun_out
 LOG=gpurun_out/r2_trip.log
-SECTIONS="${*:-attn poly unit step pdl lds}"
+SECTIONS="${*:-attn poly unit step pdl lds skinny}"
 echo "### $(date -u +%H:%M:%S) sections: $SECTIONS" >> $LOG
 run() { echo "== $*" >> $LOG; timeout 400 env "$@" >> $LOG 2>&1; echo "exit $?" >> $LOG; }
 want() { case " $SECTIONS " in *" $1 "*) return 0;; *) return 1;; esac; }
@@ -59,4 +61,12 @@ if want lds; then
   run python tools/sustained.py
   run B200_LIB=$LDS python bench.py --steps 10 --warmup 3
 fi
-grep -E "^\[|^== |exit|passed|failed|\"value\"|TF" $LOG | cut -c1-240 | tail -80
+if want skinny; then
+  run B200_SKINNY_PUSH=1 python -m pytest tests/test_gpu_gemm.py -x -q -p no:cacheprovider
+  run B200_SKINNY_PUSH=1 B200_SKINNY_ALWAYS=1 python -m pytest tests/test_gpu_gemm.py tests/test_gpu_flux_engine.py -x -q -p no:cacheprovider -k "not curve"
+  run python tools/time_skinny.py
+  run B200_SKINNY_PUSH=1 python tools/time_skinny.py
+  run B200_SKINNY_PUSH=1 python bench.py --steps 10 --warmup 3
+  run B200_SKINNY_PUSH=1 B200_SKINNY_ALWAYS=1 python bench.py --steps 10 --warmup 3
+fi
+grep -E "^\[|^== |exit|passed|failed|\"value\"|TF|persistent" $LOG | cut -c1-240 | tail -80
