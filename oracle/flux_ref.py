@@ -15,9 +15,15 @@ the in-tree call sites and the in-tree BFL-lineage restatement:
   * FLUX.1 dimensions .............. extensions_built_in/diffusion_models/chroma/src/model.py:37-53
 
 PARITY UNPINNED at the diffusers boundary: the reference holds no golden vectors for the DiT forward
-(SURVEY.md §8c); parity for the blocks is oracle-vs-kernel on identical weights, and the LoRA wrapper
-(which IS in-tree) is pinned by running the reference's own classes on top of this model
-(oracle/make_golden.py).
+ and diffusers itself cannot be run here.  What IS checked (tests/test_oracle_pinned.py,
+tests/test_oracle_crosscheck_bfl.py):
+  * the double / single stream blocks and the timestep embedding against the reference's OWN in-tree blocks listed
+    above, executed from /root/reference with mapped weights (forward 1e-5, backward 1e-4, fp32);
+  * the whole model (embedders, modulation order, RoPE, final AdaLN with its scale/shift swap) against an independent
+    BFL-lineage implementation installed with torchtitan, through the public BFL -> diffusers weight conversion;
+  * the LoRA wrapper (which IS in-tree) by running the reference's own classes on top of this model
+    (oracle/make_golden.py).
+What stays unpinned is only that diffusers @ c9438378 implements this same published architecture.
 
 Every nn.Linear here is a plain `torch.nn.Linear` so that the reference's unmodified
 `LoRASpecialNetwork` (class-name matching, toolkit/lora_special.py:484-489) attaches to it.
