@@ -688,7 +688,12 @@ extern "C" int b200_gemm_bf16(b200_ctx* ctx, const b200_gemm_desc* d, void* stre
       // few rows (the 512-token text stream): 256 x 256 pair tiles would leave most SMs idle; 128 x 128 tiles give
       // 4x the CTAs at the cost of operand re-reads that L2 absorbs
       const long long pair_tiles = static_cast<long long>((d->M + 255) / 256) * ((d->N + 255) / 256);
-      if (pair_tiles * 2 < ctx->sm_count) config = B200_GEMM_1CTA_N128;
+      static int pair_min = -1;  // B200_GEMM_PAIR_MIN (tuning): fewer pair tiles than this -> 128 x 128 tiles; default SMs / 2
+      if (pair_min < 0) {
+        const char* e = getenv("B200_GEMM_PAIR_MIN");
+        pair_min = (e && atoi(e) > 0) ? atoi(e) : ctx->sm_count / 2;
+      }
+      if (pair_tiles < pair_min) config = B200_GEMM_1CTA_N128;
     }
   }
 

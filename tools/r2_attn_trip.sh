@@ -9,13 +9,14 @@
 #  pdl   programmatic-dependent-launch build: GPU test suite + bench
 #  skinny  cluster split-K rank-side GEMM with the PUSH reduction (B200_SKINNY_PUSH=1): tests, hot-L2 timing vs the pull
 #          reduction and the persistent kernel, bench with it forced for every rank-side GEMM (B200_SKINNY_ALWAYS=1)
+#  tiles   threshold between 128x128 and 256x256 (2-CTA) tiles for the GEMMs of the short text stream (B200_GEMM_PAIR_MIN)
 #  lds   shared-address-space variant of the VALIDATED kernels: tests + sustained GEMM rate + bench
 # Every process runs under its own `timeout` (a barrier-protocol mistake ends in the 2.5 s mbarrier watchdog trap, not in
 # a hung box).  Output: gpurun_out/r2_trip.log.  Promote a candidate to the default only if parity = OK on every shape,
 # the unit tests pass with it, and it is faster than the baseline IN THE SAME LOG (box-to-box spread is +-2 %).
 mkdir -p gpurun_out
 LOG=gpurun_out/r2_trip.log
-SECTIONS="${*:-attn poly unit step pdl lds skinny}"
+SECTIONS="${*:-attn poly unit step pdl lds skinny tiles}"
 echo "### $(date -u +%H:%M:%S) sections: $SECTIONS" >> $LOG
 run() { echo "== $*" >> $LOG; timeout 400 env "$@" >> $LOG 2>&1; echo "exit $?" >> $LOG; }
 want() { case " $SECTIONS " in *" $1 "*) return 0;; *) return 1;; esac; }
@@ -60,6 +61,11 @@ if want lds; then
   run B200_LIB=$LDS python tools/sustained.py
   run python tools/sustained.py
   run B200_LIB=$LDS python bench.py --steps 10 --warmup 3
+fi
+if want tiles; then  # 512-token text stream: 128x128 tiles (L2-bound, measured 490 TF/s cold on qkv) vs 256x256 pair tiles
+  for n in 74 64 40 20; do
+    run B200_GEMM_PAIR_MIN=$n python bench.py --steps 10 --warmup 3
+  done
 fi
 if want skinny; then
   run B200_SKINNY_PUSH=1 python -m pytest tests/test_gpu_gemm.py -x -q -p no:cacheprovider
