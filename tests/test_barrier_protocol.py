@@ -70,3 +70,11 @@ def test_backward_dq_without_d_free_wait_is_caught():
             assert "overwrites dS" in str(e)
             hits += 1
     assert hits > 0
+
+
+@pytest.mark.parametrize("n_tiles,kb,stages,zero", [(5, 4, 3, ()), (7, 1, 6, ()), (3, 48, 6, ()), (6, 3, 2, (1, 4)), (1, 2, 6, ())])
+def test_gemm_pipeline_protocol(n_tiles, kb, stages, zero):
+    """gemm_tcgen05.cu: TMA ring (full / empty), two TMEM accumulators (tfull / tempty), including split-K slices that have
+    no k-block at all (the handshake must still run, and the epilogue must see a zero partial)."""
+    for seed in range(60 if kb > 20 else 300):
+        m.run_gemm(seed, n_tiles=n_tiles, kb_per_tile=kb, stages=stages, n_epi=3, tiles_with_zero_k=zero)

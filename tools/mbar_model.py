@@ -437,3 +437,82 @@ def run_bwd_q2(seed, n_t=9, group_size=2, stages=4, wait_d_free=True):
             sim.add(f"soft{g}_{w}", softmax(g, w))
     sim.run()
     return sim.steps
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# persistent GEMM (gemm_tcgen05.cu): TMA ring of STAGES k-blocks, two TMEM accumulators, epilogue warps
+# ---------------------------------------------------------------------------------------------------------------------
+def run_gemm(seed, n_tiles=5, kb_per_tile=4, stages=3, n_epi=3, tiles_with_zero_k=()):
+    """One worker (CTA or CTA pair): producer fills stage s when `empty[s]` says the MMAs that read it have retired;
+    the MMA warp accumulates tile t into accumulator t & 1 once the epilogue has drained it (`tempty`), commits
+    `empty[s]` per k-block and `tfull[acc]` per tile; every epilogue agent reads the accumulator and arrives `tempty`.
+    `tiles_with_zero_k`: split-K slices without k-blocks (the kernel still runs the tfull / tempty handshake)."""
+    sim = Sim(seed)
+    full = [Barrier(f"full{s}", 1) for s in range(stages)]
+    empty = [Barrier(f"empty{s}", 1) for s in range(stages)]
+    tfull = [Barrier(f"tfull{a}", 1) for a in (0, 1)]
+    tempty = [Barrier(f"tempty{a}", n_epi) for a in (0, 1)]
+    st = dict(stage=[None] * stages, acc_tile=[None, None], acc_kb=[0, 0], acc_read=[set(), set()], consumed=-1)
+    kbs = [0 if t in tiles_with_zero_k else kb_per_tile for t in range(n_tiles)]
+    starts = [sum(kbs[:t]) for t in range(n_tiles)]
+
+    def tma():
+        n = 0
+        for t in range(n_tiles):
+            for kb in range(kbs[t]):
+                s = n % stages
+                yield ("wait", empty[s], ((n // stages) & 1) ^ 1, n // stages - 1)
+
+                def load(n=n, s=s):
+                    if st["stage"][s] is not None and st["consumed"] < st["stage"][s]:
+                        raise ProtocolError(f"TMA overwrites stage {s} (k-block {st['stage'][s]}) before the MMA read it")
+                    st["stage"][s] = n
+                yield ("do", load)
+                yield ("arrive", full[s])
+                n += 1
+
+    def mma():
+        n = 0
+        for t in range(n_tiles):
+            a = t & 1
+            yield ("wait", tempty[a], ((t >> 1) & 1) ^ 1, (t >> 1) - 1)
+            for kb in range(kbs[t]):
+                s = n % stages
+                yield ("wait", full[s], (n // stages) & 1, n // stages)
+
+                def exec_mma(n=n, s=s, t=t, a=a, kb=kb):
+                    if st["stage"][s] != n:
+                        raise ProtocolError(f"MMA reads stage {s} holding k-block {st['stage'][s]} instead of {n}")
+                    if kb == 0:
+                        if st["acc_tile"][a] is not None and len(st["acc_read"][a]) != n_epi:
+                            raise ProtocolError(f"tile {t} overwrites accumulator {a} before the epilogue drained tile {st['acc_tile'][a]}")
+                        st["acc_tile"][a], st["acc_kb"][a], st["acc_read"][a] = t, 0, set()
+                    st["acc_kb"][a] += 1
+                    st["consumed"] = n
+                yield ("push", ("mma", exec_mma))
+                yield ("push", ("commit", empty[s]))
+                n += 1
+            if kbs[t] == 0:
+                def mark(t=t, a=a):
+                    st["acc_tile"][a], st["acc_kb"][a], st["acc_read"][a] = t, 0, set()
+                yield ("push", ("mma", mark))
+            yield ("push", ("commit", tfull[a]))
+
+    def epilogue(w):
+        for t in range(n_tiles):
+            a = t & 1
+            yield ("wait", tfull[a], (t >> 1) & 1, t >> 1)
+
+            def drain(t=t, a=a):
+                if st["acc_tile"][a] != t or st["acc_kb"][a] != kbs[t]:
+                    raise ProtocolError(f"epilogue {w} reads accumulator {a}: tile {st['acc_tile'][a]}, {st['acc_kb'][a]}/{kbs[t]} k-blocks")
+                st["acc_read"][a].add(w)
+            yield ("do", drain)
+            yield ("arrive", tempty[a])
+
+    sim.add("tma", tma())
+    sim.add("mma", mma())
+    for w in range(n_epi):
+        sim.add(f"epi{w}", epilogue(w))
+    sim.run()
+    return sim.steps
