@@ -351,3 +351,23 @@ def test_module_selection_options_identical_to_live_reference(opts):
     n = LoRASpecialNetwork(unet=FluxTransformer2DModel(FluxConfig(**cfg), dtype=torch.float32), **base, **opts)
     assert [l.lora_name for l in r.unet_loras] == [l.lora_name for l in n.unet_loras]
     assert r.peft_format == n.peft_format and [float(l.scale) for l in r.unet_loras] == [float(l.scale) for l in n.unet_loras]
+
+
+def test_lr_scheduler_drives_the_device_hyper_buffer():
+    """`lr_scheduler.step()` after every optimizer step (SDTrainer.py:2299-2301): torch schedulers write
+    `param_groups[i]['lr']`; the fused optimizer reads its hyper-parameters from a device buffer, which `sync_hyper()`
+    (called by `step()` and by `FluxLoRATrainStep.run`) refreshes only when a value changed."""
+    from ai_toolkit_b200.optimizer import B200AdamW
+    model, net = _net()
+    opt = B200AdamW(net, lr=1e-3, eps=1e-6, weight_decay=0.0)
+    sched = torch.optim.lr_scheduler.LambdaLR(opt, lambda step: 0.5 ** step)
+    assert abs(float(opt.hyper[0]) - 1e-3) < 1e-9
+    for k in range(1, 4):
+        opt._step_count = getattr(opt, "_step_count", 0) + 1  # (silences torch's "scheduler before optimizer" warning)
+        sched.step()
+        before = opt.hyper.data_ptr()
+        opt.sync_hyper()
+        assert abs(float(opt.hyper[0]) - 1e-3 * 0.5 ** k) < 1e-9 and opt.hyper.data_ptr() == before  # same buffer (CUDA graphs)
+    host = list(opt._hyper_host)
+    opt.sync_hyper()
+    assert opt._hyper_host == host
