@@ -59,7 +59,8 @@ class B200AdamW(torch.optim.Optimizer):
         net = self.network
         if net.flat_params.device.type != "cuda":
             raise RuntimeError("B200AdamW runs on the B200 only (no CPU fallback)")
-        self.sync_hyper()  # pick up what an lr scheduler wrote into param_groups (no copy when nothing changed)
+        if not torch.cuda.is_current_stream_capturing():  # (a captured step is refreshed by FluxLoRATrainStep.run)
+            self.sync_hyper()  # pick up what an lr scheduler wrote into param_groups (no copy when nothing changed)
         ops.grad_sumsq(net.flat_grads, self.sumsq)
         ops.clip_adamw(net.flat_params, net.flat_grads, self.exp_avg, self.exp_avg_sq, self.sumsq, self.hyper, self.state_buf,
                        ema=self.ema, norm_out=self.grad_norm)
