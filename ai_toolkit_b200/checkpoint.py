@@ -95,8 +95,9 @@ def save_checkpoint(network, optimizer, save_root: str, name: str, step: Optiona
     os.makedirs(save_root, exist_ok=True)
     step_num = "" if step is None else f"_{str(step).zfill(9)}"
     save_meta = copy.deepcopy(meta) if meta is not None else OrderedDict()
-    for k, v in training_metadata(name, 0 if step is None else step, epoch, base_model_version).items():
-        save_meta.setdefault(k, v)
+    # `update_training_metadata` does `self.meta.update(...)` (BaseSDTrainProcess.py:388-409): the CURRENT step / epoch /
+    # ss_* keys overwrite whatever a loaded checkpoint's metadata carried
+    save_meta.update(training_metadata(name, 0 if step is None else step, epoch, base_model_version))
     save_meta = get_meta_for_safetensors(save_meta, name)
     lora_name = name + ("_LoRA" if named_lora else "")
     file_path = os.path.join(save_root, f"{lora_name}{step_num}.safetensors")
@@ -158,6 +159,12 @@ def resume(network, optimizer, save_root: str, name: str, pretrained_lora_path: 
     step, epoch = 0, 0
     if path is not None:
         network.load_weights(path)
+        if hasattr(network, "mark_params_changed"):
+            network.mark_params_changed()
+        # the reference builds the EMA after the weights are loaded (load_weights :2053, setup_ema :2229): the shadow
+        # starts from the LOADED parameters, not from the fresh init the optimizer was constructed on
+        if optimizer is not None and hasattr(optimizer, "reset_ema"):
+            optimizer.reset_ema()
         state = load_training_state_from_metadata(path, pretrained_lora_path)
         if state is not None:
             step, epoch = state
@@ -166,7 +173,9 @@ def resume(network, optimizer, save_root: str, name: str, pretrained_lora_path: 
         previous_lrs = [g["lr"] for g in optimizer.param_groups]
         try:
             sd = torch.load(opt_path, weights_only=True)
-            if hasattr(optimizer, "load_torch_state_dict"):
+            if isinstance(sd, dict) and sd.get("b200_flat"):  # written through B200AdamW.state_dict() (e.g. by the
+                optimizer.load_state_dict(sd)                 # reference trainer's own save(), which calls state_dict())
+            elif hasattr(optimizer, "load_torch_state_dict"):
                 optimizer.load_torch_state_dict(sd)
             else:
                 optimizer.load_state_dict(sd)

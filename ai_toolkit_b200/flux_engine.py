@@ -62,6 +62,46 @@ class FluxEngine:
         self._rope_cache[key] = out
         return out
 
+    # Linears outside the transformer blocks: computed straight from their frozen weights by this engine
+    _PRELUDE = ("x_embedder", "context_embedder", "time_text_embed.timestep_embedder.linear_1",
+                "time_text_embed.timestep_embedder.linear_2", "time_text_embed.text_embedder.linear_1",
+                "time_text_embed.text_embedder.linear_2", "time_text_embed.guidance_embedder.linear_1",
+                "time_text_embed.guidance_embedder.linear_2", "norm_out.linear", "proj_out")
+
+    def active_network(self):
+        """The LoRASpecialNetwork applied to this model, or None.  Found through the model (`apply_to` leaves a weak
+        reference) or, failing that, through ANY adapted Linear -- never through one particular layer, which
+        only_if_contains / ignore_if_contains configs may leave unadapted."""
+        ref = getattr(self.model, "_b200_network", None)
+        net = ref() if ref is not None else None
+        if net is None:
+            for mod in self.model.modules():
+                r = getattr(mod, "_b200_lora", None)
+                lora = r() if r is not None else None
+                if lora is not None and lora.network_ref is not None and lora.network_ref() is not None:
+                    net = lora.network_ref()
+                    break
+        if net is None:
+            return None
+        if getattr(self, "_checked_for", None) is not net:
+            # transformer_only=False (the class default; the trainer's NetworkConfig default is True) also wraps the
+            # embedders / norm_out / proj_out: this engine has no adapter path (nor the conditioning-vector backward they
+            # would need) for them.  Refuse instead of silently training without them.
+            for name in self._PRELUDE:
+                mod = self.model
+                try:
+                    for part in name.split("."):
+                        mod = getattr(mod, part)
+                except AttributeError:
+                    continue
+                if getattr(mod, "_b200_lora", None) is not None and mod._b200_lora() is not None:
+                    raise NotImplementedError(
+                        f"LoRA on `{name}` (transformer_only=False): the fused FLUX engine adapts the Linears under "
+                        "transformer_blocks / single_transformer_blocks only; build the network with transformer_only=True "
+                        "(the reference's NetworkConfig default, toolkit/config_modules.py:202)")
+            self._checked_for = net
+        return net
+
     def _register_groups(self, net):
         """q/k/v projections share their input: fuse each triple into one GEMM (weights re-pointed at one matrix)."""
         m = self.model
@@ -143,9 +183,8 @@ class FluxEngine:
         dev = packed.device
         if dev.type != "cuda":
             raise cabi.B200Error("FluxEngine needs a B200; there is no CPU / eager fallback")
-        net_mods = [live_lora(m.transformer_blocks[0].attn.to_q)] if len(m.transformer_blocks) else []
-        if net_mods and net_mods[0] is not None:
-            net = net_mods[0].network_ref()
+        net = self.active_network()
+        if net is not None and net.is_active and not net.is_merged_in and len(net.get_all_modules()):
             if getattr(self, "_groups_for", None) is not net:
                 self._register_groups(net)
             net.refresh_packs()
@@ -444,9 +483,11 @@ def flux_apply(model, hidden_states, timestep, encoder_hidden_states, pooled_pro
     packed = hidden_states.to(torch.bfloat16).contiguous()
     enc = encoder_hidden_states.to(torch.bfloat16).contiguous()
     pooled = pooled_projections.to(torch.bfloat16).contiguous()
-    lora0 = live_lora(model.transformer_blocks[0].attn.to_q) if len(model.transformer_blocks) else None
-    if torch.is_grad_enabled() and lora0 is not None:
-        anchor = lora0.lora_down.weight  # a leaf that requires grad, so that autograd calls our backward
+    net = model.engine.active_network()
+    mods = net.get_all_modules() if net is not None else []
+    live = bool(mods) and mods[0].is_live()
+    if torch.is_grad_enabled() and live:
+        anchor = mods[0].lora_down.weight  # a leaf that requires grad, so that autograd calls our backward
         return FluxFunction.apply(anchor, model, packed, t01, enc, pooled, g, txt_ids, img_ids)
     pred = model.engine.forward(packed, t01, enc, pooled, g, txt_ids, img_ids, save=False)
     return pred.view(B, packed.shape[1], -1)

@@ -519,6 +519,13 @@ class LoRASpecialNetwork(nn.Module):
         for lora in self.text_encoder_loras + self.unet_loras:
             lora.apply_to()
             self.add_module(lora.lora_name, lora)
+        # the fused engines find their network through the model, not through one particular Linear (module-selection
+        # options such as only_if_contains / ignore_if_contains may leave any given Linear unadapted)
+        for root in ([unet] if unet is not None and self.unet_loras else []):
+            try:
+                root._b200_network = weakref.ref(self)
+            except Exception:  # objects that refuse attributes: the engines then scan for an adapted Linear
+                pass
         self._flatten()
 
     def is_mergeable(self):

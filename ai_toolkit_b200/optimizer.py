@@ -50,6 +50,13 @@ class B200AdamW(torch.optim.Optimizer):
             self._hyper_host = vals
 
     @torch.no_grad()
+    def reset_ema(self):
+        """EMA shadow := current parameters (the reference constructs its ExponentialMovingAverage after load_weights,
+        BaseSDTrainProcess.py:2053 then :2229)."""
+        if self.ema is not None:
+            self.ema.copy_(self.network.flat_params)
+
+    @torch.no_grad()
     def zero_grad(self, set_to_none: bool = False):
         self.network.ensure_grad_views()
         self.network.flat_grads.zero_()

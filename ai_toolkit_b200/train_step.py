@@ -56,10 +56,33 @@ class FluxLoRATrainStep:
         self.txt_ids = torch.zeros(text_len, 3, device=dev)
         self.img_ids = make_img_ids(H, W, dev)
         self.loss_ws = torch.zeros(B + 1, device=dev, dtype=torch.float32)
-        self.loss_host = torch.zeros(1, dtype=torch.float32).pin_memory()
+        self.loss_host = torch.zeros(1, dtype=torch.float32)
+        if torch.device(dev).type == "cuda":
+            self.loss_host = self.loss_host.pin_memory()
+        if self.world > 1:
+            self._setup_replicas()
         self._graph_fb = None
         self._graph_opt = None
         self._warm = 0
+
+    def _setup_replicas(self):
+        """N > 1: what `accelerator.prepare(network / optimizer)` (BaseSDTrainProcess.py:744-779) would give a DDP run.
+        (1) every replica starts from rank 0's adapter values (DDP broadcasts module state at construction; lora_down is
+        drawn from each process's own RNG); (2) the all-reduce SUMS, so the 1/W of the average goes into the clip/AdamW
+        kernel (hyper[7]) -- set here, not left to the caller, because with the default 1.0 the clipping norm would be
+        W times too large; (3) the EMA shadow follows the broadcast values."""
+        net, opt = self.network, self.optimizer
+        if net.flat_params is None:
+            net._flatten()
+        torch.distributed.broadcast(net.flat_params, src=torch.distributed.get_global_rank(self.pg, 0) if self.pg is not None else 0,
+                                    group=self.pg)
+        net.mark_params_changed()
+        if opt is not None:
+            opt.grad_prescale = 1.0 / self.world
+            if getattr(opt, "ema", None) is not None:
+                opt.ema.copy_(net.flat_params)
+            opt._hyper_host = None
+            opt.sync_hyper()
 
     # -- the launch schedule -------------------------------------------------------------------------
     def _forward_backward(self):

@@ -151,3 +151,33 @@ def test_metadata_and_hashes_identical_to_live_reference():
     got = my_meta.add_model_hash_to_meta(sd, copy.deepcopy(got))
     assert got["sshs_model_hash"] == want["sshs_model_hash"] and got["sshs_legacy_hash"] == want["sshs_legacy_hash"]
     assert ck.parse_metadata_from_safetensors(got) == ref_meta.parse_metadata_from_safetensors(want)
+
+
+def test_resume_resets_ema_and_reads_both_optimizer_layouts_and_overwrites_stale_training_info(tmp_path):
+    """(1) EMA shadow after resume = the LOADED weights (the reference builds its EMA after load_weights,
+    BaseSDTrainProcess.py:2053 then :2229); (2) an optimizer.pt written through B200AdamW.state_dict() (what the reference
+    trainer's own save() calls) loads as well as the torch.optim.AdamW layout; (3) `meta` carrying a previous run's
+    training_info is overwritten with the current step (`self.meta.update`, :388-409)."""
+    root = str(tmp_path / "run")
+    _, net = _net(seed=1)
+    opt = B200AdamW(net, lr=2e-4, ema_decay=0.99)
+    opt.exp_avg.normal_()
+    opt.state_buf[0] = 7
+    stale = {"training_info": {"step": 3, "epoch": 0}, "ss_output_name": "old"}
+    path = ck.save_checkpoint(net, opt, root, "r", step=7, epoch=1, dtype=torch.float32, meta=stale)
+    assert ck.load_training_state_from_metadata(path) == (7, 1)
+    assert ck.load_metadata_from_safetensors(path)["ss_output_name"] == "r"
+    _, net2 = _net(seed=2)
+    opt2 = B200AdamW(net2, lr=1e-4, ema_decay=0.99)
+    assert not torch.equal(opt2.ema, net.flat_params)
+    ck.resume(net2, opt2, root, "r")
+    assert torch.equal(net2.flat_params, net.flat_params)
+    assert torch.equal(opt2.ema, net2.flat_params)
+    assert torch.equal(opt2.exp_avg, opt.exp_avg) and int(opt2.state_buf[0]) == 7
+    # flat layout on disk
+    torch.save(opt.state_dict(), os.path.join(root, "optimizer.pt"))
+    _, net3 = _net(seed=3)
+    opt3 = B200AdamW(net3, lr=1e-4, ema_decay=0.99)
+    ck.resume(net3, opt3, root, "r")
+    assert torch.equal(opt3.exp_avg, opt.exp_avg) and int(opt3.state_buf[0]) == 7
+    assert opt3.param_groups[0]["lr"] == 1e-4
