@@ -91,6 +91,14 @@ SIGNATURES = {
     "b200_attn_bwd": (c_int, [_V, _V, _V, _V, _V, _I, _V, _I, _V, _I, _V, _I, _V, _V, _V, _V, _V, _V, _I, _I, _I, _I, _F, _V]),
     "b200_lora_gemv_fwd": (c_int, [_V, _V, _I, _V, _I, _V, _V, _V, _I, _F, _V, _I, _V, _I, _I, _I, _V]),
     "b200_lora_gemv_bwd": (c_int, [_V, _V, _I, _V, _I, _V, _V, _V, _I, _F, _V, _V, _V, _I, _I, _I, _V]),
+    "b200_lora_gemv_fwd_rows": (c_int, [_V, _V, _I, _V, _I, _V, _V, _V, _I, _F, _V, _V, _I, _V, _I, _I, _I, _V]),
+    "b200_lora_gemv_bwd_rows": (c_int, [_V, _V, _I, _V, _I, _V, _V, _V, _I, _F, _V, _V, _V, _V, _I, _I, _I, _V]),
+    "b200_ddpm_add_noise": (c_int, [_V, _V, _V, _V, _V, _I, _V, _I, _L, _V]),
+    "b200_train_loss": (c_int, [_V, _V, _V, _V, _V, _V, _V, _V, _V, _I, _V, _V, _V, _I, _I, _I, _I, _I, _F, _V]),
+    "b200_nchw_rows": (c_int, [_V, _V, _V, _I, _I, _I, _I, _I, _V]),
+    "b200_im2col": (c_int, [_V, _V, _V, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _V]),
+    "b200_col2im": (c_int, [_V, _V, _V, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _V]),
+    "b200_mask_rows": (c_int, [_V, _V, _I, _V, _I, _V, _I, _L, _I, _V]),
     "b200_flow_add_noise": (c_int, [_V, _V, _V, _V, _V, _I, _I, _I, _I, _I, _V]),
     "b200_flow_loss": (c_int, [_V, _V, _V, _V, _V, _V, _V, _I, _I, _I, _I, _I, _F, _V]),
     "b200_grad_sumsq": (c_int, [_V, _V, _L, _V, _V]),

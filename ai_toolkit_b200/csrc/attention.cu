@@ -910,13 +910,15 @@ extern "C" int b200_attn_fwd(b200_ctx* ctx, const void* Q, const void* K, const 
   if ((rc = attn_maps(ctx, K, rows, 128, &tk))) return rc;
   if ((rc = attn_maps(ctx, V, rows, 64, &tv))) return rc;
   static bool configured = false;
-  // variant 1 (one stream, two threads per row) measured 278 us vs 304 us for variant 2 (two streams) at 24 x 4608 x 128
-  static int variant = 1;
+  // same-box log gpurun_out/r2_trip.log (round 2, 24 x 4608 x 128): variant 3 (attention_r2.cu: packed FFMA2 softmax, scale
+  // folded into the exponent FFMA) 255.3 us = 1022 TF/s; variant 4 (16 softmax warps) 256.3 us; variant 1 278.2 us;
+  // variant 2 (two streams) 304 us in round 1.  B200_ATTN_FWD=1|2|4 selects the others for A/B runs.
+  static int variant = 3;
   if (!configured) {
     B200_CUDA_CHECK(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwdSmem));
     B200_CUDA_CHECK(cudaFuncSetAttribute(attn_fwd2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwdSmem));
     const char* e = getenv("B200_ATTN_FWD");
-    if (e) variant = (atoi(e) >= 2 && atoi(e) <= 4) ? atoi(e) : 1;  // 3, 4: opt-in round-2 candidates (attention_r2.cu)
+    if (e && atoi(e) >= 1 && atoi(e) <= 5) variant = atoi(e);
     configured = true;
   }
   AttnFwdArgs a{(bf16*)o0, ld0, (bf16*)o1, ld1, (float*)lse, B, H, L, split, scale};
@@ -962,12 +964,14 @@ extern "C" int b200_attn_bwd(b200_ctx* ctx, const void* Q, const void* K, const 
   if ((rc = attn_maps(ctx, V, rows, 64, &v64))) return rc;
   if ((rc = attn_maps(ctx, dOh, rows, 64, &d64))) return rc;
   static bool configured = false;
-  static int variant = 1;
+  // same-box log gpurun_out/r2_trip.log (round 2, 24 x 4608 x 128): variant 2 (attention_r2.cu: LDS, deferred prefetch
+  // scaling, 16-column TMEM chunks) 787.7 us = 828 TF/s algorithmic; 3: 797.3; 5: 813.1; 4: 817.3; variant 1: 888.1 us
+  static int variant = 2;
   if (!configured) {
     B200_CUDA_CHECK(cudaFuncSetAttribute(attn_bwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdSmem));
     B200_CUDA_CHECK(cudaFuncSetAttribute(attn_bwd_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdSmem));
     const char* e = getenv("B200_ATTN_BWD");
-    if (e && atoi(e) >= 2 && atoi(e) <= 5) variant = atoi(e);  // opt-in round-2 candidates (attention_r2.cu)
+    if (e && atoi(e) >= 1 && atoi(e) <= 5) variant = atoi(e);
     configured = true;
   }
   dim3 grid((L + 127) / 128, B * H);

@@ -17,7 +17,8 @@ constexpr int kMaxRank = 128;
 
 // z[b, j] = c * sum_k x[b,k] A[j,k]          one warp per (b, j)
 __global__ void __launch_bounds__(256) lora_gemv_down_kernel(const bf16* __restrict__ x, int ldx, const float* __restrict__ A,
-                                                             float c, float* __restrict__ z, int Bm, int r, int K) {
+                                                             float c, const float* __restrict__ row_c,
+                                                             float* __restrict__ z, int Bm, int r, int K) {
   pdl_grid_sync();
   const int w = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
@@ -28,7 +29,7 @@ __global__ void __launch_bounds__(256) lora_gemv_down_kernel(const bf16* __restr
   float acc = 0.f;
   for (int k = lane; k < K; k += 32) acc += __bfloat162float(xr[k]) * ar[k];
   acc = warp_sum(acc);
-  if (lane == 0) z[b * r + j] = c * acc;
+  if (lane == 0) z[b * r + j] = c * (row_c ? row_c[b] : 1.0f) * acc;  // per-sample multiplier (network_mixins.py:311-322)
 }
 
 // y[b, n] for all b; one warp per n.  x is staged in shared memory once per block.
@@ -86,7 +87,8 @@ __global__ void __launch_bounds__(256) lora_gemv_fwd_kernel(const bf16* __restri
 // blocks [nb_db, ..): t[b, j]   += c * sum_{n in 256-row slab} dy[b,n] Bw[n,j]   (thread (sub, j): j fastest, so the
 //                     reads of Bw rows are coalesced; fp32 atomics into t, which the caller zeroed)
 __global__ void __launch_bounds__(256) lora_gemv_bwd1_kernel(const float* __restrict__ dy, int lddy, const float* __restrict__ z,
-                                                             const float* __restrict__ Bw, float c, float* __restrict__ dBw,
+                                                             const float* __restrict__ Bw, float c,
+                                                             const float* __restrict__ row_c, float* __restrict__ dBw,
                                                              float* __restrict__ t, int Bm, int r, int N, int nb_db) {
   pdl_grid_sync();
   if (static_cast<int>(blockIdx.x) < nb_db) {
@@ -113,7 +115,7 @@ __global__ void __launch_bounds__(256) lora_gemv_bwd1_kernel(const float* __rest
     }
 #pragma unroll
     for (int b = 0; b < kMaxRows; ++b)
-      if (b < Bm) atomicAdd(t + b * r + j, c * acc[b]);
+      if (b < Bm) atomicAdd(t + b * r + j, c * (row_c ? row_c[b] : 1.0f) * acc[b]);
   }
 }
 
@@ -136,6 +138,12 @@ using namespace b200;
 extern "C" int b200_lora_gemv_fwd(b200_ctx* ctx, const void* x, int ldx, const void* W, int ldw, const void* bias,
                                   const void* A, const void* Bw, int r, float c, void* y, int ldy, void* z, int Bm, int N,
                                   int K, void* stream) {
+  return b200_lora_gemv_fwd_rows(ctx, x, ldx, W, ldw, bias, A, Bw, r, c, nullptr, y, ldy, z, Bm, N, K, stream);
+}
+
+extern "C" int b200_lora_gemv_fwd_rows(b200_ctx* ctx, const void* x, int ldx, const void* W, int ldw, const void* bias,
+                                       const void* A, const void* Bw, int r, float c, const void* row_c, void* y, int ldy,
+                                       void* z, int Bm, int N, int K, void* stream) {
   int rc = check_ctx(ctx);
   if (rc) return rc;
   B200_REQUIRE(x && W && y && Bm >= 1 && Bm <= kMaxRows && N > 0 && K > 0, "b200_lora_gemv_fwd: bad args Bm=%d N=%d K=%d", Bm,
@@ -145,7 +153,7 @@ extern "C" int b200_lora_gemv_fwd(b200_ctx* ctx, const void* x, int ldx, const v
   if (r > 0) B200_REQUIRE(A && Bw && z, "b200_lora_gemv_fwd: rank > 0 needs A, B and z");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (r > 0) {
-    B200_KLAUNCH(lora_gemv_down_kernel, (Bm * r + 7) / 8, 256, 0, st, (const bf16*)x, ldx, (const float*)A, c, (float*)z, Bm, r, K);
+    B200_KLAUNCH(lora_gemv_down_kernel, (Bm * r + 7) / 8, 256, 0, st, (const bf16*)x, ldx, (const float*)A, c, (const float*)row_c, (float*)z, Bm, r, K);
     B200_CUDA_CHECK(cudaGetLastError());
     ctx->launches.fetch_add(1);
   }
@@ -171,6 +179,12 @@ extern "C" int b200_lora_gemv_fwd(b200_ctx* ctx, const void* x, int ldx, const v
 extern "C" int b200_lora_gemv_bwd(b200_ctx* ctx, const void* dy, int lddy, const void* x, int ldx, const void* z,
                                   const void* A, const void* Bw, int r, float c, void* dA, void* dBw, void* t_ws, int Bm,
                                   int N, int K, void* stream) {
+  return b200_lora_gemv_bwd_rows(ctx, dy, lddy, x, ldx, z, A, Bw, r, c, nullptr, dA, dBw, t_ws, Bm, N, K, stream);
+}
+
+extern "C" int b200_lora_gemv_bwd_rows(b200_ctx* ctx, const void* dy, int lddy, const void* x, int ldx, const void* z,
+                                       const void* A, const void* Bw, int r, float c, const void* row_c, void* dA, void* dBw,
+                                       void* t_ws, int Bm, int N, int K, void* stream) {
   int rc = check_ctx(ctx);
   if (rc) return rc;
   B200_REQUIRE(dy && x && z && A && Bw && dA && dBw && t_ws, "b200_lora_gemv_bwd: null argument");
@@ -180,7 +194,7 @@ extern "C" int b200_lora_gemv_bwd(b200_ctx* ctx, const void* dy, int lddy, const
   const int nb_t = (N + 255) / 256;
   B200_CUDA_CHECK(cudaMemsetAsync(t_ws, 0, sizeof(float) * Bm * r, st));
   B200_KLAUNCH(lora_gemv_bwd1_kernel, nb_db + nb_t, 256, 0, st, (const float*)dy, lddy, (const float*)z, (const float*)Bw, c,
-                                                      (float*)dBw, (float*)t_ws, Bm, r, N, nb_db);
+                                                      (const float*)row_c, (float*)dBw, (float*)t_ws, Bm, r, N, nb_db);
   B200_CUDA_CHECK(cudaGetLastError());
   const int nb_da = static_cast<int>((static_cast<long long>(r) * K + 255) / 256);
   B200_KLAUNCH(lora_gemv_bwd2_kernel, nb_da, 256, 0, st, (const float*)t_ws, (const bf16*)x, ldx, (float*)dA, Bm, r, K);

@@ -152,21 +152,26 @@ class FluxEngine:
         lora = live_lora(lin)
         if lora is None:
             y, _ = ops.lora_gemv_fwd(temb_silu, lin.weight, lin.bias)
-            return y, None, 0.0
-        alpha, row_alpha, _ = lora_coeff(lora, temb_silu.shape[0])
+            return y, None, (0.0, None)
+        # per-sample multipliers (SDTrainer.py:1558 -> network_mixins.py:311-322): one row of the conditioning vector per
+        # sample, so the per-sample coefficient is a per-row coefficient of the GEMV (alpha, row_c) saved for the backward
+        alpha, row_alpha, rps = lora_coeff(lora, temb_silu.shape[0])
+        row_c = None
         if row_alpha is not None:
-            raise NotImplementedError("per-sample multipliers with the fused FLUX engine")
-        y, z = ops.lora_gemv_fwd(temb_silu, lin.weight, lin.bias, lora.down_weight_2d(), lora.up_weight_2d(), alpha)
-        return y, z, alpha
+            row_c = row_alpha.repeat_interleave(rps).contiguous() if rps > 1 else row_alpha
+        y, z = ops.lora_gemv_fwd(temb_silu, lin.weight, lin.bias, lora.down_weight_2d(), lora.up_weight_2d(), alpha,
+                                 row_c=row_c)
+        return y, z, (alpha, row_c)
 
     @staticmethod
     def _mod_bwd(lin, dmod, temb_silu, z, alpha):
         lora = live_lora(lin)
         if lora is None:
             return
+        alpha, row_c = alpha
         ops.lora_gemv_bwd(dmod, temb_silu, z, lora.down_weight_2d(), lora.up_weight_2d(), alpha,
                           lora.lora_down.weight.grad.view(lora.lora_dim, lora.in_dim),
-                          lora.lora_up.weight.grad.view(lora.out_dim, lora.lora_dim))
+                          lora.lora_up.weight.grad.view(lora.out_dim, lora.lora_dim), row_c=row_c)
 
     # ------------------------------------------------------------------------------------------
     # forward
@@ -187,6 +192,9 @@ class FluxEngine:
         if net is not None and net.is_active and not net.is_merged_in and len(net.get_all_modules()):
             if getattr(self, "_groups_for", None) is not net:
                 self._register_groups(net)
+            if any(mod.has_dropout() or (mod.module_dropout and mod.training) for mod in net.get_all_modules()):
+                raise NotImplementedError("dropout / rank_dropout / module_dropout with the fused FLUX engine: use the "
+                                          "per-module path (LoRAModule.forward) or set them to None (the reference default)")
             net.refresh_packs()
             net.ensure_grad_views()
         cos, sin = self.rope_tables(txt_ids, img_ids)

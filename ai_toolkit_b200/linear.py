@@ -61,7 +61,7 @@ def lora_coeff(lora, n_rows: int):
     return lora.scale, tm.to(torch.float32).contiguous(), n_rows // nb
 
 
-def linear_fwd(lin, x2, out, *, lora=None, zc_out=None, **epi):
+def linear_fwd(lin, x2, out, *, lora=None, zc_out=None, zc_hook=None, **epi):
     """out = epilogue(x2 @ W^T [+ adapter] + bias).  Returns Zc (saved for backward) or None."""
     W = lin.weight if lin.weight.dim() == 2 else lin.weight.view(lin.weight.shape[0], -1)
     if lora is None:
@@ -70,11 +70,13 @@ def linear_fwd(lin, x2, out, *, lora=None, zc_out=None, **epi):
     alpha, row_alpha, rps = lora_coeff(lora, x2.shape[0])
     zc = zc_out if zc_out is not None else torch.empty((x2.shape[0], RANK_PAD), device=x2.device, dtype=torch.bfloat16)
     gemm_bf16(x2, lora.a_pack, zc, alpha=alpha, row_alpha=row_alpha, rows_per_sample=rps)  # cluster split-K skinny GEMM
+    if zc_hook is not None:  # dropout / rank-dropout masks on the rank-side activation (network_mixins.py:211-226)
+        zc_hook(zc)
     gemm_bf16(x2, W, out, a1=zc, b1=lora.b_pack, bias=lin.bias, **epi)
     return zc
 
 
-def linear_bwd(lin, dy, x2, zc, dx_out, *, lora=None, n_slices=None, **epi):
+def linear_bwd(lin, dy, x2, zc, dx_out, *, lora=None, n_slices=None, t_hook=None, **epi):
     """dX (into dx_out, may be None) and, with an adapter, accumulation of dA / dB into their `.grad` views.
 
     n_slices: optional list of (col0, col1, epi_kwargs) to produce dX in column ranges with different epilogues
@@ -85,6 +87,8 @@ def linear_bwd(lin, dy, x2, zc, dx_out, *, lora=None, n_slices=None, **epi):
         alpha, row_alpha, rps = lora_coeff(lora, dy.shape[0])
         t = torch.empty((dy.shape[0], RANK_PAD), device=dy.device, dtype=torch.bfloat16)
         gemm_bf16(dy, lora.b_pack, t, trans_b=True, alpha=alpha, row_alpha=row_alpha, rows_per_sample=rps)
+        if t_hook is not None:
+            t_hook(t)
     if dx_out is not None:
         slices = n_slices if n_slices is not None else [(0, W.shape[1], epi)]
         for c0, c1, e in slices:

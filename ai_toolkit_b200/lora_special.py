@@ -51,32 +51,39 @@ class LoRAModule(nn.Module):
         self.lora_name = lora_name
         self.orig_module_ref = weakref.ref(org_module)
         cls = org_module.__class__.__name__
+        self.lora_dim = int(lora_dim)
+        if self.lora_dim > RANK_PAD:
+            raise NotImplementedError(f"rank {self.lora_dim} > {RANK_PAD}")
         if cls in CONV_MODULES:
-            if tuple(org_module.kernel_size) != (1, 1):
-                raise NotImplementedError(f"{lora_name}: only Linear and 1x1 Conv2d adapters are implemented "
-                                          "(3x3 conv LoRA is a SURVEY.md section 8(f) 'next' row)")
-            in_dim, out_dim = org_module.in_channels, org_module.out_channels
+            # lora_special.py:95-104: down = Conv2d(in, r, k, stride, padding), up = Conv2d(r, out, 1x1).  Here both (and
+            # the frozen conv) are ONE fused GEMM over im2col rows [B Ho Wo, in*kh*kw]; `in_dim` is that contraction length
+            if getattr(org_module, "groups", 1) != 1 or tuple(getattr(org_module, "dilation", (1, 1))) != (1, 1):
+                raise NotImplementedError(f"{lora_name}: grouped / dilated Conv2d adapters are not implemented")
+            if isinstance(org_module.padding, str):
+                raise NotImplementedError(f"{lora_name}: string padding modes are not implemented")
+            self.kernel_size = tuple(org_module.kernel_size)
+            self.stride, self.padding = tuple(org_module.stride), tuple(org_module.padding)
+            self.in_channels = org_module.in_channels
+            in_dim, out_dim = org_module.in_channels * self.kernel_size[0] * self.kernel_size[1], org_module.out_channels
+            if in_dim % 8 != 0 or out_dim % 8 != 0:
+                raise NotImplementedError(f"{lora_name}: conv adapter needs in*kh*kw ({in_dim}) and out ({out_dim}) % 8 == 0")
             self.is_conv = True
+            self.lora_down = nn.Conv2d(self.in_channels, self.lora_dim, self.kernel_size, self.stride, self.padding, bias=False)
+            self.lora_up = nn.Conv2d(self.lora_dim, out_dim, (1, 1), (1, 1), bias=False)
         else:
             in_dim, out_dim = org_module.in_features, org_module.out_features
             self.is_conv = False
+            self.lora_down = nn.Linear(in_dim, self.lora_dim, bias=False)
+            self.lora_up = nn.Linear(self.lora_dim, out_dim, bias=False)
         if org_module.bias is None:
             use_bias = False
         if use_bias:
             raise NotImplementedError("use_bias (LoRM) adapters are not implemented")
-        if dropout or rank_dropout or module_dropout:
-            raise NotImplementedError("dropout / rank_dropout / module_dropout are not implemented (reference default: None)")
+        for nm, pv in (("dropout", dropout), ("rank_dropout", rank_dropout), ("module_dropout", module_dropout)):
+            if pv is not None and not isinstance(pv, (int, float)):
+                raise NotImplementedError(f"{nm} must be a float or None")
         self.in_dim, self.out_dim = in_dim, out_dim
-        self.lora_dim = int(lora_dim)
-        if self.lora_dim > RANK_PAD:
-            raise NotImplementedError(f"rank {self.lora_dim} > {RANK_PAD}")
         self.full_rank = False
-        if self.is_conv:
-            self.lora_down = nn.Conv2d(in_dim, self.lora_dim, (1, 1), (1, 1), bias=False)
-            self.lora_up = nn.Conv2d(self.lora_dim, out_dim, (1, 1), (1, 1), bias=False)
-        else:
-            self.lora_down = nn.Linear(in_dim, self.lora_dim, bias=False)
-            self.lora_up = nn.Linear(self.lora_dim, out_dim, bias=False)
         if isinstance(alpha, torch.Tensor):
             alpha = float(alpha.detach().float().item())
         alpha = self.lora_dim if alpha is None or alpha == 0 else alpha
@@ -129,8 +136,15 @@ class LoRAModule(nn.Module):
             return False
         return True
 
+    def has_dropout(self) -> bool:
+        """dropout / rank_dropout draw masks only in training mode (network_mixins.py:211-226)."""
+        return self.training and bool((self.dropout and self.dropout > 0) or (self.rank_dropout and self.rank_dropout > 0))
+
     def forward(self, x, *args, **kwargs):
         if not self.is_live():
+            return self.org_forward(x, *args, **kwargs)
+        # module dropout (network_mixins.py:198-201): the adapter's contribution is 0.0 for this call
+        if self.module_dropout is not None and self.training and torch.rand(1) < self.module_dropout:
             return self.org_forward(x, *args, **kwargs)
         from .autograd import lora_linear  # late import: needs the CUDA library only when actually active
 
@@ -158,8 +172,50 @@ class LoRAModule(nn.Module):
     def reset_weights(self):
         self.lora_up.weight.zero_()
 
-    def extract_weight(self, *args, **kwargs):
-        raise NotImplementedError("extract_weight (LoRA extraction from a tuned model) is outside the training hot path")
+    @torch.no_grad()
+    def extract_weight(self, extract_mode="existing", extract_mode_param=None, _reflatten=True):
+        """LoRM-style extraction (network_mixins.py:113-168 + toolkit/lorm.py:210-260): truncated SVD of the wrapped layer's
+        OWN weight -> lora_up = U_r diag(S_r), lora_down = Vh_r; the adapter takes the extracted rank, alpha = rank, and
+        the runtime scale is re-synchronised (pinned by testing/test_lora_compile_scalars.py:72-92).  Set-up-time host
+        mathematics (torch.linalg.svd), not hot path."""
+        if extract_mode == "existing":
+            extract_mode, extract_mode_param = "fixed", self.lora_dim
+        w = self.org_module[0].weight.detach().clone().float()
+        out_ch = w.shape[0]
+        w2 = w.reshape(out_ch, -1)
+        in_ch = w2.shape[1]
+        U, S, Vh = torch.linalg.svd(w2)
+        if extract_mode == "percentage":
+            rank = int(float(extract_mode_param) * out_ch * in_ch / (in_ch + out_ch))
+        elif extract_mode == "fixed":
+            rank = int(extract_mode_param)
+        elif extract_mode == "threshold":
+            rank = int((S > float(extract_mode_param)).sum())
+        elif extract_mode == "ratio":
+            rank = int((S > S.max() * float(extract_mode_param)).sum())
+        elif extract_mode == "quantile":
+            rank = int((torch.cumsum(S, 0) < float(extract_mode_param) * S.sum()).sum())
+        else:
+            raise NotImplementedError('Extract mode should be "fixed", "threshold", "ratio" or "quantile"')
+        rank = min(out_ch, in_ch, max(1, rank))
+        if rank >= out_ch / 2:
+            rank = int(out_ch / 2)
+        if rank > RANK_PAD:
+            raise NotImplementedError(f"extracted rank {rank} > {RANK_PAD}")
+        dev = self.lora_down.weight.device
+        up = (U[:, :rank] @ torch.diag(S[:rank])).reshape(out_ch, rank)
+        down = Vh[:rank, :].reshape(rank, in_ch)
+        self.lora_dim = rank
+        if self.is_conv:
+            down = down.view(rank, self.in_channels, *self.kernel_size)
+            up = up.view(out_ch, rank, 1, 1)
+        self.lora_down.weight = nn.Parameter(down.to(dev, torch.float32).clone())
+        self.lora_up.weight = nn.Parameter(up.to(dev, torch.float32).clone())
+        self.alpha = (self.alpha * 0) + rank
+        self._set_runtime_scale(float(self.alpha.detach().float().item()) / self.lora_dim)
+        net = self.network_ref() if self.network_ref is not None else None
+        if _reflatten and net is not None and net.flat_params is not None:
+            net._flatten()  # shapes changed: rebuild the flat views and operand packs
 
 
 class FusedGroup:
@@ -245,8 +301,6 @@ class LoRASpecialNetwork(nn.Module):
             alpha = self.alpha
             self.conv_alpha = self.conv_lora_dim
             conv_alpha = self.conv_alpha
-        if conv_lora_dim is not None and conv_lora_dim > 0:
-            raise NotImplementedError("conv_lora_dim (3x3 conv LoRA) is not implemented")
         # the reference's defaults are kohya's class attributes, not this class's (lora_special.py:331-332,
         # kohya_lora.py:750-751): LoRA goes on the Linear / 1x1-conv layers inside `Transformer2DModel` blocks
         if target_lin_modules is None:
@@ -304,8 +358,10 @@ class LoRASpecialNetwork(nn.Module):
                             dim, alpha_ = modules_dim[lora_name], modules_alpha[lora_name]
                     elif is_linear or is_conv2d_1x1:
                         dim, alpha_ = self.lora_dim, self.alpha
+                    elif self.conv_lora_dim is not None:  # k x k convs (lora_special.py:585-587)
+                        dim, alpha_ = self.conv_lora_dim, self.conv_alpha
                     if dim is None or dim == 0:
-                        if is_linear or is_conv2d_1x1:
+                        if is_linear or is_conv2d_1x1 or self.conv_lora_dim is not None or conv_block_dims is not None:
                             skipped.append(lora_name)
                         continue
                     loras.append(module_class(lora_name, child_module, self.multiplier, dim, alpha_, dropout=dropout,
@@ -324,7 +380,7 @@ class LoRASpecialNetwork(nn.Module):
                 te_loras, _ = create_modules(False, index, te, replace)
                 self.text_encoder_loras.extend(te_loras)
         target_modules = list(target_lin_modules)
-        if modules_dim is not None:
+        if modules_dim is not None or self.conv_lora_dim is not None or conv_block_dims is not None:  # :679-681
             target_modules += list(target_conv_modules or KOHYA_UNET_TARGET_REPLACE_MODULE_CONV2D_3X3)
         if is_v3:
             target_modules = ["SD3Transformer2DModel"]
@@ -631,6 +687,15 @@ class LoRASpecialNetwork(nn.Module):
         self.is_merged_in = False
         for m in self.get_all_modules():
             m.merge_out(merge_weight)
+
+    def extract_weight(self, extract_mode="existing", extract_mode_param=None):
+        """network_mixins.py:908-919: every adapter re-initialised from the SVD of its wrapped layer."""
+        if extract_mode_param is None:
+            raise ValueError("extract_mode_param must be set")
+        for m in self.get_all_modules():
+            m.extract_weight(extract_mode=extract_mode, extract_mode_param=extract_mode_param, _reflatten=False)
+        if self.flat_params is not None:
+            self._flatten()
 
     # -- state dict / files (network_mixins.py:525-789) ------------------------------------------
     def get_keymap(self, force_weight_mapping=False):

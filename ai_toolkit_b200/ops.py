@@ -97,25 +97,26 @@ def add_bf16(a, b, c=None, out=None):
     return out
 
 
-def lora_gemv_fwd(x, W, bias, A=None, Bw=None, c=1.0, out=None):
-    """x [Bm, K] bf16, W [N, K] bf16, A [r, K] fp32, Bw [N, r] fp32 -> (y [Bm, N] bf16, z [Bm, r] fp32 | None)."""
+def lora_gemv_fwd(x, W, bias, A=None, Bw=None, c=1.0, out=None, row_c=None):
+    """x [Bm, K] bf16, W [N, K] bf16, A [r, K] fp32, Bw [N, r] fp32 -> (y [Bm, N] bf16, z [Bm, r] fp32 | None).
+    row_c: optional fp32 [Bm] per-row coefficient (per-sample multipliers), multiplied with c."""
     Bm, K = x.shape
     N = W.shape[0]
     r = 0 if A is None else int(A.shape[0])
     y = torch.empty((Bm, N), device=x.device, dtype=torch.bfloat16) if out is None else out
     z = torch.empty((Bm, r), device=x.device, dtype=torch.float32) if r > 0 else None
-    cabi.call("b200_lora_gemv_fwd", _p(x), _ld(x), _p(W), _ld(W), _p(bias), _p(A), _p(Bw), r, float(c), _p(y), _ld(y),
-              _p(z), Bm, N, K, device=_dev(x))
+    cabi.call("b200_lora_gemv_fwd_rows", _p(x), _ld(x), _p(W), _ld(W), _p(bias), _p(A), _p(Bw), r, float(c), _p(row_c), _p(y),
+              _ld(y), _p(z), Bm, N, K, device=_dev(x))
     return y, z
 
 
-def lora_gemv_bwd(dy, x, z, A, Bw, c, dA, dBw, t_ws=None):
+def lora_gemv_bwd(dy, x, z, A, Bw, c, dA, dBw, t_ws=None, row_c=None):
     """dy fp32 [Bm, N] (row stride = stride(0)); accumulates into dA [r, K], dBw [N, r] (fp32)."""
     Bm, K = x.shape
     N, r = Bw.shape
     t_ws = torch.empty(Bm * r, device=x.device, dtype=torch.float32) if t_ws is None else t_ws
-    cabi.call("b200_lora_gemv_bwd", _p(dy), int(dy.stride(0)), _p(x), _ld(x), _p(z), _p(A), _p(Bw), r, float(c), _p(dA),
-              _p(dBw), _p(t_ws), Bm, N, K, device=_dev(x))
+    cabi.call("b200_lora_gemv_bwd_rows", _p(dy), int(dy.stride(0)), _p(x), _ld(x), _p(z), _p(A), _p(Bw), r, float(c),
+              _p(row_c), _p(dA), _p(dBw), _p(t_ws), Bm, N, K, device=_dev(x))
 
 
 def flow_add_noise(latents, noise, t, pack=True, out=None):
@@ -138,6 +139,86 @@ def flow_loss(pred, latents, noise, pack=True, gscale=1.0, dpred=None, want_grad
     cabi.call("b200_flow_loss", _p(pred), _p(latents), _p(noise), _p(dpred if want_grad else None), _p(per), _p(tot), B, C,
               H, W, int(pack), float(gscale), device=_dev(pred))
     return tot, per, dpred
+
+
+def train_loss(pred, latents, noise, *, target=None, coef_noise=None, coef_latent=None, sample_weight=None, mask=None,
+               pack=False, gscale=1.0, dpred=None, want_grad=True, loss_ws=None):
+    """The default 'mse' path of `SDTrainer.calculate_loss` (SDTrainer.py:522-1052) in one launch; see include/b200_lora.h.
+    latents gives the geometry [B, C, H, W] (5-D video latents [B, C, T, H, W] are folded to [B, C, T*H, W]);
+    -> (loss_total [1] fp32, loss_per_sample [B] fp32, dpred like pred)."""
+    shp = latents.shape if latents is not None else target.shape
+    if len(shp) == 5:
+        B, C, H, W = shp[0], shp[1], shp[2] * shp[3], shp[4]
+    else:
+        B, C, H, W = shp
+    if want_grad and dpred is None:
+        dpred = torch.empty_like(pred)
+    if loss_ws is None:
+        loss_ws = torch.empty(B + 1, device=pred.device, dtype=torch.float32)
+    per, tot = loss_ws[:B], loss_ws[B:B + 1]
+    mc = 0
+    if mask is not None:
+        assert mask.dtype == torch.float32 and mask.is_contiguous()
+        mc = int(mask.shape[1])
+    cabi.call("b200_train_loss", _p(pred), _p(latents), _p(noise), _p(target), _p(coef_noise), _p(coef_latent),
+              _p(sample_weight), _p(mask), mc, _p(dpred if want_grad else None), _p(per), _p(tot), int(B), int(C), int(H),
+              int(W), int(pack), float(gscale), device=_dev(pred))
+    return tot, per, dpred
+
+
+def ddpm_add_noise(latents, noise, timesteps_i64, alphas_cumprod, out=None):
+    """DDPMScheduler.add_noise (toolkit/sampler.py:31-50 config) on bf16 latents with integer timesteps."""
+    B = latents.shape[0]
+    per = latents.numel() // B
+    out = torch.empty_like(latents) if out is None else out
+    assert timesteps_i64.dtype == torch.int64 and alphas_cumprod.dtype == torch.float32
+    cabi.call("b200_ddpm_add_noise", _p(latents), _p(noise), _p(timesteps_i64), _p(alphas_cumprod),
+              int(alphas_cumprod.numel()), _p(out), int(B), int(per), device=_dev(latents))
+    return out
+
+
+def nchw_to_rows(x, out=None):
+    """[B, C, H, W] bf16 contiguous -> rows [B*H*W, C] (channels-last rows: the operand layout of the fused GEMM)."""
+    B, C, H, W = x.shape
+    out = torch.empty((B * H * W, C), device=x.device, dtype=torch.bfloat16) if out is None else out
+    cabi.call("b200_nchw_rows", _p(x), _p(out), int(B), int(C), int(H * W), int(out.stride(0)), 1, device=_dev(x))
+    return out
+
+
+def rows_to_nchw(rows, B, C, H, W, out=None):
+    out = torch.empty((B, C, H, W), device=rows.device, dtype=torch.bfloat16) if out is None else out
+    cabi.call("b200_nchw_rows", _p(rows), _p(out), int(B), int(C), int(H * W), int(rows.stride(0)), 0, device=_dev(rows))
+    return out
+
+
+def conv_out_hw(H, W, k, s, p):
+    return (H + 2 * p[0] - k[0]) // s[0] + 1, (W + 2 * p[1] - k[1]) // s[1] + 1
+
+
+def im2col(x, k, s, p, out=None):
+    """[B, C, H, W] bf16 -> rows [B*Ho*Wo, ld] with ld = C*kh*kw rounded up to 8 (zero columns), order (c, ky, kx)."""
+    B, C, H, W = x.shape
+    Ho, Wo = conv_out_hw(H, W, k, s, p)
+    ld = (C * k[0] * k[1] + 7) // 8 * 8
+    out = torch.empty((B * Ho * Wo, ld), device=x.device, dtype=torch.bfloat16) if out is None else out
+    cabi.call("b200_im2col", _p(x), _p(out), int(B), int(C), int(H), int(W), int(k[0]), int(k[1]), int(s[0]), int(s[1]),
+              int(p[0]), int(p[1]), int(out.stride(0)), device=_dev(x))
+    return out
+
+
+def col2im(dcols, shape, k, s, p, out=None, accumulate=False):
+    B, C, H, W = shape
+    out = torch.empty((B, C, H, W), device=dcols.device, dtype=torch.bfloat16) if out is None else out
+    cabi.call("b200_col2im", _p(dcols), _p(out), int(B), int(C), int(H), int(W), int(k[0]), int(k[1]), int(s[0]), int(s[1]),
+              int(p[0]), int(p[1]), int(dcols.stride(0)), int(bool(accumulate)), device=_dev(dcols))
+    return out
+
+
+def mask_rows(z, cols, row_mask=None, col_mask=None, rows_per_sample=0):
+    """z[:, :cols] *= row_mask [rows, cols] * col_mask [samples, cols] (fp32, either may be None), in place."""
+    cabi.call("b200_mask_rows", _p(z), int(z.stride(0)), _p(row_mask), 0 if row_mask is None else int(row_mask.stride(0)),
+              _p(col_mask), int(rows_per_sample), int(z.shape[0]), int(cols), device=_dev(z))
+    return z
 
 
 def grad_sumsq(g, out_f64):

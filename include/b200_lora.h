@@ -190,6 +190,16 @@ int b200_lora_gemv_bwd(b200_ctx* ctx, const void* dy, int lddy, const void* x, i
                        const void* Bw, int r, float c, void* dA, void* dBw, void* t_ws, int Bm, int N, int K,
                        void* stream);
 
+/* Same with a per-row coefficient: row r uses c * row_c[r] (row_c fp32 [Bm], may be NULL).  The per-sample
+ * `network.multiplier` list of the trainer (SDTrainer.py:1558 -> toolkit/network_mixins.py:311-322) on modules whose
+ * input is the [B, D] conditioning vector. */
+int b200_lora_gemv_fwd_rows(b200_ctx* ctx, const void* x, int ldx, const void* W, int ldw, const void* bias, const void* A,
+                            const void* Bw, int r, float c, const void* row_c, void* y, int ldy, void* z, int Bm, int N,
+                            int K, void* stream);
+int b200_lora_gemv_bwd_rows(b200_ctx* ctx, const void* dy, int lddy, const void* x, int ldx, const void* z, const void* A,
+                            const void* Bw, int r, float c, const void* row_c, void* dA, void* dBw, void* t_ws, int Bm,
+                            int N, int K, void* stream);
+
 /* -------------------------------------------------------------------------------------------------
  * Flow-matching batch preparation and loss.
  * b200_flow_add_noise: out = bf16((1 - t/1000) x0 + (t/1000) noise), optionally written in FLUX's packed
@@ -205,6 +215,46 @@ int b200_flow_add_noise(b200_ctx* ctx, const void* latents, const void* noise, c
 int b200_flow_loss(b200_ctx* ctx, const void* pred, const void* latents, const void* noise, void* dpred,
                    void* loss_per_sample, void* loss_total, int B, int C, int H, int W, int pack, float gscale,
                    void* stream);
+
+/* -------------------------------------------------------------------------------------------------
+ * eps / v-prediction models (SD1.5, SDXL) and the non-default branches of `calculate_loss`.
+ * b200_ddpm_add_noise: diffusers DDPMScheduler.add_noise as built by toolkit/sampler.py:31-50,120-185 and called
+ *   through toolkit/stable_diffusion_model.py:1854-1876 with INTEGER timesteps: noisy = sqrt(ac[t]) x0 +
+ *   sqrt(1 - ac[t]) noise in bf16 tensor arithmetic (table value, both roots and both products rounded to bf16).
+ *   timesteps int64 [B]; alphas_cumprod fp32 [n_train]; per_sample = C H W (even).
+ * b200_train_loss: the default 'mse' path of SDTrainer.calculate_loss (SDTrainer.py:522-1052):
+ *   target = `target` if given (prior prediction :619-621, or anything precomputed)
+ *          | bf16(bf16(coef_noise[b] noise) - bf16(coef_latent[b] x0))   coef NULL = 1: flow matching (:644-646);
+ *            (1, 0): eps (:650); (sqrt(ac), sqrt(1-ac)): v-prediction (:623-625, DDPMScheduler.get_velocity)
+ *   loss_per_sample[b] = sample_weight[b] * mean((pred - target)^2 * mask[b, (c), h, w])      (:916, :923-959, :987-1011;
+ *     timestep weights, loss_multiplier and SNR-gamma weights are per-sample scalars: the caller multiplies them into
+ *     sample_weight, fp32 [B] or NULL; mask fp32 [B, mask_channels in {1, C}, H, W] or NULL)
+ *   loss_total = mean_b (:1013); dpred = bf16(d loss_total / d pred * gscale) in pred's layout (pack as b200_flow_loss).
+ */
+int b200_ddpm_add_noise(b200_ctx* ctx, const void* latents, const void* noise, const void* timesteps_i64,
+                        const void* alphas_cumprod_f32, int n_train, void* out, int B, int64_t per_sample, void* stream);
+int b200_train_loss(b200_ctx* ctx, const void* pred, const void* latents, const void* noise, const void* target,
+                    const void* coef_noise, const void* coef_latent, const void* sample_weight, const void* mask,
+                    int mask_channels, void* dpred, void* loss_per_sample, void* loss_total, int B, int C, int H, int W,
+                    int pack, float gscale, void* stream);
+
+/* -------------------------------------------------------------------------------------------------
+ * Conv2d LoRA (toolkit/lora_special.py:95-104: lora_down = Conv2d(in, r, k, stride, padding), lora_up = 1x1) and the
+ * frozen Conv2d it wraps, as the SAME fused tcgen05 GEMM as a Linear over rows [B Ho Wo, C kh kw]:
+ * b200_nchw_rows: to_rows = 1: NCHW bf16 [B, C, HW] -> rows [B HW, ld_rows] (first C columns); 0: the inverse.
+ * b200_im2col: cols[(b, oy, ox), (c, ky, kx)] = x[b, c, oy sh + ky - ph, ox sw + kx - pw] (0 outside), the column order
+ *   of `weight.view(out, -1)`; columns [C kh kw, ld) are zero-filled.
+ * b200_col2im: the adjoint (gather form, deterministic): dx (+)= sum of the matching dcols entries.
+ * b200_mask_rows: z[row, col] *= row_mask[row, col] * col_mask[sample(row), col]  (either may be NULL): the dropout /
+ *   rank-dropout masks of toolkit/network_mixins.py:197-239 on the rank-side activations.
+ */
+int b200_nchw_rows(b200_ctx* ctx, const void* src, void* dst, int B, int C, int HW, int ld_rows, int to_rows, void* stream);
+int b200_im2col(b200_ctx* ctx, const void* x, void* cols, int B, int C, int H, int W, int kh, int kw, int sh, int sw, int ph,
+                int pw, int ld, void* stream);
+int b200_col2im(b200_ctx* ctx, const void* dcols, void* dx, int B, int C, int H, int W, int kh, int kw, int sh, int sw, int ph,
+                int pw, int ld, int accumulate, void* stream);
+int b200_mask_rows(b200_ctx* ctx, void* z, int ldz, const void* row_mask, int ldm, const void* col_mask, int rows_per_sample,
+                   int64_t rows, int cols, void* stream);
 
 /* -------------------------------------------------------------------------------------------------
  * Optimizer over the flat fp32 LoRA parameter buffer.

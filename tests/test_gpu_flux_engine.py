@@ -18,15 +18,16 @@ def _rel(a, b):
     return ((a - b).norm() / (b.norm() + 1e-30)).item()
 
 
-def _setup(layers, single, heads, B, hl, wl, Lt, rank, seed=0):
+def _setup(layers, single, heads, B, hl, wl, Lt, rank, seed=0, text_dim=64, pooled_dim=32, std=0.05, up_std=0.05,
+           precisions=("bf16", "fp32")):
     from oracle import flux_ref, lora_ref
     from ai_toolkit_b200 import LoRASpecialNetwork
     from ai_toolkit_b200.flux import FluxConfig, FluxTransformer2DModel
     torch.manual_seed(seed)
-    cfgd = dict(num_layers=layers, num_single_layers=single, num_attention_heads=heads, joint_attention_dim=64,
-                pooled_projection_dim=32)
+    cfgd = dict(num_layers=layers, num_single_layers=single, num_attention_heads=heads, joint_attention_dim=text_dim,
+                pooled_projection_dim=pooled_dim)
     ocfg = flux_ref.FluxConfig(**cfgd)
-    omodel = flux_ref.init_synthetic_(flux_ref.FluxTransformer2DModel(ocfg), seed=seed, std=0.05)
+    omodel = flux_ref.init_synthetic_(flux_ref.FluxTransformer2DModel(ocfg), seed=seed, std=std)
     omodel.requires_grad_(False)
     model = FluxTransformer2DModel(FluxConfig(**cfgd), device=DEV)
     missing = model.load_state_dict(omodel.state_dict(), strict=True)
@@ -39,13 +40,15 @@ def _setup(layers, single, heads, B, hl, wl, Lt, rank, seed=0):
     g = torch.Generator().manual_seed(seed + 1)
     onets = {}
     for name, dt in (("bf16", torch.bfloat16), ("fp32", torch.float32)):
+        if name not in precisions:
+            continue
         om = copy.deepcopy(omodel).to(DEV, dt)
         on = lora_ref.LoRANetworkRef(om, lora_dim=rank)
         on.to(DEV, torch.float32)
         onets[name] = (om, on)
     with torch.no_grad():
         for i, lora in enumerate(net.get_all_modules()):
-            up = torch.randn(lora.lora_up.weight.shape, generator=g) * 0.05
+            up = torch.randn(lora.lora_up.weight.shape, generator=g) * up_std
             lora.lora_up.weight.copy_(up)
             for om, on in onets.values():
                 ol = on.loras[i]
@@ -56,8 +59,8 @@ def _setup(layers, single, heads, B, hl, wl, Lt, rank, seed=0):
     lat = torch.randn(B, 16, hl, wl, generator=g).bfloat16().to(DEV)
     noise = torch.randn(B, 16, hl, wl, generator=g).bfloat16().to(DEV)
     t = torch.tensor([500.0, 250.0, 750.0][:B], device=DEV)  # t/1000 exact in bf16: the fp32 oracle sees the same timestep
-    text = (torch.randn(B, Lt, 64, generator=g) * 0.5).bfloat16().to(DEV)
-    pooled = torch.randn(B, 32, generator=g).bfloat16().to(DEV)
+    text = (torch.randn(B, Lt, text_dim, generator=g) * 0.5).bfloat16().to(DEV)
+    pooled = torch.randn(B, pooled_dim, generator=g).bfloat16().to(DEV)
     return model, net, onets, (lat, noise, t, text, pooled)
 
 
@@ -108,6 +111,57 @@ def test_engine_step_matches_oracle(layers, single, heads, B, hl, wl, Lt, rank):
     assert e_pred < max(1e-3, 1.5 * floor_pred)
     assert e_g < max(1e-3, 1.5 * floor_g)
     assert e_loss < max(1e-3, 1.5 * floor_loss)
+
+
+def test_engine_step_matches_oracle_at_flux_dims():
+    """BASELINE.json configs[2] geometry on the blocks themselves: D = 3072, 24 heads x 128, MLP 12288, 4096 image + 512
+    text tokens, T5 width 4096, pooled 768, r = 16 -- one double + one single block (the 19 + 38 of the full model repeat
+    these two).  Engine (forward, loss, backward) vs the oracle on the GPU in fp32 AND in bf16:
+      * loss (fp32 scalar)          <= 1e-3 relative to the fp32 oracle      (north-star criterion, asserted as is)
+      * prediction, dA / dB (fp32)  reported against the fp32 oracle and against the bf16 eager oracle; asserted
+                                    <= max(1e-3, 1.5 x the bf16 eager oracle's own distance to the fp32 oracle): bf16
+                                    activations carry 2^-9 relative rounding per element, which no implementation that
+                                    stores bf16 activations can undercut (the reference's own eager path sits AT this floor)
+    The tensor-core accumulation itself is checked at <= 1e-3 against fp32 math on identical bf16 operands in
+    tests/test_gpu_gemm.py (dgrad / wgrad at these shapes)."""
+    from oracle import flux_ref
+    from ai_toolkit_b200 import ops
+    from ai_toolkit_b200.train_step import make_img_ids
+    B, hl, wl, Lt, rank = 1, 128, 128, 512, 16
+    model, net, onets, batch = _setup(1, 1, 24, B, hl, wl, Lt, rank, seed=3, text_dim=4096, pooled_dim=768, std=0.02,
+                                      up_std=0.02)
+    assert model.cfg.inner_dim == 3072 and len(net.get_all_modules()) == 14 + 6
+    lat, noise, t, text, pooled = batch
+    loss32, pred32, g32 = _oracle_step(*onets["fp32"], batch, torch.float32)
+    loss16, pred16, g16 = _oracle_step(*onets["bf16"], batch, torch.bfloat16)
+    packed = ops.flow_add_noise(lat, noise, t, pack=True)
+    net.flat_grads.zero_()
+    with net:
+        pred = model.engine.forward(packed, t, text, pooled, torch.ones(B, device=DEV), torch.zeros(Lt, 3, device=DEV),
+                                    make_img_ids(hl, wl, DEV), save=True, t_div=1000.0)
+        tot, per, dpred = ops.flow_loss(pred.view(B, -1, 64), lat, noise, pack=True)
+        model.engine.backward(dpred.view(-1, 64))
+    torch.cuda.synchronize()
+    pred_unp = flux_ref.unpack_latents(pred.view(B, -1, 64), hl, wl)
+    g = net.flat_grads[:g32.numel()]
+    floor_pred, floor_g = _rel(pred16, pred32), _rel(g16, g32)
+    e_pred, e_g = _rel(pred_unp, pred32), _rel(g, g32)
+    e_loss, floor_loss = abs(tot.item() - loss32) / abs(loss32), abs(loss16 - loss32) / abs(loss32)
+    print(f"[FLUX dims] loss rel {e_loss:.3e} (bf16 eager oracle: {floor_loss:.3e}) | pred vs fp32 oracle {e_pred:.3e} "
+          f"(bf16 eager: {floor_pred:.3e}), vs bf16 eager {_rel(pred_unp, pred16):.3e} | dA/dB vs fp32 oracle {e_g:.3e} "
+          f"(bf16 eager: {floor_g:.3e}), vs bf16 eager {_rel(g, g16):.3e}")
+    assert torch.isfinite(g).all() and g32.norm() > 0
+    assert e_loss < 1e-3
+    assert e_pred < max(1e-3, 1.5 * floor_pred)
+    assert e_g < max(1e-3, 1.5 * floor_g)
+    # per-adapter: no single module may be off (a wrong slice / stride would hide in the global norm)
+    off = 0
+    for lora in net.get_all_modules():
+        for w in (lora.lora_down.weight, lora.lora_up.weight):
+            n = w.numel()
+            a, b = g[off:off + n], g32[off:off + n]
+            assert _rel(a, b) < max(5e-3, 3 * floor_g), (lora.lora_name, _rel(a, b))
+            off += n
 
 
 def test_lora_module_autograd_dropin():
