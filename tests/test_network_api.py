@@ -371,3 +371,91 @@ def test_lr_scheduler_drives_the_device_hyper_buffer():
     host = list(opt._hyper_host)
     opt.sync_hyper()
     assert opt._hyper_host == host
+
+
+class ResnetBlock2D(torch.nn.Module):  # kohya_lora.py:751: the 3x3-conv targets
+    def __init__(self):
+        super().__init__()
+        self.conv1 = torch.nn.Conv2d(8, 16, 3, padding=1)
+        self.conv2 = torch.nn.Conv2d(16, 16, 3, stride=2, padding=1)
+        self.conv_shortcut = torch.nn.Conv2d(8, 16, 1)
+
+
+def _toy_unet_conv():
+    cls = type("UNet2DConditionModel", (torch.nn.Module,), {})
+
+    def init(self):
+        torch.nn.Module.__init__(self)
+        self.down_blocks = torch.nn.ModuleList([Transformer2DModel(), ResnetBlock2D()])
+
+    cls.__init__ = init
+    return cls()
+
+
+@pytest.mark.skipif(not ref_import.available(), reason="reference tree not present (GPU box)")
+def test_conv3x3_lora_extract_and_merge_identical_to_live_reference():
+    """conv_lora_dim (toolkit/lora_special.py:95-104, :585-587, :679-681): k x k adapters on the ResNet convs -- names,
+    shapes (down = Conv k x k with the wrapped conv's stride / padding, up = 1x1), kaiming draws, saved keys, merge_in and
+    extract_weight next to the UNMODIFIED reference."""
+    RefNet, _ = ref_import.reference_lora()
+    u1, u2 = _toy_unet_conv(), _toy_unet_conv()
+    u2.load_state_dict(u1.state_dict())
+    kw = dict(text_encoder=None, lora_dim=4, alpha=2, conv_lora_dim=4, conv_alpha=1, train_unet=True, train_text_encoder=False,
+              target_lin_modules=["Transformer2DModel"], target_conv_modules=["ResnetBlock2D"])
+    torch.manual_seed(5)
+    r = RefNet(unet=u1, **dict(kw, target_lin_modules=["Transformer2DModel"]))
+    r.force_to("cpu", torch.float32); r._update_torch_multiplier(); r.apply_to(None, u1, False, True)
+    torch.manual_seed(5)
+    n = LoRASpecialNetwork(unet=u2, **dict(kw, target_lin_modules=["Transformer2DModel"]))
+    n.force_to("cpu", torch.float32); n._update_torch_multiplier(); n.apply_to(None, u2, False, True)
+    assert [l.lora_name for l in r.unet_loras] == [l.lora_name for l in n.unet_loras]
+    assert any("conv2" in l.lora_name for l in n.unet_loras)
+    sr, sn = r.get_state_dict(dtype=torch.float32), n.get_state_dict(dtype=torch.float32)
+    assert list(sr.keys()) == list(sn.keys())
+    for k in sr:
+        assert sr[k].shape == sn[k].shape and torch.equal(sr[k], sn[k]), k
+    assert [l.scale for l in r.unet_loras] == [l.scale for l in n.unet_loras]
+    c2r = [l for l in r.unet_loras if l.lora_name.endswith("conv2")][0]
+    c2n = [l for l in n.unet_loras if l.lora_name.endswith("conv2")][0]
+    assert tuple(c2n.lora_down.weight.shape) == tuple(c2r.lora_down.weight.shape) == (4, 16, 3, 3)
+    assert c2n.lora_down.stride == c2r.lora_down.stride == (2, 2) and c2n.lora_down.padding == c2r.lora_down.padding
+    # merge_in on a conv adapter
+    with torch.no_grad():
+        for a, b in zip(r.unet_loras, n.unet_loras):
+            a.lora_up.weight.normal_(0, 0.1)
+            b.lora_up.weight.copy_(a.lora_up.weight)
+    r.merge_in(0.7); n.merge_in(0.7)
+    for (k1, p1), (k2, p2) in zip(u1.state_dict().items(), u2.state_dict().items()):
+        torch.testing.assert_close(p1, p2, rtol=1e-6, atol=1e-6, msg=k1)
+    r.merge_out(0.7); n.merge_out(0.7)
+    # extract_weight: truncated SVD of the wrapped layer (linear and conv), rank / alpha / runtime scale updates
+    for a, b in zip(r.unet_loras, n.unet_loras):
+        a.extract_weight(extract_mode="fixed", extract_mode_param=2)
+        b.extract_weight(extract_mode="fixed", extract_mode_param=2)
+        assert a.lora_dim == b.lora_dim and a.scale == b.scale == 1.0 and float(b._runtime_scale) == 1.0
+        assert tuple(a.lora_down.weight.shape) == tuple(b.lora_down.weight.shape), a.lora_name
+        # SVD factors are unique up to sign per component: compare the product up @ down
+        pa = a.lora_up.weight.flatten(1) @ a.lora_down.weight.flatten(1)
+        pb = b.lora_up.weight.flatten(1) @ b.lora_down.weight.flatten(1)
+        torch.testing.assert_close(pa, pb, rtol=1e-4, atol=1e-5)
+    assert n.flat_params.data_ptr() == n.unet_loras[0].lora_down.weight.data_ptr()  # flat views rebuilt after the rank change
+
+
+def test_module_and_rank_dropout_flags():
+    """dropout / rank_dropout / module_dropout are accepted (reference default None); masks are only drawn in training mode
+    (toolkit/network_mixins.py:197-226); an inactive / eval network never consults them."""
+    unet = _toy_unet()
+    net = LoRASpecialNetwork(text_encoder=None, unet=unet, lora_dim=4, alpha=2, train_unet=True, train_text_encoder=False,
+                             dropout=0.1, rank_dropout=0.2, module_dropout=1.0)
+    net.force_to("cpu", torch.float32)
+    net._update_torch_multiplier()
+    net.apply_to(None, unet, False, True)
+    lora = net.unet_loras[1]
+    net.train()
+    assert lora.has_dropout()
+    lin = lora.org_module[0]
+    x = torch.randn(2, 3, 16)
+    with net:  # module_dropout = 1.0 -> the adapter contributes 0.0: the frozen layer's output, even on CPU
+        assert torch.equal(lin(x), torch.nn.functional.linear(x, lin.weight))
+    net.eval()
+    assert not lora.has_dropout()
