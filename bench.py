@@ -33,6 +33,13 @@ sys.path.insert(0, ROOT)
 RANK = 16
 LATENT = (16, 128, 128)  # 1024^2 image -> 16 x 128 x 128 latent -> 4096 packed tokens
 TEXT_LEN = 512
+METRIC = "train-steps/sec FLUX.1-dev LoRA r=16 bs=1 1024^2"
+
+
+def workload_name(args):
+    if args.batch == 1 and args.rank == 16:
+        return "FLUX.1-dev LoRA r=16 bs=1/GPU 1024^2 (BASELINE.json configs[2])"
+    return f"FLUX.1-dev LoRA r={args.rank} bs={args.batch}/GPU 1024^2 (BASELINE.json configs[4] rank sweep)"
 
 
 def flux_flops(B=1, r=RANK, I=4096, T=512, D=3072, M=12288, n_double=19, n_single=38):
@@ -55,6 +62,54 @@ def measured_peaks():
         d = json.load(open(p))
         return d, "measured"
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+def host_cores() -> int:
+    """Threads this process may really use: the scheduler affinity mask, bounded by the cgroup CPU quota (cpu.max) --
+    `os.cpu_count()` reports the machine, not the lease, and oversubscribing a quota'd container makes CPU timings
+    irreproducible (round-1 BENCH vs SCALE differed 32x)."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    for path in ("/sys/fs/cgroup/cpu.max", "/sys/fs/cgroup/cpu/cpu.cfs_quota_us"):
+        try:
+            txt = open(path).read().split()
+            if path.endswith("cpu.max"):
+                if txt[0] != "max":
+                    n = min(n, max(1, int(float(txt[0]) / float(txt[1]))))
+            else:
+                q = int(txt[0])
+                per = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+                if q > 0:
+                    n = min(n, max(1, q // per))
+            break
+        except Exception:
+            continue
+    return max(1, n)
+
+
+def profile_numbers(prefixes=("r2_gemm_fwd", "r1_gemm_fwd")):
+    """dram bytes / tensor-pipe activity of the dominant kernel from the newest COMMITTED ncu --set full summary
+    (profiles/*_ncu_full_summary.csv, written by tools/ncu_summary.py from the .ncu-rep of tools/r2_profile_trip.sh)."""
+    import csv
+
+    for pre in prefixes:
+        path = os.path.join(ROOT, "profiles", f"{pre}_ncu_full_summary.csv")
+        if not os.path.exists(path):
+            continue
+        try:
+            rows = list(csv.reader(open(path)))
+            hdr, units, row = rows[0], rows[1], rows[2]
+            get = lambda k: float(row[hdr.index(k)])  # noqa: E731
+            scale = {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1.0}
+            rd = get("dram__bytes_read.sum") * scale.get(units[hdr.index("dram__bytes_read.sum")], 1.0)
+            wr = get("dram__bytes_write.sum") * scale.get(units[hdr.index("dram__bytes_write.sum")], 1.0)
+            return {"traffic": rd + wr, "tensor_pipe_active_pct_ncu": get("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active"),
+                    "ncu_us": get("gpu__time_duration.sum"), "kernel_ncu": row[0][:80], "source": f"profiles/{os.path.basename(path)}"}
+        except Exception as e:  # malformed summary: say so instead of inventing numbers
+            return {"traffic": None, "source": f"profiles/{os.path.basename(path)} (unreadable: {e})"}
+    return {"traffic": None, "source": None}
 
 
 class ClockSampler(threading.Thread):
@@ -95,31 +150,35 @@ class ClockSampler(threading.Thread):
 # ---------------------------------------------------------------------------------------------------
 # CPU baseline / reference arm: the oracle port on the host cores
 # ---------------------------------------------------------------------------------------------------
-def cpu_reference_sample(n_double=1, n_single=1, steps=1, warmup=0, tokens_img=1024, tokens_txt=128):
-    """Eager oracle (oracle/flux_ref.py + oracle/lora_ref.py) on the host CPU, FLUX width (D = 3072, 24 heads,
-    MLP 12288) but a bounded number of blocks / tokens; returns (seconds per sample-step, F_sample, description)."""
+def cpu_reference_sample(n_double=1, n_single=1, steps=3, warmup=1, tokens_img=1024, tokens_txt=128, rank=None):
+    """Eager oracle (oracle/flux_ref.py + oracle/lora_ref.py: the reference's LoRA forward restated, pinned bit-for-bit to
+    the reference classes in tests/test_oracle_pinned.py) on the host CPU in float32 (BASELINE.json configs[0]: the
+    reference's CPU path is float32), FLUX width (D = 3072, 24 heads, MLP 12288) but a bounded number of blocks / tokens.
+    Returns (median seconds per sample-step, [all step seconds], F_sample, description, threads)."""
     import torch
 
     from oracle import flux_ref, lora_ref
 
-    torch.set_num_threads(os.cpu_count() or 1)
+    rank = rank or RANK
+    threads = host_cores()
+    torch.set_num_threads(threads)
     torch.manual_seed(0)
     cfg = flux_ref.FluxConfig(num_layers=n_double, num_single_layers=n_single)
-    model = flux_ref.FluxTransformer2DModel(cfg).to(torch.bfloat16).requires_grad_(False)
-    net = lora_ref.LoRANetworkRef(model, lora_dim=RANK)
+    model = flux_ref.FluxTransformer2DModel(cfg).to(torch.float32).requires_grad_(False)
+    net = lora_ref.LoRANetworkRef(model, lora_dim=rank)
     params = [p for l in net.loras for p in (l.lora_down.weight, l.lora_up.weight)]
     opt = torch.optim.AdamW(params, lr=1e-4, eps=1e-6)
     side = int(round((tokens_img * 4) ** 0.5))
-    lat = torch.randn(1, 16, side, side).bfloat16()
+    lat = torch.randn(1, 16, side, side)
     noise = torch.randn_like(lat)
     t = torch.tensor([500.0])
-    text = (torch.randn(1, tokens_txt, 4096) * 0.1).bfloat16()
-    pooled = torch.randn(1, 768).bfloat16()
+    text = torch.randn(1, tokens_txt, 4096) * 0.1
+    pooled = torch.randn(1, 768)
     times = []
     for it in range(warmup + steps):
         t0 = time.perf_counter()
         opt.zero_grad(set_to_none=True)
-        noisy = lora_ref.add_noise_flowmatch(lat, noise, t).to(torch.bfloat16)
+        noisy = lora_ref.add_noise_flowmatch(lat, noise, t)
         with net:
             pred = lora_ref.flux_predict(model, noisy, t, text, pooled, 1.0, flux_ref.pack_latents, flux_ref.unpack_latents,
                                          flux_ref.make_img_ids)
@@ -131,27 +190,98 @@ def cpu_reference_sample(n_double=1, n_single=1, steps=1, warmup=0, tokens_img=1
         if it >= warmup:
             times.append(time.perf_counter() - t0)
     I = (side // 2) ** 2
-    f_sample = flux_flops(1, RANK, I, tokens_txt, n_double=n_double, n_single=n_single)[0]
-    desc = (f"oracle port (eager PyTorch bf16) on {os.cpu_count()} host cores: FLUX-width blocks {n_double} double + {n_single} "
-            f"single, {I}+{tokens_txt} tokens, r={RANK}; steps/s extrapolated linearly in F_step "
-            f"({f_sample / 1e12:.2f} of {flux_flops()[0] / 1e12:.1f} TFLOP)")
-    return sum(times) / len(times), f_sample, desc
+    f_sample = flux_flops(1, rank, I, tokens_txt, n_double=n_double, n_single=n_single)[0]
+    med = sorted(times)[len(times) // 2]
+    desc = (f"oracle port (eager PyTorch float32) on {threads} host threads (affinity / cgroup quota; machine has "
+            f"{os.cpu_count()}): FLUX-width blocks {n_double} double + {n_single} single, {I}+{tokens_txt} tokens, r={rank}; "
+            f"{warmup} warm-up + {steps} timed steps, median {med:.2f} s (min {min(times):.2f}, max {max(times):.2f}); steps/s "
+            f"extrapolated linearly in F_step ({f_sample / 1e12:.2f} of {flux_flops(1, rank)[0] / 1e12:.1f} TFLOP)")
+    return med, times, f_sample, desc, threads
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    sec, f_sample, desc = cpu_reference_sample(steps=max(1, min(args.steps, 3)), warmup=min(args.warmup, 1))
-    f_step = flux_flops()[0]
+    sec, times, f_sample, desc, threads = cpu_reference_sample(steps=max(3, min(args.steps, 5)), warmup=max(1, min(args.warmup, 2)),
+                                                               rank=args.rank)
+    f_step = flux_flops(args.batch, args.rank)[0]
     value = 1.0 / (sec * f_step / f_sample)
-    out = {"metric": "train-steps/sec FLUX.1-dev LoRA r=16 bs=1 1024^2", "value": value, "unit": "steps/s", "n_gpus": args.gpus,
+    out = {"metric": METRIC, "value": value, "unit": "steps/s", "n_gpus": args.gpus,
            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 / value, "higher_is_better": True, "scaling": "weak",
-           "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "impl": "reference",
-           "config": {"workload": "FLUX.1-dev LoRA r=16 bs=1 1024^2 (configs[2]), CPU sample extrapolated"},
-           "cpu_baseline": {"value": value, "unit": "steps/s", "cores": os.cpu_count(), "kind": "port", "sample": desc},
+           "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "reference",
+           "config": {"workload": workload_name(args) + ", CPU sample extrapolated in F_step"},
+           "cpu_baseline": {"value": value, "unit": "steps/s", "cores": threads, "kind": "port", "sample": desc,
+                            "step_seconds": times},
            "e2e": {"value": value, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
     print(json.dumps(out), flush=True)
+
+
+def gpu_reference_leg(dev, steps=3, warmup=2, rank=None, batch=1):
+    """the reference-style EAGER PyTorch step on the SAME B200 -- the denominator of the north
+    star's ">= 4x the reference's 1xB200 PyTorch step time".  diffusers-named FLUX blocks (oracle/flux_ref.py) + the
+    reference's LoRA forward as restated in oracle/lora_ref.py (fp32 side branch, network_mixins.py:304-342; pinned
+    bit-for-bit to the reference class, which cannot travel to the GPU box) + torch SDPA + clip_grad_norm_ +
+    torch.optim.AdamW(eps=1e-6); bf16 base, fp32 adapters; timed with gradient checkpointing (the reference default,
+    toolkit/config_modules.py:413) and without (equal work to this repo's path, which stores activations)."""
+    import torch
+
+    from oracle import flux_ref, lora_ref
+
+    rank = rank or RANK
+    torch.set_default_dtype(torch.bfloat16)
+    with torch.device(dev):
+        model = flux_ref.FluxTransformer2DModel(flux_ref.flux_dev_config())
+    torch.set_default_dtype(torch.float32)
+    g = torch.Generator(device=dev).manual_seed(0)
+    with torch.no_grad():
+        for p in model.parameters():
+            p.copy_(torch.randn(p.shape, generator=g, device=dev, dtype=torch.float32) * 0.02)
+    model.requires_grad_(False)
+    net = lora_ref.LoRANetworkRef(model, lora_dim=rank).to(dev)
+    with torch.no_grad():
+        for l in net.loras:
+            l.lora_up.weight.normal_(0, 0.02)
+    params = [p for l in net.loras for p in (l.lora_down.weight, l.lora_up.weight)]
+    opt = torch.optim.AdamW(params, lr=1e-4, eps=1e-6)
+    lat = torch.randn(batch, *LATENT, device=dev).bfloat16()
+    noise = torch.randn_like(lat)
+    t = torch.full((batch,), 500.0, device=dev)
+    text = (torch.randn(batch, TEXT_LEN, 4096, device=dev) * 0.1).bfloat16()
+    pooled = torch.randn(batch, 768, device=dev).bfloat16()
+
+    def step():
+        opt.zero_grad(set_to_none=True)
+        noisy = lora_ref.add_noise_flowmatch(lat, noise, t).to(torch.bfloat16)
+        with net:
+            pred = lora_ref.flux_predict(model, noisy, t, text, pooled, 1.0, flux_ref.pack_latents, flux_ref.unpack_latents,
+                                         flux_ref.make_img_ids)
+            loss = lora_ref.flow_loss(pred, lat, noise)
+            loss.backward()
+        torch.nn.utils.clip_grad_norm_(params, 1.0)
+        opt.step()
+        return loss
+
+    out = {"what": "eager PyTorch reference-style step on the same GPU (oracle FLUX blocks + reference LoRA forward + torch "
+                   "SDPA + torch AdamW), CUDA-event timed", "steps": steps, "warmup": warmup}
+    for name, ck in (("checkpointing", True), ("no_checkpointing", False)):
+        try:
+            model.gradient_checkpointing = ck
+            for _ in range(warmup):
+                step()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(steps):
+                loss = step()
+            e1.record()
+            torch.cuda.synchronize()
+            out[name] = {"ms_per_step": e0.elapsed_time(e1) / steps, "loss": float(loss)}
+        except Exception as e:  # e.g. out of memory without checkpointing at bs 4
+            out[name] = {"error": f"{type(e).__name__}: {str(e)[:100]}"}
+            torch.cuda.empty_cache()
+    out["peak_mem_gib"] = torch.cuda.max_memory_allocated() / 2 ** 30
+    return out
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -180,7 +310,8 @@ def run_b200(args):
         cfg.num_layers, cfg.num_single_layers = args.layers
     t_setup = time.time()
     model = FluxTransformer2DModel(cfg, device=dev).init_synthetic_(seed=0)
-    net = LoRASpecialNetwork(text_encoder=None, unet=model, lora_dim=RANK, alpha=RANK, train_unet=True,
+    BS, R = args.batch, args.rank
+    net = LoRASpecialNetwork(text_encoder=None, unet=model, lora_dim=R, alpha=R, train_unet=True,
                              train_text_encoder=False, is_flux=True, transformer_only=True)
     net.force_to(dev, torch.float32)
     net._update_torch_multiplier()
@@ -192,16 +323,16 @@ def run_b200(args):
     net.mark_params_changed()
     opt = B200AdamW(net, lr=1e-4, betas=(0.9, 0.999), eps=1e-6, weight_decay=1e-2, max_grad_norm=1.0, ema_decay=0.99,
                     grad_prescale=1.0 / world)
-    step = FluxLoRATrainStep(model, net, opt, batch_size=1, latent_shape=LATENT, text_len=TEXT_LEN, guidance_scale=1.0,
+    step = FluxLoRATrainStep(model, net, opt, batch_size=BS, latent_shape=LATENT, text_len=TEXT_LEN, guidance_scale=1.0,
                              use_cuda_graph=not args.no_graph)
     # synthetic batch: host (pinned) copies for the e2e leg, seeded per rank
     hg = torch.Generator().manual_seed(1234 + rank)
     host = {
-        "latents": torch.randn(1, *LATENT, generator=hg).bfloat16().pin_memory(),
-        "noise": torch.randn(1, *LATENT, generator=hg).bfloat16().pin_memory(),
-        "timesteps": torch.linspace(1000, 1, 1000)[torch.randint(0, 999, (1,), generator=hg)].float().pin_memory(),
-        "text_embeds": (torch.randn(1, TEXT_LEN, 4096, generator=hg) * 0.1).bfloat16().pin_memory(),
-        "pooled_embeds": torch.randn(1, 768, generator=hg).bfloat16().pin_memory(),
+        "latents": torch.randn(BS, *LATENT, generator=hg).bfloat16().pin_memory(),
+        "noise": torch.randn(BS, *LATENT, generator=hg).bfloat16().pin_memory(),
+        "timesteps": torch.linspace(1000, 1, 1000)[torch.randint(0, 999, (BS,), generator=hg)].float().pin_memory(),
+        "text_embeds": (torch.randn(BS, TEXT_LEN, 4096, generator=hg) * 0.1).bfloat16().pin_memory(),
+        "pooled_embeds": torch.randn(BS, 768, generator=hg).bfloat16().pin_memory(),
     }
     h2d = sum(v.numel() * v.element_size() for v in host.values())
     step.load_batch(**{k: host[k] for k in ("latents", "noise", "timesteps")}, text_embeds=host["text_embeds"],
@@ -255,7 +386,7 @@ def run_b200(args):
     peaks, peak_kind = measured_peaks()
     roof = None
     if rank == 0:
-        M_, N_, K_ = 4608, 12288, 3072
+        M_, N_, K_ = (4608 if BS == 1 else 4096 * BS), 12288, 3072  # bs 4: the image stream of a double block, M = 16384
         x = (torch.randn(M_, K_, device=dev) * 0.5).bfloat16()
         w = (torch.randn(N_, K_, device=dev) * 0.02).bfloat16()
         zc = (torch.randn(M_, 64, device=dev) * 0.1).bfloat16()
@@ -280,26 +411,28 @@ def run_b200(args):
             torch.cuda.synchronize()
             tt.append(a.elapsed_time(b))
         kms = sum(tt) / len(tt)
-        fl = 2.0 * M_ * N_ * K_ + 2.0 * M_ * RANK * N_  # base GEMM + rank-r up-projection riding in the same tile
+        fl = 2.0 * M_ * N_ * K_ + 2.0 * M_ * R * N_  # base GEMM + rank-r up-projection riding in the same tile
         ach = fl / kms / 1e9
+        prof = profile_numbers() if (BS == 1 and R == 16) else {"traffic": None, "source": None}
         roof = {"bound": "tensor",
-                "kernel": "gemm_bf16_kernel<2,256,6,0,0> fused LoRA-Linear + bias + GELU(+pre-activation) M=4608 N=12288 K=3072 r=16",
+                "kernel": f"gemm_bf16_kernel<2,256,6,0,0> fused LoRA-Linear + bias + GELU(+pre-activation) M={M_} N={N_} K={K_} r={R}",
                 "achieved": ach, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": ach / peaks["bf16_tflops"],
                 "peak_kind": f"{peak_kind} burst (kernel timed alone, L2 flushed)",
-                # dram__bytes_read.sum + dram__bytes_write.sum of this launch, ncu --set full
-                # (profiles/r1_gemm_fwd_ncu_full_summary.csv): 137.2 MB + 191.3 MB; algorithmic bytes 332 MB
-                "traffic": 328.5e6, "traffic_unit": "bytes/launch", "algorithmic_bytes": 2.0 * (M_ * K_ + N_ * K_ + 2 * M_ * N_ + M_ * 64 + N_ * 64),
-                "tensor_pipe_active_pct_ncu": 85.6, "us_per_launch": kms * 1e3}
+                # dram__bytes_read.sum + dram__bytes_write.sum of this launch, parsed from the committed ncu --set full
+                # summary named in `traffic_source` (null when no capture of this exact shape is committed)
+                "traffic": prof.get("traffic"), "traffic_unit": "bytes/launch", "traffic_source": prof.get("source"),
+                "algorithmic_bytes": 2.0 * (M_ * K_ + N_ * K_ + 2 * M_ * N_ + M_ * 64 + N_ * 64),
+                "tensor_pipe_active_pct_ncu": prof.get("tensor_pipe_active_pct_ncu"), "us_per_launch": kms * 1e3}
     if rank != 0:
         return
-    f_step, f_lin, f_attn, f_lora = flux_flops(1, RANK, n_double=cfg.num_layers, n_single=cfg.num_single_layers)
+    f_step, f_lin, f_attn, f_lora = flux_flops(BS, R, n_double=cfg.num_layers, n_single=cfg.num_single_layers)
     value = world * 1e3 / ms
     out = {
-        "metric": "train-steps/sec FLUX.1-dev LoRA r=16 bs=1 1024^2", "value": value, "unit": "steps/s", "n_gpus": world,
+        "metric": METRIC if (BS == 1 and R == 16) else f"train-steps/sec FLUX.1-dev LoRA r={R} bs={BS} 1024^2", "value": value, "unit": "steps/s", "n_gpus": world,
         "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": "FLUX.1-dev LoRA r=16 bs=1/GPU 1024^2 (BASELINE.json configs[2])", "global_batch": world,
-                   "tokens": 4608, "lora_modules": len(net.get_all_modules()), "lora_params": int(net.n_params),
+        "config": {"workload": workload_name(args), "global_batch": world * BS, "img_per_s": world * BS * 1e3 / ms,
+                   "tokens": 4608 * BS, "rank": R, "lora_modules": len(net.get_all_modules()), "lora_params": int(net.n_params),
                    "blocks": [cfg.num_layers, cfg.num_single_layers], "parallelism": f"dp{world}", "ema": True,
                    "cuda_graph": not args.no_graph,
                    "l2": "per-step working set (23.8 GB weights + activations) >> 126 MB L2; no explicit flush"},
@@ -317,9 +450,23 @@ def run_b200(args):
         "setup_s": setup_s,
     }
     if not args.skip_cpu_baseline and world == 1:  # rank 0 at N = 1 only (a bounded CPU sample of the same workload)
-        sec, f_sample, desc = cpu_reference_sample(steps=1, warmup=0)
+        sec, times, f_sample, desc, threads = cpu_reference_sample(steps=3, warmup=1, rank=R)
         v = 1.0 / (sec * f_step / f_sample)
-        out["cpu_baseline"] = {"value": v, "unit": "steps/s", "cores": os.cpu_count(), "kind": "port", "sample": desc}
+        out["cpu_baseline"] = {"value": v, "unit": "steps/s", "cores": threads, "kind": "port", "sample": desc,
+                               "step_seconds": times}
+    if not args.skip_gpu_reference and world == 1 and not args.layers:
+        # free this arm's model / activations first: the eager reference needs its own 24 GB of weights + autograd state
+        del step, opt, net, model
+        import gc
+
+        gc.collect()
+        torch.cuda.empty_cache()
+        torch.cuda.reset_peak_memory_stats()
+        ref = gpu_reference_leg(dev, rank=R, batch=BS)
+        for k in ("checkpointing", "no_checkpointing"):
+            if "ms_per_step" in ref.get(k, {}):
+                ref[k]["speedup_of_this_repo"] = ref[k]["ms_per_step"] / ms
+        out["gpu_reference"] = ref
     print(json.dumps(out), flush=True)
     if world > 1:
         torch.distributed.destroy_process_group()
@@ -333,6 +480,10 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--skip-cpu-baseline", action="store_true")
+    ap.add_argument("--skip-gpu-reference", action="store_true",
+                    help="do not time the eager reference-style PyTorch step on the same GPU after the main measurement")
+    ap.add_argument("--batch", type=int, default=1, help="samples per GPU (BASELINE.json configs[4] uses 4)")
+    ap.add_argument("--rank", type=int, default=RANK, help="LoRA rank (configs[4] sweeps 4, 8, 16, 32, 64)")
     ap.add_argument("--layers", type=int, nargs=2, default=None, help="debug: override (double, single) block counts")
     args = ap.parse_args()
     if args.impl == "reference":

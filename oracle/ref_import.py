@@ -22,8 +22,34 @@ _STUB_ROOTS = {
     "diffusers", "optimum", "torchao", "torchaudio", "av", "lycoris", "peft", "accelerate", "bitsandbytes",
     "prodigyopt", "oyaml", "flatten_json", "omegaconf", "kornia", "albumentations", "lpips", "open_clip", "timm",
     "pytorch_wavelets", "torchcodec", "librosa", "mutagen", "controlnet_aux", "cv2", "k_diffusion", "dctorch",
-    "wandb", "tensorboard", "gguf",
+    "wandb", "tensorboard", "gguf", "torch_xla",
 }
+
+
+class _Any:
+    """Instance returned by any call on a stub class: every attribute / call yields another `_Any`."""
+
+    def __init__(self, *a, **k):
+        pass
+
+    def __getattr__(self, name):
+        if name.startswith("__") and name.endswith("__"):
+            raise AttributeError(name)
+        return _Any()
+
+    def __call__(self, *a, **k):
+        return _Any()
+
+
+class _StubMeta(type):
+    """Stub classes answer class-level attribute access (`logging.get_logger(...)`, `Scheduler.from_config(...)`) with a
+    permissive callable, stay subclassable (`class CustomLCMScheduler(LCMScheduler)`) and remain real classes for the
+    `isinstance(x, QTensor)` checks on the LoRA path (False for every real tensor)."""
+
+    def __getattr__(cls, name):
+        if name.startswith("__") and name.endswith("__"):
+            raise AttributeError(name)
+        return lambda *a, **k: _Any()
 
 
 class _StubModule(types.ModuleType):
@@ -32,7 +58,7 @@ class _StubModule(types.ModuleType):
     def __getattr__(self, name):
         if name.startswith("__") and name.endswith("__"):
             raise AttributeError(name)
-        cls = type(name, (), {"__module__": self.__name__})
+        cls = _StubMeta(name, (), {"__module__": self.__name__, "__init__": lambda s, *a, **k: None})
         setattr(self, name, cls)
         return cls
 
@@ -88,6 +114,15 @@ def install():
     if REFERENCE_ROOT not in sys.path:
         sys.path.insert(0, REFERENCE_ROOT)
     _installed = True
+
+
+def reference_sd_trainer():
+    """The reference's `SDTrainer` class, unmodified (extensions_built_in/sd_trainer/SDTrainer.py).  It imports with the
+    stubs; instances are made with `object.__new__` + the attributes a method reads (its __init__ needs a real job)."""
+    install()
+    from extensions_built_in.sd_trainer.SDTrainer import SDTrainer  # type: ignore
+
+    return SDTrainer
 
 
 def reference_lora():
