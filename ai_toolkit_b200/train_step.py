@@ -18,7 +18,8 @@ from collections import OrderedDict
 
 import torch
 
-from . import ops
+from . import calc_loss, ops
+from . import timesteps as ts
 
 
 def make_img_ids(h_lat: int, w_lat: int, device) -> torch.Tensor:
@@ -31,7 +32,10 @@ def make_img_ids(h_lat: int, w_lat: int, device) -> torch.Tensor:
 
 class FluxLoRATrainStep:
     def __init__(self, model, network, optimizer, *, batch_size, latent_shape=(16, 128, 128), text_len=512,
-                 guidance_scale=1.0, loss_multiplier=1.0, use_cuda_graph=True, process_group=None):
+                 guidance_scale=1.0, loss_multiplier=1.0, use_cuda_graph=True, process_group=None,
+                 timestep_type="sigmoid", num_train_timesteps=1000, min_denoising_steps=0, max_denoising_steps=999,
+                 linear_timesteps=False, linear_timesteps2=False, noise_multiplier=1.0, latent_multiplier=1.0,
+                 use_loss_options=False):
         self.model, self.network, self.optimizer = model, network, optimizer
         dev = model.device
         self.dev = dev
@@ -55,6 +59,17 @@ class FluxLoRATrainStep:
         self.guidance = torch.full((B,), float(guidance_scale), device=dev, dtype=torch.float32)
         self.txt_ids = torch.zeros(text_len, 3, device=dev)
         self.img_ids = make_img_ids(H, W, dev)
+        # batch-preparation config (TrainConfig defaults, toolkit/config_modules.py:377-417, :556)
+        self.timestep_type, self.num_train_timesteps = timestep_type, int(num_train_timesteps)
+        self.min_denoising_steps, self.max_denoising_steps = int(min_denoising_steps), int(max_denoising_steps)
+        self.linear_timesteps, self.linear_timesteps2 = bool(linear_timesteps), bool(linear_timesteps2)
+        self.noise_multiplier, self.latent_multiplier = float(noise_multiplier), float(latent_multiplier)
+        # calculate_loss options (timestep weights / per-sample loss multipliers / mask): device vectors the fused loss
+        # kernel reads every step, so a captured CUDA graph picks up new values
+        self.use_loss_options = bool(use_loss_options or linear_timesteps or linear_timesteps2 or timestep_type == "weighted")
+        self.sample_weight = torch.ones(B, device=dev, dtype=torch.float32) if self.use_loss_options else None
+        self.mask = None
+        self._table = None
         self.loss_ws = torch.zeros(B + 1, device=dev, dtype=torch.float32)
         self.loss_host = torch.zeros(1, dtype=torch.float32)
         if torch.device(dev).type == "cuda":
@@ -95,8 +110,13 @@ class FluxLoRATrainStep:
             eng = self.model.engine
             pred = eng.forward(packed, self.timesteps, self.text, self.pooled, self.guidance, self.txt_ids, self.img_ids,
                                save=True, t_div=1000.0)
-            _, _, dpred = ops.flow_loss(pred.view(self.B, -1, pred.shape[-1]), self.latents, self.noise, pack=True,
-                                        gscale=self.loss_multiplier, loss_ws=self.loss_ws)
+            if self.use_loss_options or self.mask is not None:
+                _, _, dpred = ops.train_loss(pred.view(self.B, -1, pred.shape[-1]), self.latents, self.noise,
+                                             sample_weight=self.sample_weight, mask=self.mask, pack=True,
+                                             gscale=self.loss_multiplier, loss_ws=self.loss_ws)
+            else:
+                _, _, dpred = ops.flow_loss(pred.view(self.B, -1, pred.shape[-1]), self.latents, self.noise, pack=True,
+                                            gscale=self.loss_multiplier, loss_ws=self.loss_ws)
             eng.backward(dpred.view(-1, pred.shape[-1]))
         finally:
             net.is_active = False
@@ -116,6 +136,104 @@ class FluxLoRATrainStep:
         self.timesteps.copy_(timesteps, non_blocking=True)
         self.text.copy_(text_embeds, non_blocking=True)
         self.pooled.copy_(pooled_embeds, non_blocking=True)
+
+    # -- batch preparation: BaseSDTrainProcess.process_general_training_batch for cached latents (:1036-1478) ---------
+    def prepare_batch(self, latents, text_embeds, pooled_embeds, generator=None, loss_multiplier=None, mask=None):
+        """latents [B, C, H, W] -> loads the step's device buffers with what the reference's batch preparation yields:
+        the per-step timestep table (`set_train_timesteps`, :1195-1229), index draw (`content_or_style == 'balanced'`,
+        :1301-1318), `timesteps = table[idx]` (:1323), noise = randn_like x noise_multiplier (:1327, :1351), latents x
+        latent_multiplier (:1402); add_noise itself (:1421) is the first kernel of the step.  Timestep weights / loss
+        multipliers go to the device vector of the fused loss.  `generator`: a torch.Generator on the step's device (the
+        RNG stream is torch's).  Returns (timesteps, indices) for logging / tests."""
+        dev = self.dev
+        lat = latents.to(dev, torch.bfloat16)
+        if self.latent_multiplier != 1.0:
+            lat = lat * self.latent_multiplier
+        table = ts.set_train_timesteps(self.num_train_timesteps, dev, self.timestep_type, generator=generator, latents=lat,
+                                       patch_size=1)
+        idx = ts.sample_timestep_indices(self.B, dev, self.min_denoising_steps, self.max_denoising_steps, flowmatch=True,
+                                         generator=generator)
+        timesteps = ts.timesteps_for_batch(table, idx).float()
+        noise = torch.randn(lat.shape, device=dev, dtype=lat.dtype, generator=generator)
+        if self.noise_multiplier != 1.0:
+            noise = noise * self.noise_multiplier
+        self._table = table
+        self.load_batch(lat, noise, timesteps, text_embeds, pooled_embeds)
+        self.set_loss_options(timesteps, loss_multiplier=loss_multiplier, mask=mask)
+        return timesteps, idx
+
+    def set_loss_options(self, timesteps, loss_multiplier=None, mask=None):
+        """Per-sample weights (timestep weights x loss multipliers, SDTrainer.py:923-943, :994) and the mask multiplier
+        (:953-959) of the step's loss; needs `use_loss_options=True` at construction when a CUDA graph is in use."""
+        want = self.linear_timesteps or self.linear_timesteps2 or self.timestep_type == "weighted" or loss_multiplier is not None
+        if want:
+            if self.sample_weight is None:
+                raise RuntimeError("construct FluxLoRATrainStep(use_loss_options=True) to use timestep weights / loss multipliers")
+            v = calc_loss.loss_vectors(timesteps, is_flow_matching=True, flow_table=self._table,
+                                       linear_timesteps=self.linear_timesteps, linear_timesteps2=self.linear_timesteps2,
+                                       timestep_type=self.timestep_type, loss_multiplier=loss_multiplier, device=self.dev)
+            if v["sample_weight"] is None:
+                self.sample_weight.fill_(1.0)
+            else:
+                self.sample_weight.copy_(v["sample_weight"], non_blocking=True)
+        if mask is not None:
+            m = mask.to(self.dev, torch.float32).contiguous()
+            if self.mask is None:
+                if self._graph_fb is not None:
+                    raise RuntimeError("a mask must be present before the step is captured into its CUDA graph")
+                self.mask = torch.empty_like(m)
+            self.mask.copy_(m, non_blocking=True)
+
+    # -- deterministic evaluation: BaseSDTrainProcess.validate (:1681-1743) --------------------------------------------
+    @torch.no_grad()
+    def validate(self, latents_list, embeds_list, sigmas=(1.0, 0.75, 0.5, 0.25)):
+        """Validation loss with the reference's protocol: fixed CPU-generator noise per image (seeds 42 + i, :1666-1672),
+        all sigmas as one batch (timesteps = sigma x 1000), network active at multiplier 1.0, no gradient;
+        `mse_loss(pred.float(), (noise - latents).float())` per image, mean over images.  -> python float."""
+        net = self.network
+        start_multiplier = net.multiplier
+        net.multiplier = 1.0
+        n = len(sigmas)
+        t = torch.tensor([s * 1000.0 for s in sigmas], device=self.dev, dtype=torch.float32)
+        losses = []
+        was_active = net.is_active
+        net.is_active = True
+        try:
+            for i, (lat, (text, pooled)) in enumerate(zip(latents_list, embeds_list)):
+                g = torch.Generator(device="cpu").manual_seed(42 + i)
+                noise = torch.randn(lat.shape, generator=g, dtype=torch.float32)
+                lat_b = torch.cat([lat.to(self.dev, torch.bfloat16)] * n, 0)
+                noise_b = torch.cat([noise.to(self.dev, torch.bfloat16)] * n, 0)
+                text_b = torch.cat([text.to(self.dev, torch.bfloat16)] * n, 0)
+                pooled_b = torch.cat([pooled.to(self.dev, torch.bfloat16)] * n, 0)
+                packed = ops.flow_add_noise(lat_b, noise_b, t, pack=True)
+                H, W = lat_b.shape[2], lat_b.shape[3]
+                pred = self.model.engine.forward(packed, t, text_b, pooled_b, torch.full((n,), float(self.guidance[0]), device=self.dev),
+                                                 torch.zeros(text_b.shape[1], 3, device=self.dev), make_img_ids(H, W, self.dev),
+                                                 save=False, t_div=1000.0)
+                tot, _, _ = ops.flow_loss(pred.view(n, -1, pred.shape[-1]), lat_b, noise_b, pack=True, want_grad=False)
+                losses.append(tot.clone())
+        finally:
+            net.is_active = was_active
+            net.multiplier = start_multiplier
+        return float(torch.stack(losses).mean())
+
+    # -- save / resume from the device flat buffers (BaseSDTrainProcess.save :505-721, run :2046-2060, :2189-2222) ----
+    def save(self, save_root, name, step, epoch=0, dtype=torch.float16, **kw):
+        from . import checkpoint
+
+        torch.cuda.synchronize()
+        return checkpoint.save_checkpoint(self.network, self.optimizer, save_root, name, step=step, epoch=epoch, dtype=dtype, **kw)
+
+    def resume(self, save_root, name, **kw):
+        """-> (path, step, epoch).  Weights, EMA shadow, AdamW moments and step counter are restored into the flat device
+        buffers; the bf16 operand packs are refreshed by the next step (captured graphs stay valid: same buffers)."""
+        from . import checkpoint
+
+        out = checkpoint.resume(self.network, self.optimizer, save_root, name, **kw)
+        self.network.mark_params_changed()
+        self.network.refresh_packs(force=True)
+        return out
 
     def run(self, first_micro_batch=True, last_micro_batch=True):
         """Launch one (micro-)step on the resident batch; returns the device loss scalar (no host sync).

@@ -304,3 +304,178 @@ def test_gradient_accumulation_sums_micro_batches():
     assert abs(out["loss"] - sum(losses) / 2) < 1e-6 * abs(out["loss"]) + 1e-7
     assert _rel(net.flat_grads, g[0] + g[1]) < 1e-5
     assert int(opt.state_buf[0].item()) == 3
+
+
+def test_loss_curve_100_steps_with_validation_protocol(tmp_path):
+    """North-star criterion: 100 optimizer steps, loss per step within 1e-3 relative of the eager bf16 oracle +
+    torch.optim.AdamW(eps 1e-6) + clip_grad_norm_(1.0), plus the reference's deterministic validation loss
+    (BaseSDTrainProcess.validate :1681-1743: fixed CPU-generator noise seeds 42 + i, sigmas 1.0 / 0.75 / 0.5 / 0.25, network
+    active, no grad) at steps 0, 50 and 100 within 1e-3; post-training parameters: the UPDATE (p - p_init) within 5e-2.
+    A fresh batch every step (4 samples cycled with different noise / timesteps), CUDA graphs on, EMA on.  Then the state is
+    saved from the device flat buffers, reloaded into a second network / optimizer, and one more step matches."""
+    from oracle import flux_ref, lora_ref
+    from ai_toolkit_b200.optimizer import B200AdamW
+    from ai_toolkit_b200.train_step import FluxLoRATrainStep
+    B, hl, wl, Lt = 2, 16, 16, 24
+    model, net, onets, batch = _setup(1, 1, 2, B, hl, wl, Lt, 8, seed=13, precisions=("bf16",))
+    _, _, _, text, pooled = batch
+    om, on = onets["bf16"]
+    oparams = [p for l in on.loras for p in (l.lora_down.weight, l.lora_up.weight)]
+    p_init = torch.cat([p.detach().reshape(-1) for p in oparams]).clone()
+    oopt = torch.optim.AdamW(oparams, lr=2e-4, eps=1e-6, weight_decay=1e-2)
+    opt = B200AdamW(net, lr=2e-4, eps=1e-6, weight_decay=1e-2, max_grad_norm=1.0, ema_decay=0.99)
+    step = FluxLoRATrainStep(model, net, opt, batch_size=B, latent_shape=(16, hl, wl), text_len=Lt, use_cuda_graph=True)
+    g = torch.Generator().manual_seed(99)
+    data = torch.randn(4, 16, hl, wl, generator=g).bfloat16()
+    val_lat = [data[0:1].float(), data[3:4].float()]
+    val_emb = [(text[0:1], pooled[0:1]), (text[1:2], pooled[1:2])]
+    table = torch.linspace(1000, 1, 1000)
+
+    def oracle_validate():
+        losses = []
+        sig = torch.tensor([1000.0, 750.0, 500.0, 250.0], device=DEV)
+        with torch.no_grad(), on:
+            for i, (lat, (te, pe)) in enumerate(zip(val_lat, val_emb)):
+                noise = torch.randn(lat.shape, generator=torch.Generator(device="cpu").manual_seed(42 + i), dtype=torch.float32)
+                lb = torch.cat([lat.to(DEV, torch.bfloat16)] * 4, 0)
+                nb = torch.cat([noise.to(DEV, torch.bfloat16)] * 4, 0)
+                noisy = lora_ref.add_noise_flowmatch(lb, nb, sig).to(torch.bfloat16)
+                pred = lora_ref.flux_predict(om, noisy, sig, torch.cat([te] * 4, 0), torch.cat([pe] * 4, 0), 1.0,
+                                             flux_ref.pack_latents, flux_ref.unpack_latents, flux_ref.make_img_ids)
+                losses.append(torch.nn.functional.mse_loss(pred.float(), (nb - lb).float()))
+        return float(torch.stack(losses).mean())
+
+    mine, ref, vals = [], [], []
+    for it in range(100):
+        if it in (0, 50):
+            vals.append((step.validate(val_lat, val_emb), oracle_validate()))
+        sel = torch.tensor([(2 * it) % 4, (2 * it + 1) % 4])
+        lat = data[sel].to(DEV)
+        noise = torch.randn(B, 16, hl, wl, generator=g).bfloat16().to(DEV)
+        t = table[torch.randint(0, 999, (B,), generator=g)].to(DEV)
+        mine.append(step.hook_train_loop(dict(latents=lat, noise=noise, timesteps=t, text_embeds=text, pooled_embeds=pooled))["loss"])
+        oopt.zero_grad(set_to_none=True)
+        noisy = lora_ref.add_noise_flowmatch(lat, noise, t).to(torch.bfloat16)
+        with on:
+            pred = lora_ref.flux_predict(om, noisy, t, text, pooled, 1.0, flux_ref.pack_latents, flux_ref.unpack_latents,
+                                         flux_ref.make_img_ids)
+            loss = lora_ref.flow_loss(pred, lat, noise)
+            loss.backward()
+        torch.nn.utils.clip_grad_norm_(oparams, 1.0)
+        oopt.step()
+        ref.append(loss.item())
+    vals.append((step.validate(val_lat, val_emb), oracle_validate()))
+    rel = [abs(a - b) / abs(b) for a, b in zip(mine, ref)]
+    vrel = [abs(a - b) / abs(b) for a, b in vals]
+    p_ref = torch.cat([p.detach().reshape(-1) for p in oparams])
+    upd = _rel(net.flat_params[:p_ref.numel()] - p_init, p_ref - p_init)
+    print(f"100-step loss curve: max rel {max(rel):.3e} (mean {sum(rel) / len(rel):.3e}); validation loss rel at 0/50/100: "
+          + " ".join(f"{v:.3e}" for v in vrel) + f"; val loss {vals[0][0]:.5f} -> {vals[-1][0]:.5f}; update rel err {upd:.3e}")
+    assert max(rel) < 1e-3
+    assert max(vrel) < 1e-3
+    assert vals[-1][0] < vals[0][0]  # it trains
+    assert upd < 5e-2 and int(opt.state_buf[0].item()) == 100
+    # ---- save from the device flat buffers, resume into a fresh network / optimizer / step, continue identically
+    root = str(tmp_path / "ckpt")
+    step.save(root, "curve", step=100, epoch=1, dtype=torch.float32)
+    model2, net2, _, _ = _setup(1, 1, 2, B, hl, wl, Lt, 8, seed=13, precisions=())
+    opt2 = B200AdamW(net2, lr=2e-4, eps=1e-6, weight_decay=1e-2, max_grad_norm=1.0, ema_decay=0.99)
+    step2 = FluxLoRATrainStep(model2, net2, opt2, batch_size=B, latent_shape=(16, hl, wl), text_len=Lt, use_cuda_graph=False)
+    path, st, ep = step2.resume(root, "curve")
+    assert (st, ep) == (100, 1) and path.endswith("curve_000000100.safetensors")
+    assert torch.equal(net2.flat_params, net.flat_params) and int(opt2.state_buf[0]) == 100
+    assert torch.equal(opt2.exp_avg, opt.exp_avg) and torch.equal(opt2.ema, net2.flat_params)
+    bd = dict(latents=data[:2].to(DEV), noise=torch.randn(B, 16, hl, wl, generator=g).bfloat16().to(DEV),
+              timesteps=torch.tensor([300.0, 700.0], device=DEV), text_embeds=text, pooled_embeds=pooled)
+    l1 = step.hook_train_loop(bd)["loss"]
+    l2 = step2.hook_train_loop(bd)["loss"]
+    assert abs(l1 - l2) < 1e-6 * abs(l1) + 1e-8
+    assert _rel(net2.flat_params, net.flat_params) < 1e-6
+
+
+def test_prepare_batch_draws_the_reference_timesteps_and_weights():
+    """a3 / a6 wired into the step: `prepare_batch` = set_train_timesteps + randint index + table[idx] + randn noise
+    (BaseSDTrainProcess.py:1195-1421), bit-exact on the index ops given the generator; timestep weights reach the loss."""
+    from ai_toolkit_b200 import timesteps as ts
+    from ai_toolkit_b200.optimizer import B200AdamW
+    from ai_toolkit_b200.train_step import FluxLoRATrainStep
+    B, hl, wl, Lt = 2, 16, 16, 24
+    model, net, onets, batch = _setup(1, 1, 2, B, hl, wl, Lt, 4, seed=3, precisions=())
+    lat, _, _, text, pooled = batch
+    opt = B200AdamW(net, lr=0.0, weight_decay=0.0, max_grad_norm=0.0)
+    for ttype in ("sigmoid", "linear"):
+        step = FluxLoRATrainStep(model, net, opt, batch_size=B, latent_shape=(16, hl, wl), text_len=Lt, use_cuda_graph=False,
+                                 timestep_type=ttype, linear_timesteps=(ttype == "linear"), noise_multiplier=1.5,
+                                 use_loss_options=True)
+        g1, g2 = torch.Generator(device=DEV).manual_seed(5), torch.Generator(device=DEV).manual_seed(5)
+        t, idx = step.prepare_batch(lat, text, pooled, generator=g1, loss_multiplier=[1.0, 0.5])
+        table = ts.set_train_timesteps(1000, DEV, ttype, generator=g2)
+        idx2 = torch.randint(0, 999, (B,), device=DEV, generator=g2).long()
+        noise2 = torch.randn(lat.shape, device=DEV, dtype=lat.dtype, generator=g2) * 1.5
+        assert torch.equal(idx, idx2) and torch.equal(t, table[idx2].float())
+        assert torch.equal(step.timesteps, t) and torch.equal(step.noise, noise2.to(torch.bfloat16))
+        want_w = torch.tensor([1.0, 0.5], device=DEV)
+        if ttype == "linear":
+            want_w = want_w * ts.weights_for_timesteps(table, t).to(DEV)
+        assert torch.allclose(step.sample_weight, want_w)
+        weighted = step.hook_train_loop(dict(latents=step.latents.clone(), noise=step.noise.clone(), timesteps=t, text_embeds=text,
+                                             pooled_embeds=pooled))["loss"]
+        per = step.loss_ws[:B].clone()
+        step.sample_weight.fill_(1.0)
+        step.run()
+        plain = step.loss_ws[:B].clone()
+        assert torch.allclose(per, plain * want_w, rtol=1e-5)
+        assert weighted == pytest.approx(float((plain * want_w).mean()), rel=1e-5)
+
+
+def _nccl_worker(rank, world, port, out_dir):
+    import os
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    import torch.distributed as dist
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    global DEV
+    DEV = f"cuda:{rank}"
+    from ai_toolkit_b200.optimizer import B200AdamW
+    from ai_toolkit_b200.train_step import FluxLoRATrainStep
+    B, hl, wl, Lt = 1, 16, 16, 24
+    model, net, onets, batch = _setup(1, 1, 2, 2, hl, wl, Lt, 8, seed=17, precisions=())
+    lat, noise, t, text, pooled = batch
+    with torch.no_grad():  # replicas start DIFFERENT: the step's constructor must broadcast rank 0's values
+        net.flat_params.add_(0.01 * rank)
+    net.mark_params_changed()
+    opt = B200AdamW(net, lr=1e-3, eps=1e-6, weight_decay=1e-2, max_grad_norm=1.0, ema_decay=0.99)  # prescale default 1.0
+    step = FluxLoRATrainStep(model, net, opt, batch_size=B, latent_shape=(16, hl, wl), text_len=Lt, use_cuda_graph=True)
+    sl = slice(rank, rank + 1)
+    bd = dict(latents=lat[sl], noise=noise[sl], timesteps=t[sl], text_embeds=text[sl], pooled_embeds=pooled[sl])
+    losses = [step.hook_train_loop(bd)["loss"] for _ in range(4)]  # eager, eager, captured, replay
+    torch.cuda.synchronize()
+    torch.save(dict(params=net.flat_params.cpu(), grads=net.flat_grads.cpu(), losses=losses, norm=float(opt.grad_norm)),
+               os.path.join(out_dir, f"r{rank}.pt"))
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs (gpurun --gpus 2)")
+def test_two_ranks_nccl_equal_accumulation_over_two_samples(tmp_path):
+    """SURVEY.md section 8e on real GPUs: 2 ranks x 1 sample over NCCL == 1 rank accumulating the same 2 samples with
+    grad_prescale 1/2 -- parameters after 4 optimizer steps (clipping sees the GLOBAL averaged gradient), through CUDA
+    graphs with the all-reduce between the two graph replays."""
+    import torch.multiprocessing as mp
+    from ai_toolkit_b200.optimizer import B200AdamW
+    from ai_toolkit_b200.train_step import FluxLoRATrainStep
+    mp.spawn(_nccl_worker, args=(2, 29617, str(tmp_path)), nprocs=2, join=True)
+    r0, r1 = (torch.load(str(tmp_path / f"r{k}.pt")) for k in range(2))
+    assert torch.equal(r0["params"], r1["params"])  # replicas stay identical
+    assert torch.equal(r0["grads"], r1["grads"])
+    B, hl, wl, Lt = 1, 16, 16, 24
+    model, net, onets, batch = _setup(1, 1, 2, 2, hl, wl, Lt, 8, seed=17, precisions=())
+    lat, noise, t, text, pooled = batch
+    opt = B200AdamW(net, lr=1e-3, eps=1e-6, weight_decay=1e-2, max_grad_norm=1.0, ema_decay=0.99, grad_prescale=0.5)
+    step = FluxLoRATrainStep(model, net, opt, batch_size=B, latent_shape=(16, hl, wl), text_len=Lt, use_cuda_graph=False)
+    mbs = [dict(latents=lat[i:i + 1], noise=noise[i:i + 1], timesteps=t[i:i + 1], text_embeds=text[i:i + 1],
+                pooled_embeds=pooled[i:i + 1]) for i in range(2)]
+    losses = [step.hook_train_loop(mbs)["loss"] for _ in range(4)]
+    mean_ddp = [(a + b) / 2 for a, b in zip(r0["losses"], r1["losses"])]
+    assert max(abs(a - b) / abs(b) for a, b in zip(mean_ddp, losses)) < 1e-4
+    assert _rel(r0["params"].to(DEV), net.flat_params) < 1e-4  # fp32 atomics in the wgrad: not bit-identical
+    assert abs(r0["norm"] - float(opt.grad_norm)) < 1e-3 * float(opt.grad_norm)
