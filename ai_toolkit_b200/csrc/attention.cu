@@ -922,6 +922,11 @@ extern "C" int b200_attn_fwd(b200_ctx* ctx, const void* Q, const void* K, const 
     configured = true;
   }
   AttnFwdArgs a{(bf16*)o0, ld0, (bf16*)o1, ld1, (float*)lse, B, H, L, split, scale};
+  if (variant == 5) {
+    if ((rc = attn_fwd_pp_launch(tq, tk, tv, a, reinterpret_cast<cudaStream_t>(stream)))) return rc;
+    ctx->launches.fetch_add(1);
+    return B200_OK;
+  }
   if (variant >= 3) {
     if ((rc = attn_fwd_r2_launch(variant, tq, tk, tv, a, reinterpret_cast<cudaStream_t>(stream)))) return rc;
     ctx->launches.fetch_add(1);
