@@ -181,3 +181,28 @@ def test_resume_resets_ema_and_reads_both_optimizer_layouts_and_overwrites_stale
     ck.resume(net3, opt3, root, "r")
     assert torch.equal(opt3.exp_avg, opt.exp_avg) and int(opt3.state_buf[0]) == 7
     assert opt3.param_groups[0]["lr"] == 1e-4
+
+
+@pytest.mark.skipif(not ref_import.available(), reason="reference tree not present (GPU box)")
+def test_weight_mapped_keymap_identical_to_live_reference(monkeypatch):
+    """`get_keymap(force_weight_mapping=True)` / the ssd and vega paths (toolkit/network_mixins.py:524-566,
+    toolkit/saving.py:279-330) on the reference's own key-map data files."""
+    import types
+
+    ref_import.install()
+    from toolkit.saving import get_lora_keymap_from_model_keymap
+    import toolkit
+    from ai_toolkit_b200 import keymaps
+
+    monkeypatch.setenv("AITK_KEYMAPS_ROOT", os.path.join(os.path.dirname(toolkit.__file__), "keymaps"))
+    for flags in (dict(is_sdxl=True), dict(), dict(is_ssd=True), dict(is_vega=True)):
+        net = types.SimpleNamespace(is_ssd=False, is_vega=False, is_sdxl=False, is_v2=False)
+        net.__dict__.update(flags)
+        tail = "ssd" if net.is_ssd else "vega" if net.is_vega else "sdxl" if net.is_sdxl else "sd1"
+        import json
+        with open(os.path.join(os.environ["AITK_KEYMAPS_ROOT"], f"stable_diffusion_{tail}.json")) as f:
+            want = get_lora_keymap_from_model_keymap(json.load(f)["ldm_diffusers_keymap"])
+        got = keymaps.load_keymap(net, force_weight_mapping=True)
+        assert got is not None and list(got.items()) == list(want.items()) and len(got) > 100
+        if not (net.is_ssd or net.is_vega):
+            assert keymaps.load_keymap(net) is None  # no stable_diffusion_locon_<tail>.json in the reference tree

@@ -106,7 +106,9 @@ def test_flux_packed_train_loss_equals_flow_loss():
     pred = torch.randn(B, (H // 2) * (W // 2), C * 4, device=DEV).bfloat16()
     a = ops.flow_loss(pred, lat, noise, pack=True, gscale=0.5)
     b = ops.train_loss(pred, lat, noise, pack=True, gscale=0.5)
-    assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1]) and torch.equal(a[2], b[2])
+    assert torch.equal(a[2], b[2])  # same arithmetic per element: the gradients are bit-identical
+    torch.testing.assert_close(a[0], b[0], rtol=1e-6, atol=0)  # the sums are fp32 atomics (order-dependent last bits)
+    torch.testing.assert_close(a[1], b[1], rtol=1e-6, atol=0)
 
 
 @pytest.mark.parametrize("B,C,H,W", [(2, 320, 16, 24), (1, 8, 5, 7), (3, 40, 33, 31)])
@@ -248,7 +250,10 @@ def test_dropout_variants_on_the_module_seam():
 def test_per_sample_multipliers_through_the_fused_engine():
     """network.multiplier = [m_0, m_1] (SDTrainer.py:1558): every adapter, including the AdaLN projections of the
     conditioning vector, scales sample b by m_b (network_mixins.py:311-322) -- engine vs oracle."""
-    from tests.test_gpu_flux_engine import _oracle_step, _setup
+    import os
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from test_gpu_flux_engine import _oracle_step, _setup
     from ai_toolkit_b200 import ops
     from ai_toolkit_b200.train_step import make_img_ids
     B, hl, wl, Lt = 2, 16, 16, 24
