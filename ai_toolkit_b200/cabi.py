@@ -89,6 +89,8 @@ SIGNATURES = {
     "b200_add_bf16": (c_int, [_V, _V, _V, _V, _V, _L, _V]),
     "b200_attn_fwd": (c_int, [_V, _V, _V, _V, _V, _I, _V, _I, _V, _I, _I, _I, _I, _F, _V]),
     "b200_attn_bwd": (c_int, [_V, _V, _V, _V, _V, _I, _V, _I, _V, _I, _V, _I, _V, _V, _V, _V, _V, _V, _I, _I, _I, _I, _F, _V]),
+    "b200_attn_fwd_x": (c_int, [_V, _V, _V, _V, _V, _I, _V, _I, _V, _I, _I, _I, _I, _I, _F, _V]),
+    "b200_attn_bwd_x": (c_int, [_V, _V, _V, _V, _V, _I, _V, _I, _V, _I, _V, _I, _V, _V, _V, _V, _V, _V, _I, _I, _I, _I, _I, _F, _V]),
     "b200_lora_gemv_fwd": (c_int, [_V, _V, _I, _V, _I, _V, _V, _V, _I, _F, _V, _I, _V, _I, _I, _I, _V]),
     "b200_lora_gemv_bwd": (c_int, [_V, _V, _I, _V, _I, _V, _V, _V, _I, _F, _V, _V, _V, _I, _I, _I, _V]),
     "b200_lora_gemv_fwd_rows": (c_int, [_V, _V, _I, _V, _I, _V, _V, _V, _I, _F, _V, _V, _I, _V, _I, _I, _I, _V]),

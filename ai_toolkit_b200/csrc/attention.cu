@@ -898,17 +898,22 @@ static int attn_maps(b200_ctx* ctx, const void* p, uint64_t rows, uint32_t box_r
 
 extern "C" int b200_attn_fwd(b200_ctx* ctx, const void* Q, const void* K, const void* V, void* o0, int ld0, void* o1, int ld1,
                              void* lse, int B, int H, int L, int split, float scale, void* stream) {
+  return b200_attn_fwd_x(ctx, Q, K, V, o0, ld0, o1, ld1, lse, B, H, L, L, split, scale, stream);
+}
+
+extern "C" int b200_attn_fwd_x(b200_ctx* ctx, const void* Q, const void* K, const void* V, void* o0, int ld0, void* o1,
+                               int ld1, void* lse, int B, int H, int L, int Lk, int split, float scale, void* stream) {
   int rc = check_ctx(ctx);
   if (rc) return rc;
-  B200_REQUIRE(Q && K && V && o1 && lse && B > 0 && H > 0 && L > 0, "b200_attn_fwd: bad args");
+  B200_REQUIRE(Q && K && V && o1 && lse && B > 0 && H > 0 && L > 0 && Lk > 0, "b200_attn_fwd: bad args");
   B200_REQUIRE(split >= 0 && split <= L && (split == 0 || o0 != nullptr), "b200_attn_fwd: bad split %d", split);
   B200_REQUIRE(ld1 % 8 == 0 && (split == 0 || ld0 % 8 == 0), "b200_attn_fwd: output leading dims must be multiples of 8");
-  const uint64_t rows = static_cast<uint64_t>(B) * H * L;
-  B200_REQUIRE(rows < (1ull << 31), "b200_attn_fwd: too many rows");
+  const uint64_t rows = static_cast<uint64_t>(B) * H * L, rows_kv = static_cast<uint64_t>(B) * H * Lk;
+  B200_REQUIRE(rows < (1ull << 31) && rows_kv < (1ull << 31), "b200_attn_fwd: too many rows");
   CUtensorMap tq, tk, tv;
   if ((rc = attn_maps(ctx, Q, rows, 128, &tq))) return rc;
-  if ((rc = attn_maps(ctx, K, rows, 128, &tk))) return rc;
-  if ((rc = attn_maps(ctx, V, rows, 64, &tv))) return rc;
+  if ((rc = attn_maps(ctx, K, rows_kv, 128, &tk))) return rc;
+  if ((rc = attn_maps(ctx, V, rows_kv, 64, &tv))) return rc;
   static bool configured = false;
   // same-box log gpurun_out/r2_trip.log (round 2, 24 x 4608 x 128): variant 3 (attention_r2.cu: packed FFMA2 softmax, scale
   // folded into the exponent FFMA) 255.3 us = 1022 TF/s; variant 4 (16 softmax warps) 256.3 us; variant 1 278.2 us;
@@ -921,7 +926,8 @@ extern "C" int b200_attn_fwd(b200_ctx* ctx, const void* Q, const void* K, const 
     if (e && atoi(e) >= 1 && atoi(e) <= 5) variant = atoi(e);
     configured = true;
   }
-  AttnFwdArgs a{(bf16*)o0, ld0, (bf16*)o1, ld1, (float*)lse, B, H, L, split, scale};
+  AttnFwdArgs a{(bf16*)o0, ld0, (bf16*)o1, ld1, (float*)lse, B, H, L, split, scale, Lk};
+  B200_REQUIRE(Lk == L || variant >= 3, "b200_attn_fwd: cross attention (Lk != L) needs forward variant 3, 4 or 5");
   if (variant == 5) {
     if ((rc = attn_fwd_pp_launch(tq, tk, tv, a, reinterpret_cast<cudaStream_t>(stream)))) return rc;
     ctx->launches.fetch_add(1);
@@ -946,14 +952,22 @@ extern "C" int b200_attn_bwd(b200_ctx* ctx, const void* Q, const void* K, const 
                              const void* o1, int ld1, const void* do0, int ldd0, const void* do1, int ldd1, const void* lse,
                              void* delta, void* dOh, void* dQ, void* dK, void* dV, int B, int H, int L, int split,
                              float scale, void* stream) {
+  return b200_attn_bwd_x(ctx, Q, K, V, o0, ld0, o1, ld1, do0, ldd0, do1, ldd1, lse, delta, dOh, dQ, dK, dV, B, H, L, L, split,
+                         scale, stream);
+}
+
+extern "C" int b200_attn_bwd_x(b200_ctx* ctx, const void* Q, const void* K, const void* V, const void* o0, int ld0,
+                               const void* o1, int ld1, const void* do0, int ldd0, const void* do1, int ldd1, const void* lse,
+                               void* delta, void* dOh, void* dQ, void* dK, void* dV, int B, int H, int L, int Lk, int split,
+                               float scale, void* stream) {
   int rc = check_ctx(ctx);
   if (rc) return rc;
   B200_REQUIRE(Q && K && V && o1 && do1 && lse && delta && dOh && dQ && dK && dV, "b200_attn_bwd: null argument");
-  B200_REQUIRE(B > 0 && H > 0 && L > 0 && split >= 0 && split <= L && (split == 0 || (o0 && do0)), "b200_attn_bwd: bad shape");
+  B200_REQUIRE(B > 0 && H > 0 && L > 0 && Lk > 0 && split >= 0 && split <= L && (split == 0 || (o0 && do0)), "b200_attn_bwd: bad shape");
   B200_REQUIRE(ld1 % 4 == 0 && ldd1 % 4 == 0 && ld0 % 4 == 0 && ldd0 % 4 == 0, "b200_attn_bwd: leading dims %% 4");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  const uint64_t rows = static_cast<uint64_t>(B) * H * L;
-  B200_REQUIRE(rows < (1ull << 31), "b200_attn_bwd: too many rows");
+  const uint64_t rows = static_cast<uint64_t>(B) * H * L, rows_kv = static_cast<uint64_t>(B) * H * Lk;
+  B200_REQUIRE(rows < (1ull << 31) && rows_kv < (1ull << 31), "b200_attn_bwd: too many rows");
   const long long warps = static_cast<long long>(B) * L * H;
   B200_KLAUNCH(attn_delta_kernel, static_cast<unsigned>((warps + 7) / 8), 256, 0, st, (const bf16*)o0, ld0, (const bf16*)o1, ld1,
                                                                             (const bf16*)do0, ldd0, (const bf16*)do1, ldd1,
@@ -961,12 +975,12 @@ extern "C" int b200_attn_bwd(b200_ctx* ctx, const void* Q, const void* K, const 
   B200_CUDA_CHECK(cudaGetLastError());
   CUtensorMap q128, k128, v128, d128, q64, k64, v64, d64;
   if ((rc = attn_maps(ctx, Q, rows, 128, &q128))) return rc;
-  if ((rc = attn_maps(ctx, K, rows, 128, &k128))) return rc;
-  if ((rc = attn_maps(ctx, V, rows, 128, &v128))) return rc;
+  if ((rc = attn_maps(ctx, K, rows_kv, 128, &k128))) return rc;
+  if ((rc = attn_maps(ctx, V, rows_kv, 128, &v128))) return rc;
   if ((rc = attn_maps(ctx, dOh, rows, 128, &d128))) return rc;
   if ((rc = attn_maps(ctx, Q, rows, 64, &q64))) return rc;
-  if ((rc = attn_maps(ctx, K, rows, 64, &k64))) return rc;
-  if ((rc = attn_maps(ctx, V, rows, 64, &v64))) return rc;
+  if ((rc = attn_maps(ctx, K, rows_kv, 64, &k64))) return rc;
+  if ((rc = attn_maps(ctx, V, rows_kv, 64, &v64))) return rc;
   if ((rc = attn_maps(ctx, dOh, rows, 64, &d64))) return rc;
   static bool configured = false;
   // same-box log gpurun_out/r2_trip.log (round 2, 24 x 4608 x 128): variant 2 (attention_r2.cu: LDS, deferred prefetch
@@ -980,8 +994,10 @@ extern "C" int b200_attn_bwd(b200_ctx* ctx, const void* Q, const void* K, const 
     configured = true;
   }
   dim3 grid((L + 127) / 128, B * H);
-  AttnBwdArgs akv{(const float*)lse, (const float*)delta, nullptr, nullptr, (bf16*)dV, (bf16*)dK, L, scale};
-  AttnBwdArgs aq{(const float*)lse, (const float*)delta, (const bf16*)Q, (const bf16*)dOh, (bf16*)dQ, nullptr, L, scale};
+  // dK/dV pass: keys / values stationary (length Lk), queries streamed (L); dQ pass: the other way round
+  AttnBwdArgs akv{(const float*)lse, (const float*)delta, nullptr, nullptr, (bf16*)dV, (bf16*)dK, Lk, scale, L};
+  AttnBwdArgs aq{(const float*)lse, (const float*)delta, (const bf16*)Q, (const bf16*)dOh, (bf16*)dQ, nullptr, L, scale, Lk};
+  B200_REQUIRE(Lk == L || variant == 2 || variant == 3, "b200_attn_bwd: cross attention (Lk != L) needs backward variant 2 or 3");
   if (variant >= 2) {
     if ((rc = attn_bwd_r2_launch(variant, k128, v128, q64, d64, q128, d128, k64, v64, akv, aq, B, H, st))) return rc;
     ctx->launches.fetch_add(3);

@@ -77,8 +77,9 @@ attn_fwd_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   const int warp = warp_id_uniform(), lane = threadIdx.x & 31;
   const int bh = blockIdx.y;
   const int q0 = blockIdx.x * 256;
-  const int n_kv = (g.L + 127) / 128;
-  const long long row_base = static_cast<long long>(bh) * g.L;
+  const int n_kv = (g.Lk + 127) / 128;
+  const long long row_base = static_cast<long long>(bh) * g.L;   // query rows / lse
+  const long long kv_base = static_cast<long long>(bh) * g.Lk;  // key / value rows
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmQ);
@@ -120,7 +121,7 @@ attn_fwd_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       for (int j = 0; j < n_kv; ++j) {
         const int s = j & 1;
         const uint32_t ph = (j >> 1) & 1;
-        const int kvrow = static_cast<int>(row_base + j * 128);
+        const int kvrow = static_cast<int>(kv_base + j * 128);
         mbar_wait(&k_empty[s], ph ^ 1u, 30);
         mbar_arrive_expect_tx(&k_full[s], 32768);
         tma_load_2d(sK + s * 32768, &tmK, &k_full[s], 0, kvrow);
@@ -199,7 +200,7 @@ attn_fwd_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     const uint32_t tO = tmem_base + 256u + static_cast<uint32_t>(t) * 128u + lane_off;
     const float c2 = g.scale * kLog2e;
     const float2 c22 = make_float2(c2, c2);
-    const int tail = g.L & 127;
+    const int tail = g.Lk & 127;
     float m_used = -INFINITY, l_sum = 0.f;
     for (int j = 0; j < n_kv; ++j) {
       mbar_wait(&s_full[t], j & 1, 38);

@@ -85,8 +85,9 @@ attn_fwd_nt_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   const int warp = warp_id_uniform(), lane = threadIdx.x & 31;
   const int bh = blockIdx.y;
   const int q0 = blockIdx.x * 128;
-  const int n_kv = (g.L + 127) / 128;
-  const long long row_base = static_cast<long long>(bh) * g.L;
+  const int n_kv = (g.Lk + 127) / 128;
+  const long long row_base = static_cast<long long>(bh) * g.L;   // query rows / lse
+  const long long kv_base = static_cast<long long>(bh) * g.Lk;  // key / value rows
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmQ);
@@ -129,7 +130,7 @@ attn_fwd_nt_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       for (int j = 0; j < n_kv; ++j) {
         const int s = j & 1;
         const uint32_t ph = (j >> 1) & 1;
-        const int kvrow = static_cast<int>(row_base + j * 128);
+        const int kvrow = static_cast<int>(kv_base + j * 128);
         mbar_wait(&k_empty[s], ph ^ 1u, 10);
         mbar_arrive_expect_tx(&k_full[s], 32768);
         tma_load_2d(sK + s * 32768, &tmK, &k_full[s], 0, kvrow);
@@ -209,7 +210,7 @@ attn_fwd_nt_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       tmem_ld_wait();
       tc_fence_before();
       mbar_arrive(&s_empty[s]);  // S is in registers: the tensor core may overwrite this buffer
-      const int nvalid = g.L - (j * 128 + h * CW);  // columns of my part that exist
+      const int nvalid = g.Lk - (j * 128 + h * CW);  // columns of my part that exist
       if (nvalid < CW) {  // ragged last tile only: missing columns become -inf IN PLACE (no second copy of the row)
 #pragma unroll
         for (int i = 0; i < CW; ++i)
@@ -355,8 +356,9 @@ attn_bwd_r2_kernel(const __grid_constant__ CUtensorMap tmR0, const __grid_consta
   const int warp = warp_id_uniform(), lane = threadIdx.x & 31;
   const int bh = blockIdx.y;
   const int r0 = blockIdx.x * 128;
-  const int n_t = (g.L + 63) / 64;
-  const long long row_base = static_cast<long long>(bh) * g.L;
+  const int n_t = (g.Lt + 63) / 64;                               // streamed side
+  const long long row_base = static_cast<long long>(bh) * g.L;   // stationary side (and its outputs)
+  const long long t_base = static_cast<long long>(bh) * g.Lt;    // streamed side
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmR0);
@@ -407,7 +409,7 @@ attn_bwd_r2_kernel(const __grid_constant__ CUtensorMap tmR0, const __grid_consta
       for (int i = 0; i < n_t; ++i) {
         const int st = i % kStages;
         const uint32_t ph = (i / kStages) & 1;
-        const int trow = static_cast<int>(row_base + i * 64);
+        const int trow = static_cast<int>(t_base + i * 64);
         mbar_wait(&t_empty[st], ph ^ 1u, 20000 + i);
         mbar_arrive_expect_tx(&t_full[st], 32768);
         uint8_t* d = sT + st * 32768;
@@ -498,8 +500,9 @@ attn_bwd_r2_kernel(const __grid_constant__ CUtensorMap tmR0, const __grid_consta
     const int ri = r0 + r;  // kv index (MODE_KV) or q index
     const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
     const float c2 = g.scale * kLog2e;
-    const float* lse_bh = g.lse + row_base;
-    const float* delta_bh = g.delta + row_base;
+    // lse / delta are indexed by QUERY position: the streamed side of the dK/dV pass, the stationary side of the dQ pass
+    const float* lse_bh = g.lse + (MODE_KV ? t_base : row_base);
+    const float* delta_bh = g.delta + (MODE_KV ? t_base : row_base);
     float* myws = colws + (warp - 2) * (2 * CW);  // per warp: CW x lse2, CW x delta*scale
     float my_lse2 = 0.f, my_dls = 0.f;
     if (!MODE_KV && ri < g.L) {
@@ -540,8 +543,8 @@ attn_bwd_r2_kernel(const __grid_constant__ CUtensorMap tmR0, const __grid_consta
 #pragma unroll
       for (int k = 0; k < NPF; ++k) {
         const int c = i * 64 + hh * CW + k * 32 + lane;
-        nl[k] = c < g.L ? lse_bh[c] : 0.f;
-        nd[k] = c < g.L ? delta_bh[c] : 0.f;
+        nl[k] = c < g.Lt ? lse_bh[c] : 0.f;
+        nd[k] = c < g.Lt ? delta_bh[c] : 0.f;
       }
     };
     if (MODE_KV && gq < n_t) fetch_cols(gq);
@@ -559,7 +562,7 @@ attn_bwd_r2_kernel(const __grid_constant__ CUtensorMap tmR0, const __grid_consta
       }
       mbar_wait(&x_full[gq], xph, 25000 + i + 100000 * MODE_KV);
       tc_fence_after();
-      const int nvalid = g.L - (i * 64 + hh * CW);  // columns of my part that exist (<= 0: none)
+      const int nvalid = g.Lt - (i * 64 + hh * CW);  // columns of my part that exist (<= 0: none)
       uint32_t pp[CW / 2], dd[CW / 2];             // packed bf16 pairs of my columns: P and dS
       uint32_t sv[2][16], dv[2][16];               // two chunks in flight (ping-pong)
       const uint32_t cs = X0(gq) + lane_off + hh * CW, cd = X1(gq) + lane_off + hh * CW;
@@ -948,10 +951,10 @@ static int launch_bwd_nh(const CUtensorMap& k128, const CUtensorMap& v128, const
     B200_CUDA_CHECK(cudaFuncSetAttribute(kq, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdR2Smem));
     configured = true;
   }
-  dim3 grid((akv.L + 127) / 128, B * H);
-  B200_KLAUNCH(kkv, grid, 64 + 256 * NH, kBwdR2Smem, stream, k128, v128, q64, d64, akv);
+  dim3 grid_kv((akv.L + 127) / 128, B * H), grid_q((aq.L + 127) / 128, B * H);
+  B200_KLAUNCH(kkv, grid_kv, 64 + 256 * NH, kBwdR2Smem, stream, k128, v128, q64, d64, akv);
   B200_CUDA_CHECK(cudaGetLastError());
-  B200_KLAUNCH(kq, grid, 64 + 256 * NH, kBwdR2Smem, stream, q128, d128, k64, v64, aq);
+  B200_KLAUNCH(kq, grid_q, 64 + 256 * NH, kBwdR2Smem, stream, q128, d128, k64, v64, aq);
   B200_CUDA_CHECK(cudaGetLastError());
   return B200_OK;
 }

@@ -96,6 +96,7 @@ struct AttnFwdArgs {
   float* lse;
   int B, H, L, split;
   float scale;
+  int Lk;  // key / value length (== L for self / joint attention; != L for cross attention: fwd variants 3, 4, 5 only)
 };
 
 
@@ -106,8 +107,9 @@ struct AttnBwdArgs {
   const bf16* r1;  // MODE_Q: dO [B,H,L,128]
   bf16* out0;  // MODE_KV: dV ; MODE_Q: dQ
   bf16* out1;  // MODE_KV: dK
-  int L;
+  int L;   // length of the STATIONARY side (MODE_KV: keys / values; MODE_Q: queries)
   float scale;
+  int Lt;  // length of the STREAMED side (MODE_KV: queries; MODE_Q: keys / values); == L for self / joint attention
 };
 
 

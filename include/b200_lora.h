@@ -177,6 +177,15 @@ int b200_attn_bwd(b200_ctx* ctx, const void* Q, const void* K, const void* V, co
                   int ld1, const void* do0, int ldd0, const void* do1, int ldd1, const void* lse, void* delta, void* dOh,
                   void* dQ, void* dK, void* dV, int B, int H, int L, int split, float scale, void* stream);
 
+/* Cross attention: Q [B,H,L,128] against K / V [B,H,Lk,128] with Lk != L (Wan2.1's text cross-attention,
+ * toolkit/models/wan21/wan_attn.py:70-76: F.scaled_dot_product_attention(query, key, value) with key / value from the
+ * 512 text tokens).  Same kernels, outputs, scratch and layouts as above; lse / delta [B,H,L]; dK / dV [B,H,Lk,128]. */
+int b200_attn_fwd_x(b200_ctx* ctx, const void* Q, const void* K, const void* V, void* o0, int ld0, void* o1, int ld1,
+                    void* lse, int B, int H, int L, int Lk, int split, float scale, void* stream);
+int b200_attn_bwd_x(b200_ctx* ctx, const void* Q, const void* K, const void* V, const void* o0, int ld0, const void* o1,
+                    int ld1, const void* do0, int ldd0, const void* do1, int ldd1, const void* lse, void* delta, void* dOh,
+                    void* dQ, void* dK, void* dV, int B, int H, int L, int Lk, int split, float scale, void* stream);
+
 /* -------------------------------------------------------------------------------------------------
  * LoRA-wrapped Linear for Bm <= 8 rows (the AdaLN modulation projections): weight streaming at the
  * HBM roofline, fp32 master A [r,K] / B [N,r] used directly.

@@ -103,3 +103,28 @@ def test_attention_fwd_variant2_two_streams():
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     out = subprocess.run([sys.executable, "-c", code], cwd=root, env=env, capture_output=True, text=True, timeout=300)
     assert out.returncode == 0, out.stdout + out.stderr
+
+
+@pytest.mark.parametrize("B,H,Lq,Lk", [(1, 2, 300, 77), (2, 3, 1000, 512), (1, 2, 64, 200), (1, 12, 3328, 512)])
+def test_cross_attention_fwd_bwd(B, H, Lq, Lk):
+    """Lq != Lk (b200_attn_fwd_x / b200_attn_bwd_x): Wan2.1's text cross-attention (toolkit/models/wan21/wan_attn.py:70-76),
+    ragged on both sides, against the fp32 reference of the same op."""
+    from ai_toolkit_b200 import attention
+    torch.manual_seed(Lq + Lk)
+    Q = torch.randn(B, H, Lq, 128, device=DEV).bfloat16()
+    K = torch.randn(B, H, Lk, 128, device=DEV).bfloat16()
+    V = torch.randn(B, H, Lk, 128, device=DEV).bfloat16()
+    D = H * 128
+    o1 = torch.full((B * Lq, D), float("nan"), device=DEV, dtype=torch.bfloat16)
+    lse = attention.fwd(Q, K, V, None, o1, 0)
+    dO = torch.randn(B, Lq, D, device=DEV).bfloat16()
+    o_ref, lse_ref, dq_ref, dk_ref, dv_ref = _ref(Q, K, V, dO.view(B, Lq, H, 128).transpose(1, 2))
+    assert not torch.isnan(o1.float()).any()
+    assert _rel(o1.view(B, Lq, D), o_ref.transpose(1, 2).reshape(B, Lq, D)) < 1e-2
+    assert (lse - lse_ref).abs().max().item() < 2e-2
+    dQ, dK, dV = attention.bwd(Q, K, V, None, o1, None, dO.reshape(B * Lq, D).contiguous(), lse, 0)
+    torch.cuda.synchronize()
+    assert dQ.shape == Q.shape and dK.shape == K.shape and dV.shape == V.shape
+    for name, g, r in (("dQ", dQ, dq_ref), ("dK", dK, dk_ref), ("dV", dV, dv_ref)):
+        assert not torch.isnan(g.float()).any(), name
+        assert _rel(g, r) < 1.5e-2, (name, _rel(g, r))

@@ -13,3 +13,14 @@ run B200_ATTN_FWD=5 python -m pytest tests/test_gpu_flux_engine.py -x -q -p no:c
 run python -m pytest tests/test_gpu_batch_ops.py -q -p no:cacheprovider
 run B200_ATTN_FWD=5 python bench.py --steps 10 --warmup 3 --skip-cpu-baseline --skip-gpu-reference
 grep -E "^\[|^== |exit|passed|failed|\"value\"" $LOG | cut -c1-250
+# programmatic dependent launch build (griddepcontrol in every kernel, PDL attribute on every launch): never measured in round 1
+PDL=ai_toolkit_b200/lib/libb200lora_pdl.so
+run B200_LIB=$PDL python -m pytest tests/test_gpu_gemm.py tests/test_gpu_ops.py tests/test_gpu_attention.py -x -q -p no:cacheprovider
+run B200_LIB=$PDL python -m pytest tests/test_gpu_flux_engine.py -x -q -p no:cacheprovider -k "oracle or golden or 20"
+run B200_LIB=$PDL python bench.py --steps 10 --warmup 3 --skip-cpu-baseline --skip-gpu-reference
+run python bench.py --steps 10 --warmup 3 --skip-cpu-baseline --skip-gpu-reference
+for n in 74 40 20; do
+  run B200_GEMM_PAIR_MIN=$n python bench.py --steps 10 --warmup 3 --skip-cpu-baseline --skip-gpu-reference
+done
+grep -E "^\[|^== |exit|passed|failed" $LOG | cut -c1-250 | tail -40
+grep -o '"ms_per_step": [0-9.]*' $LOG
