@@ -328,7 +328,9 @@ __global__ void timestep_embed_kernel(const float* __restrict__ t_in, bf16* __re
   pdl_grid_sync();
   const int b = blockIdx.x;
   const int half = dim / 2;
-  const float t = bf16_round(bf16_round(t_in[b] / div) * mult);
+  // mult > 0: the bf16 model re-scales in bf16 (FLUX).  mult <= 0: t = t_in / div stays fp32 (Wan2.1: `timesteps_proj` runs on
+  // the trainer's fp32 timestep, 0..1000)
+  const float t = mult > 0.f ? bf16_round(bf16_round(t_in[b] / div) * mult) : t_in[b] / div;
   for (int i = threadIdx.x; i < half; i += blockDim.x) {
     const float f = expf(-logf(max_period) * static_cast<float>(i) / static_cast<float>(half));
     const float ang = t * f;

@@ -77,6 +77,24 @@ def qk_norm_rope_bwd(dQ, dK, dV, q, k, wq, wk, cos, sin, dq, dk, dv, B, Lseg, se
               float(eps), device=_dev(q))
 
 
+def rms_rope_fwd(x, weight, cos, sin, out, B, Lseg, seq_off=0, eps=1e-6, mode=1):
+    """x [B*Lseg, >= H*128] bf16 view -> out [B, H, Ltot, 128] bf16 (RMSNorm across heads + optional RoPE, or mode 0: plain
+    re-layout); returns rstd [B*Lseg] fp32 (None for mode 0)."""
+    H, Ltot = out.shape[1], out.shape[2]
+    rstd = torch.empty(B * Lseg, device=x.device, dtype=torch.float32) if mode == 1 else None
+    cabi.call("b200_rms_rope_fwd", _p(x), int(x.stride(0)), _p(weight), _p(cos), _p(sin), _p(out), _p(rstd), int(B), int(Lseg),
+              int(seq_off), int(Ltot), int(H), float(eps), int(mode), device=_dev(x))
+    return rstd
+
+
+def rms_rope_bwd(dY, x, weight, cos, sin, rstd, dx, B, Lseg, seq_off=0, mode=1):
+    """dY [B, H, Ltot, 128] -> dx [B*Lseg, >= H*128] view (token-major)."""
+    H, Ltot = dY.shape[1], dY.shape[2]
+    cabi.call("b200_rms_rope_bwd", _p(dY), _p(x), 0 if x is None else int(x.stride(0)), _p(weight), _p(cos), _p(sin), _p(rstd),
+              _p(dx), int(dx.stride(0)), int(B), int(Lseg), int(seq_off), int(Ltot), int(H), int(mode), device=_dev(dY))
+    return dx
+
+
 def silu(x, out=None):
     out = torch.empty_like(x) if out is None else out
     cabi.call("b200_silu", _p(x), _p(out), x.numel(), device=_dev(x))

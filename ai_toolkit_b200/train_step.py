@@ -235,6 +235,9 @@ class FluxLoRATrainStep:
         self.network.refresh_packs(force=True)
         return out
 
+    def _load_dict(self, b):
+        self.load_batch(b["latents"], b["noise"], b["timesteps"], b["text_embeds"], b["pooled_embeds"])
+
     def run(self, first_micro_batch=True, last_micro_batch=True):
         """Launch one (micro-)step on the resident batch; returns the device loss scalar (no host sync).
 
@@ -274,9 +277,88 @@ class FluxLoRATrainStep:
         batches = batch if isinstance(batch, (list, tuple)) else [batch]
         total = 0.0
         for i, b in enumerate(batches):
-            self.load_batch(b["latents"], b["noise"], b["timesteps"], b["text_embeds"], b["pooled_embeds"])
+            self._load_dict(b)
             loss = self.run(first_micro_batch=(i == 0), last_micro_batch=(i == len(batches) - 1))
             self.loss_host.copy_(loss, non_blocking=True)
             torch.cuda.current_stream().synchronize()
             total += float(self.loss_host[0])
         return OrderedDict(loss=total / len(batches))
+
+
+class WanLoRATrainStep(FluxLoRATrainStep):
+    """The same step for the Wan2.1 video DiT (BASELINE.json configs[3]): `Wan21.get_noise_prediction`
+    (toolkit/models/wan21/wan21.py:578-603: raw 0..1000 timestep, UMT5 embeddings, no pooled vector / guidance) and
+    `get_loss_target` = noise - latents (:717-724); flow-matching add_noise with the scheduler of :80-84 (shift 3.0 is a
+    property of the timestep TABLE, i.e. of `prepare_batch(timestep_type='shift')`, not of add_noise).  Latents are 5-D
+    [B, 16, F, H, W]; the (1, 2, 2) patchify is the packed layout of the add-noise kernel on the [B, 16, F*H, W] view."""
+
+    def __init__(self, model, network, optimizer, *, batch_size, latent_shape=(16, 13, 64, 64), text_len=512,
+                 loss_multiplier=1.0, use_cuda_graph=True, process_group=None, **kw):
+        self.model, self.network, self.optimizer = model, network, optimizer
+        dev = model.device
+        self.dev = dev
+        C, Fr, H, W = latent_shape
+        B = batch_size
+        self.B, self.C, self.F, self.H, self.W, self.Lt = B, C, Fr, H, W, text_len
+        self.grid = (Fr, H // 2, W // 2)
+        self.loss_multiplier = float(loss_multiplier)
+        self.use_cuda_graph = use_cuda_graph
+        self.pg = process_group
+        self.world = 1
+        if process_group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
+            self.world = torch.distributed.get_world_size(process_group)
+        bf = torch.bfloat16
+        self.latents = torch.zeros((B, C, Fr * H, W), device=dev, dtype=bf)  # 4-D view of the 5-D latents (F and H merged)
+        self.noise = torch.zeros((B, C, Fr * H, W), device=dev, dtype=bf)
+        self.timesteps = torch.zeros(B, device=dev, dtype=torch.float32)
+        self.text = torch.zeros((B, text_len, model.cfg.text_dim), device=dev, dtype=bf)
+        self.pooled = None
+        self.timestep_type = kw.get("timestep_type", "shift")
+        self.num_train_timesteps = int(kw.get("num_train_timesteps", 1000))
+        self.min_denoising_steps, self.max_denoising_steps = int(kw.get("min_denoising_steps", 0)), int(kw.get("max_denoising_steps", 999))
+        self.linear_timesteps = self.linear_timesteps2 = False
+        self.noise_multiplier, self.latent_multiplier = float(kw.get("noise_multiplier", 1.0)), float(kw.get("latent_multiplier", 1.0))
+        self.use_loss_options = bool(kw.get("use_loss_options", False))
+        self.sample_weight = torch.ones(B, device=dev, dtype=torch.float32) if self.use_loss_options else None
+        self.mask = None
+        self._table = None
+        self.loss_ws = torch.zeros(B + 1, device=dev, dtype=torch.float32)
+        self.loss_host = torch.zeros(1, dtype=torch.float32)
+        if torch.device(dev).type == "cuda":
+            self.loss_host = self.loss_host.pin_memory()
+        if self.world > 1:
+            self._setup_replicas()
+        self._graph_fb = None
+        self._graph_opt = None
+        self._warm = 0
+
+    def load_batch(self, latents, noise, timesteps, text_embeds, pooled_embeds=None):
+        B = self.B
+        self.latents.copy_(latents.reshape(B, self.C, self.F * self.H, self.W), non_blocking=True)
+        self.noise.copy_(noise.reshape(B, self.C, self.F * self.H, self.W), non_blocking=True)
+        self.timesteps.copy_(timesteps, non_blocking=True)
+        self.text.copy_(text_embeds, non_blocking=True)
+
+    def _load_dict(self, b):
+        self.load_batch(b["latents"], b["noise"], b["timesteps"], b["text_embeds"])
+
+    def _forward_backward(self):
+        net = self.network
+        packed = ops.flow_add_noise(self.latents, self.noise, self.timesteps, pack=True)  # add_noise + (1, 2, 2) patchify
+        net.is_active = True
+        try:
+            eng = self.model.engine
+            pred = eng.forward(packed, self.timesteps, self.text, self.grid, save=True)
+            if self.use_loss_options or self.mask is not None:
+                _, _, dpred = ops.train_loss(pred.view(self.B, -1, pred.shape[-1]), self.latents, self.noise,
+                                             sample_weight=self.sample_weight, mask=self.mask, pack=True,
+                                             gscale=self.loss_multiplier, loss_ws=self.loss_ws)
+            else:
+                _, _, dpred = ops.flow_loss(pred.view(self.B, -1, pred.shape[-1]), self.latents, self.noise, pack=True,
+                                            gscale=self.loss_multiplier, loss_ws=self.loss_ws)
+            eng.backward(dpred.view(-1, pred.shape[-1]))
+        finally:
+            net.is_active = False
+
+    def validate(self, *a, **k):
+        raise NotImplementedError("validate() is implemented for the FLUX step")

@@ -156,7 +156,8 @@ int b200_qk_norm_rope_bwd(b200_ctx* ctx, const void* dQ, const void* dK, const v
                           void* dv, int ldd, int B, int Lseg, int seq_off, int Ltot, int H, int head_dim, float eps,
                           void* stream);
 int b200_silu(b200_ctx* ctx, const void* x, void* y, int64_t n, void* stream);
-/* out[b,:] = bf16([cos(t f_i) | sin(t f_i)]), t = bf16(bf16(t_in[b] / div) * mult)  (chroma/src/layers.py:30-53) */
+/* out[b,:] = bf16([cos(t f_i) | sin(t f_i)]), t = bf16(bf16(t_in[b] / div) * mult)  (chroma/src/layers.py:30-53);
+ * mult <= 0: t = t_in[b] / div in fp32 (Wan2.1 embeds the trainer's fp32 timestep directly) */
 int b200_timestep_embed(b200_ctx* ctx, const void* t_in, void* out, int B, int dim, float max_period, float div,
                         float mult, void* stream);
 int b200_add_bf16(b200_ctx* ctx, const void* a, const void* b, const void* c, void* y, int64_t n, void* stream);
@@ -185,6 +186,16 @@ int b200_attn_fwd_x(b200_ctx* ctx, const void* Q, const void* K, const void* V, 
 int b200_attn_bwd_x(b200_ctx* ctx, const void* Q, const void* K, const void* V, const void* o0, int ld0, const void* o1,
                     int ld1, const void* do0, int ldd0, const void* do1, int ldd1, const void* lse, void* delta, void* dOh,
                     void* dQ, void* dK, void* dV, int B, int H, int L, int Lk, int split, float scale, void* stream);
+
+/* Wan2.1 attention pre-processing (toolkit/models/wan21/wan_attn.py:34-61): RMSNorm ACROSS heads (one RMS over the whole
+ * inner dimension H*128, diffusers qk_norm="rms_norm_across_heads") + RoPE on interleaved pairs (cos/sin [Ltot,128] fp32, NULL:
+ * no rotation = the cross-attention) + re-layout of ONE tensor x [B*Lseg, ld] to head-major out [B,H,Ltot,128].
+ * mode 0: plain re-layout (values); mode 1: norm (+ rope), rstd [B*Lseg] fp32 saved for the backward. */
+int b200_rms_rope_fwd(b200_ctx* ctx, const void* x, int ld, const void* weight, const void* cos_t, const void* sin_t, void* out,
+                      void* rstd, int B, int Lseg, int seq_off, int Ltot, int H, float eps, int mode, void* stream);
+int b200_rms_rope_bwd(b200_ctx* ctx, const void* dY, const void* x, int ld, const void* weight, const void* cos_t,
+                      const void* sin_t, const void* rstd, void* dx, int ldd, int B, int Lseg, int seq_off, int Ltot, int H,
+                      int mode, void* stream);
 
 /* -------------------------------------------------------------------------------------------------
  * LoRA-wrapped Linear for Bm <= 8 rows (the AdaLN modulation projections): weight streaming at the
