@@ -917,8 +917,10 @@ extern "C" int b200_attn_fwd_x(b200_ctx* ctx, const void* Q, const void* K, cons
   static bool configured = false;
   // same-box log gpurun_out/r2_trip.log (round 2, 24 x 4608 x 128): variant 3 (attention_r2.cu: packed FFMA2 softmax, scale
   // folded into the exponent FFMA) 255.3 us = 1022 TF/s; variant 4 (16 softmax warps) 256.3 us; variant 1 278.2 us;
-  // variant 2 (two streams) 304 us in round 1.  B200_ATTN_FWD=1|2|4 selects the others for A/B runs.
-  static int variant = 3;
+  // variant 2 (two streams) 304 us in round 1.  Variant 5 (attention_pp.cu: two Q tiles per CTA in ping-pong, one softmax
+  // thread per row) 221.6 us = 1177 TF/s vs 257.8 us for variant 3 in the same log (gpurun_out/r2_pp.log); parity and unit
+  // tests green with it.  B200_ATTN_FWD=1|2|3|4 selects the others for A/B runs.
+  static int variant = 5;
   if (!configured) {
     B200_CUDA_CHECK(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwdSmem));
     B200_CUDA_CHECK(cudaFuncSetAttribute(attn_fwd2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwdSmem));

@@ -37,6 +37,8 @@ METRIC = "train-steps/sec FLUX.1-dev LoRA r=16 bs=1 1024^2"
 
 
 def workload_name(args):
+    if getattr(args, "model", "flux") == "wan":
+        return f"Wan2.1-T2V-1.3B LoRA r={args.rank} bs={args.batch}/GPU 49x512x512 clip (BASELINE.json configs[3])"
     if args.batch == 1 and args.rank == 16:
         return "FLUX.1-dev LoRA r=16 bs=1/GPU 1024^2 (BASELINE.json configs[2])"
     return f"FLUX.1-dev LoRA r={args.rank} bs={args.batch}/GPU 1024^2 (BASELINE.json configs[4] rank sweep)"
@@ -54,6 +56,17 @@ def flux_flops(B=1, r=RANK, I=4096, T=512, D=3072, M=12288, n_double=19, n_singl
                             (L, D, D, 3 * n_single), (L, D, M, n_single), (L, D + M, D, n_single), (1, D, 3 * D, n_single)):
         lora += cnt * 2 * B * toks * r * (i + o)
     return 2 * f_lin + 3.5 * f_attn + 3 * lora, f_lin, f_attn, lora
+
+
+WAN_LATENT = (16, 13, 64, 64)  # 49 frames x 512 x 512 -> (49 - 1) / 4 + 1 = 13 latent frames x 64 x 64 -> 13,312 tokens
+
+
+def wan_flops(B=1, r=RANK, L=13312, T=512, D=1536, F=8960, H=12, layers=30):
+    """Algorithmic FLOPs of one Wan2.1-T2V-1.3B LoRA step: 2 F_lin + 3.5 F_attn + 3 F_lora."""
+    f_lin = layers * (2 * B * L * (6 * D * D + 2 * D * F) + 2 * B * T * 2 * D * D)
+    f_attn = layers * (4 * B * H * L * L * 128 + 4 * B * H * L * T * 128)
+    f_lora = layers * 2 * B * r * (L * (8 * D + 4 * D + 2 * (D + F)) + T * 4 * D)
+    return 2 * f_lin + 3.5 * f_attn + 3 * f_lora, f_lin, f_attn, f_lora
 
 
 def measured_peaks():
@@ -284,6 +297,66 @@ def gpu_reference_leg(dev, steps=3, warmup=2, rank=None, batch=1):
     return out
 
 
+def gpu_reference_leg_wan(dev, steps=3, warmup=2, rank=None, batch=1):
+    """The same eager reference-style step for Wan2.1-T2V-1.3B (oracle/wan_ref.py blocks, whose attention is pinned to the
+    reference's in-tree WanAttnProcessor2_0, + the reference LoRA forward + torch SDPA + torch AdamW)."""
+    import torch
+
+    from oracle import lora_ref, wan_ref
+
+    rank = rank or RANK
+    torch.set_default_dtype(torch.bfloat16)
+    with torch.device(dev):
+        model = wan_ref.WanTransformer3DModel(wan_ref.wan_1_3b_config())
+    torch.set_default_dtype(torch.float32)
+    g = torch.Generator(device=dev).manual_seed(0)
+    with torch.no_grad():
+        for p in model.parameters():
+            p.copy_(torch.randn(p.shape, generator=g, device=dev, dtype=torch.float32) * 0.02)
+    model.requires_grad_(False)
+    net = lora_ref.LoRANetworkRef(model, lora_dim=rank, target_class="WanTransformer3DModel", block_substr="blocks").to(dev)
+    with torch.no_grad():
+        for l in net.loras:
+            l.lora_up.weight.normal_(0, 0.02)
+    params = [p for l in net.loras for p in (l.lora_down.weight, l.lora_up.weight)]
+    opt = torch.optim.AdamW(params, lr=1e-4, eps=1e-6)
+    lat = torch.randn(batch, *WAN_LATENT, device=dev).bfloat16()
+    noise = torch.randn_like(lat)
+    t = torch.full((batch,), 500.0, device=dev)
+    text = (torch.randn(batch, TEXT_LEN, 4096, device=dev) * 0.1).bfloat16()
+
+    def step():
+        opt.zero_grad(set_to_none=True)
+        noisy = lora_ref.add_noise_flowmatch(lat, noise, t).to(torch.bfloat16)
+        with net:
+            loss = lora_ref.flow_loss(wan_ref.wan_predict(model, noisy, t, text), lat, noise)
+            loss.backward()
+        torch.nn.utils.clip_grad_norm_(params, 1.0)
+        opt.step()
+        return loss
+
+    out = {"what": "eager PyTorch reference-style Wan2.1 step on the same GPU (oracle blocks + reference LoRA forward + torch "
+                   "SDPA + torch AdamW), CUDA-event timed", "steps": steps, "warmup": warmup}
+    for name, ck in (("checkpointing", True), ("no_checkpointing", False)):
+        try:
+            model.gradient_checkpointing = ck
+            for _ in range(warmup):
+                step()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(steps):
+                loss = step()
+            e1.record()
+            torch.cuda.synchronize()
+            out[name] = {"ms_per_step": e0.elapsed_time(e1) / steps, "loss": float(loss)}
+        except Exception as e:
+            out[name] = {"error": f"{type(e).__name__}: {str(e)[:100]}"}
+            torch.cuda.empty_cache()
+    out["peak_mem_gib"] = torch.cuda.max_memory_allocated() / 2 ** 30
+    return out
+
+
 # ---------------------------------------------------------------------------------------------------
 # B200 arm
 # ---------------------------------------------------------------------------------------------------
@@ -305,14 +378,28 @@ def run_b200(args):
     from ai_toolkit_b200.train_step import FluxLoRATrainStep
 
     ctx = cabi.Context.get(local)
-    cfg = flux_dev_config()
-    if args.layers:
-        cfg.num_layers, cfg.num_single_layers = args.layers
+    WAN = args.model == "wan"
     t_setup = time.time()
-    model = FluxTransformer2DModel(cfg, device=dev).init_synthetic_(seed=0)
     BS, R = args.batch, args.rank
-    net = LoRASpecialNetwork(text_encoder=None, unet=model, lora_dim=R, alpha=R, train_unet=True,
-                             train_text_encoder=False, is_flux=True, transformer_only=True)
+    if WAN:
+        from ai_toolkit_b200 import wan_keys
+        from ai_toolkit_b200.train_step import WanLoRATrainStep
+        from ai_toolkit_b200.wan import WanTransformer3DModel, wan_1_3b_config
+
+        cfg = wan_1_3b_config()
+        if args.layers:
+            cfg.num_layers = args.layers[0]
+        model = WanTransformer3DModel(cfg, device=dev).init_synthetic_(seed=0)
+        net = LoRASpecialNetwork(text_encoder=None, unet=model, lora_dim=R, alpha=R, train_unet=True, train_text_encoder=False,
+                                 transformer_only=True, is_transformer=True, target_lin_modules=["WanTransformer3DModel"],
+                                 base_model=wan_keys.WanLoRABaseModel())
+    else:
+        cfg = flux_dev_config()
+        if args.layers:
+            cfg.num_layers, cfg.num_single_layers = args.layers
+        model = FluxTransformer2DModel(cfg, device=dev).init_synthetic_(seed=0)
+        net = LoRASpecialNetwork(text_encoder=None, unet=model, lora_dim=R, alpha=R, train_unet=True,
+                                 train_text_encoder=False, is_flux=True, transformer_only=True)
     net.force_to(dev, torch.float32)
     net._update_torch_multiplier()
     net.apply_to(None, model, False, True)
@@ -323,20 +410,25 @@ def run_b200(args):
     net.mark_params_changed()
     opt = B200AdamW(net, lr=1e-4, betas=(0.9, 0.999), eps=1e-6, weight_decay=1e-2, max_grad_norm=1.0, ema_decay=0.99,
                     grad_prescale=1.0 / world)
-    step = FluxLoRATrainStep(model, net, opt, batch_size=BS, latent_shape=LATENT, text_len=TEXT_LEN, guidance_scale=1.0,
-                             use_cuda_graph=not args.no_graph)
-    # synthetic batch: host (pinned) copies for the e2e leg, seeded per rank (SURVEY.md section 8d)
     hg = torch.Generator().manual_seed(1234 + rank)
+    lat_shape = WAN_LATENT if WAN else LATENT
+    if WAN:
+        step = WanLoRATrainStep(model, net, opt, batch_size=BS, latent_shape=WAN_LATENT, text_len=TEXT_LEN,
+                                use_cuda_graph=not args.no_graph)
+    else:
+        step = FluxLoRATrainStep(model, net, opt, batch_size=BS, latent_shape=LATENT, text_len=TEXT_LEN, guidance_scale=1.0,
+                                 use_cuda_graph=not args.no_graph)
+    # synthetic batch: host (pinned) copies for the e2e leg, seeded per rank (SURVEY.md section 8d)
     host = {
-        "latents": torch.randn(BS, *LATENT, generator=hg).bfloat16().pin_memory(),
-        "noise": torch.randn(BS, *LATENT, generator=hg).bfloat16().pin_memory(),
+        "latents": torch.randn(BS, *lat_shape, generator=hg).bfloat16().pin_memory(),
+        "noise": torch.randn(BS, *lat_shape, generator=hg).bfloat16().pin_memory(),
         "timesteps": torch.linspace(1000, 1, 1000)[torch.randint(0, 999, (BS,), generator=hg)].float().pin_memory(),
         "text_embeds": (torch.randn(BS, TEXT_LEN, 4096, generator=hg) * 0.1).bfloat16().pin_memory(),
-        "pooled_embeds": torch.randn(BS, 768, generator=hg).bfloat16().pin_memory(),
     }
+    if not WAN:
+        host["pooled_embeds"] = torch.randn(BS, 768, generator=hg).bfloat16().pin_memory()
     h2d = sum(v.numel() * v.element_size() for v in host.values())
-    step.load_batch(**{k: host[k] for k in ("latents", "noise", "timesteps")}, text_embeds=host["text_embeds"],
-                    pooled_embeds=host["pooled_embeds"])
+    step._load_dict(host)
     torch.cuda.synchronize()
 
     def barrier():
@@ -387,6 +479,8 @@ def run_b200(args):
     roof = None
     if rank == 0:
         M_, N_, K_ = (4608 if BS == 1 else 4096 * BS), 12288, 3072  # bs 4: the image stream of a double block, M = 16384
+        if WAN:
+            M_, N_, K_ = 13312 * BS, 8960, 1536  # ffn.net.0.proj of a Wan block
         x = (torch.randn(M_, K_, device=dev) * 0.5).bfloat16()
         w = (torch.randn(N_, K_, device=dev) * 0.02).bfloat16()
         zc = (torch.randn(M_, 64, device=dev) * 0.1).bfloat16()
@@ -413,7 +507,7 @@ def run_b200(args):
         kms = sum(tt) / len(tt)
         fl = 2.0 * M_ * N_ * K_ + 2.0 * M_ * R * N_  # base GEMM + rank-r up-projection riding in the same tile
         ach = fl / kms / 1e9
-        prof = profile_numbers() if (BS == 1 and R == 16) else {"traffic": None, "source": None}
+        prof = profile_numbers() if (BS == 1 and R == 16 and not WAN) else {"traffic": None, "source": None}
         roof = {"bound": "tensor",
                 "kernel": f"gemm_bf16_kernel<2,256,6,0,0> fused LoRA-Linear + bias + GELU(+pre-activation) M={M_} N={N_} K={K_} r={R}",
                 "achieved": ach, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": ach / peaks["bf16_tflops"],
@@ -425,15 +519,19 @@ def run_b200(args):
                 "tensor_pipe_active_pct_ncu": prof.get("tensor_pipe_active_pct_ncu"), "us_per_launch": kms * 1e3}
     if rank != 0:
         return
-    f_step, f_lin, f_attn, f_lora = flux_flops(BS, R, n_double=cfg.num_layers, n_single=cfg.num_single_layers)
+    if WAN:
+        f_step, f_lin, f_attn, f_lora = wan_flops(BS, R, layers=cfg.num_layers)
+    else:
+        f_step, f_lin, f_attn, f_lora = flux_flops(BS, R, n_double=cfg.num_layers, n_single=cfg.num_single_layers)
     value = world * 1e3 / ms
     out = {
-        "metric": METRIC if (BS == 1 and R == 16) else f"train-steps/sec FLUX.1-dev LoRA r={R} bs={BS} 1024^2", "value": value, "unit": "steps/s", "n_gpus": world,
+        "metric": (f"train-steps/sec Wan2.1-T2V-1.3B LoRA r={R} bs={BS} 49x512x512" if WAN else
+                   METRIC if (BS == 1 and R == 16) else f"train-steps/sec FLUX.1-dev LoRA r={R} bs={BS} 1024^2"), "value": value, "unit": "steps/s", "n_gpus": world,
         "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "config": {"workload": workload_name(args), "global_batch": world * BS, "img_per_s": world * BS * 1e3 / ms,
-                   "tokens": 4608 * BS, "rank": R, "lora_modules": len(net.get_all_modules()), "lora_params": int(net.n_params),
-                   "blocks": [cfg.num_layers, cfg.num_single_layers], "parallelism": f"dp{world}", "ema": True,
+                   "tokens": (13312 + 512 if WAN else 4608) * BS, "rank": R, "lora_modules": len(net.get_all_modules()), "lora_params": int(net.n_params),
+                   "blocks": [cfg.num_layers] if WAN else [cfg.num_layers, cfg.num_single_layers], "parallelism": f"dp{world}", "ema": True,
                    "cuda_graph": not args.no_graph,
                    "l2": "per-step working set (23.8 GB weights + activations) >> 126 MB L2; no explicit flush"},
         "impl": "b200",
@@ -449,12 +547,24 @@ def run_b200(args):
         "loss_last": last["loss"] if last else None,
         "setup_s": setup_s,
     }
-    if not args.skip_cpu_baseline and world == 1:  # rank 0 at N = 1 only (a bounded CPU sample of the same workload)
+    if not args.skip_cpu_baseline and world == 1 and not WAN:  # rank 0 at N = 1 only (a bounded CPU sample of the same workload)
         sec, times, f_sample, desc, threads = cpu_reference_sample(steps=3, warmup=1, rank=R)
         v = 1.0 / (sec * f_step / f_sample)
         out["cpu_baseline"] = {"value": v, "unit": "steps/s", "cores": threads, "kind": "port", "sample": desc,
                                "step_seconds": times}
-    if not args.skip_gpu_reference and world == 1 and not args.layers:
+    if not args.skip_gpu_reference and world == 1 and not args.layers and WAN:
+        del step, opt, net, model
+        import gc
+
+        gc.collect()
+        torch.cuda.empty_cache()
+        torch.cuda.reset_peak_memory_stats()
+        ref = gpu_reference_leg_wan(dev, rank=R, batch=BS)
+        for k in ("checkpointing", "no_checkpointing"):
+            if "ms_per_step" in ref.get(k, {}):
+                ref[k]["speedup_of_this_repo"] = ref[k]["ms_per_step"] / ms
+        out["gpu_reference"] = ref
+    elif not args.skip_gpu_reference and world == 1 and not args.layers:
         # free this arm's model / activations first: the eager reference needs its own 24 GB of weights + autograd state
         del step, opt, net, model
         import gc
@@ -482,6 +592,8 @@ def main():
     ap.add_argument("--skip-cpu-baseline", action="store_true")
     ap.add_argument("--skip-gpu-reference", action="store_true",
                     help="do not time the eager reference-style PyTorch step on the same GPU after the main measurement")
+    ap.add_argument("--model", default="flux", choices=["flux", "wan"],
+                    help="flux = BASELINE.json configs[2] (the headline metric); wan = configs[3] (Wan2.1-T2V-1.3B, 49x512x512)")
     ap.add_argument("--batch", type=int, default=1, help="samples per GPU (BASELINE.json configs[4] uses 4)")
     ap.add_argument("--rank", type=int, default=RANK, help="LoRA rank (configs[4] sweeps 4, 8, 16, 32, 64)")
     ap.add_argument("--layers", type=int, nargs=2, default=None, help="debug: override (double, single) block counts")
