@@ -68,9 +68,10 @@ __global__ void __launch_bounds__(256) train_loss_kernel(const bf16* __restrict_
     const int c = static_cast<int>(rem / (static_cast<long long>(H) * W));
     const int h = static_cast<int>((rem / W) % H);
     const int w = static_cast<int>(rem % W);
+    const size_t o = (pack & 1) ? packed_index2(b, c, h, w, C, H, W) : static_cast<size_t>(i);
     float t0, t1;
-    if (target) {
-      const float2 tg = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(target + i));
+    if (target) {  // pack & 2: the target lies in the prediction's (packed) layout, e.g. a prior prediction of the same model
+      const float2 tg = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(target + ((pack & 2) ? o : static_cast<size_t>(i))));
       t0 = tg.x;
       t1 = tg.y;
     } else {
@@ -81,7 +82,6 @@ __global__ void __launch_bounds__(256) train_loss_kernel(const bf16* __restrict_
       t0 = bf16_round(bf16_round(cn * n.x) - bf16_round(cl * a.x));
       t1 = bf16_round(bf16_round(cn * n.y) - bf16_round(cl * a.y));
     }
-    const size_t o = pack ? packed_index2(b, c, h, w, C, H, W) : static_cast<size_t>(i);
     const float2 p = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(pred + o));
     float m0 = 1.0f, m1 = 1.0f;
     if (mask) {
@@ -240,7 +240,7 @@ extern "C" int b200_train_loss(b200_ctx* ctx, const void* pred, const void* late
   if (rc) return rc;
   B200_REQUIRE(pred && loss_per_sample && loss_total && B > 0 && C > 0 && H > 0 && W > 0, "b200_train_loss: bad args");
   B200_REQUIRE(target || (latents && noise), "b200_train_loss: needs a target tensor or latents + noise");
-  B200_REQUIRE(W % 2 == 0 && (!pack || H % 2 == 0), "b200_train_loss: H/W must be even");
+  B200_REQUIRE(W % 2 == 0 && (!(pack & 1) || H % 2 == 0), "b200_train_loss: H/W must be even");
   B200_REQUIRE(!mask || mask_channels == 1 || mask_channels == C, "b200_train_loss: mask channels %d (1 or %d)", mask_channels, C);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   B200_CUDA_CHECK(cudaMemsetAsync(loss_per_sample, 0, sizeof(float) * B, st));

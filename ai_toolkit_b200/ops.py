@@ -160,7 +160,7 @@ def flow_loss(pred, latents, noise, pack=True, gscale=1.0, dpred=None, want_grad
 
 
 def train_loss(pred, latents, noise, *, target=None, coef_noise=None, coef_latent=None, sample_weight=None, mask=None,
-               pack=False, gscale=1.0, dpred=None, want_grad=True, loss_ws=None):
+               pack=False, gscale=1.0, dpred=None, want_grad=True, loss_ws=None, target_in_pred_layout=False):
     """The default 'mse' path of `SDTrainer.calculate_loss` (SDTrainer.py:522-1052) in one launch; see include/b200_lora.h.
     latents gives the geometry [B, C, H, W] (5-D video latents [B, C, T, H, W] are folded to [B, C, T*H, W]);
     -> (loss_total [1] fp32, loss_per_sample [B] fp32, dpred like pred)."""
@@ -180,7 +180,7 @@ def train_loss(pred, latents, noise, *, target=None, coef_noise=None, coef_laten
         mc = int(mask.shape[1])
     cabi.call("b200_train_loss", _p(pred), _p(latents), _p(noise), _p(target), _p(coef_noise), _p(coef_latent),
               _p(sample_weight), _p(mask), mc, _p(dpred if want_grad else None), _p(per), _p(tot), int(B), int(C), int(H),
-              int(W), int(pack), float(gscale), device=_dev(pred))
+              int(W), int(bool(pack)) | (2 if target_in_pred_layout else 0), float(gscale), device=_dev(pred))
     return tot, per, dpred
 
 

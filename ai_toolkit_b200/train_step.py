@@ -35,7 +35,7 @@ class FluxLoRATrainStep:
                  guidance_scale=1.0, loss_multiplier=1.0, use_cuda_graph=True, process_group=None,
                  timestep_type="sigmoid", num_train_timesteps=1000, min_denoising_steps=0, max_denoising_steps=999,
                  linear_timesteps=False, linear_timesteps2=False, noise_multiplier=1.0, latent_multiplier=1.0,
-                 use_loss_options=False):
+                 use_loss_options=False, prior_target=False):
         self.model, self.network, self.optimizer = model, network, optimizer
         dev = model.device
         self.dev = dev
@@ -70,6 +70,9 @@ class FluxLoRATrainStep:
         self.sample_weight = torch.ones(B, device=dev, dtype=torch.float32) if self.use_loss_options else None
         self.mask = None
         self._table = None
+        # prior prediction as the target (SDTrainer.get_prior_prediction :1211-1339 -> calculate_loss `target = prior_pred`
+        # :619-621): the frozen model's own prediction on the same noisy latents (network inactive, no gradient)
+        self.prior_target = bool(prior_target)
         self.loss_ws = torch.zeros(B + 1, device=dev, dtype=torch.float32)
         self.loss_host = torch.zeros(1, dtype=torch.float32)
         if torch.device(dev).type == "cuda":
@@ -105,12 +108,21 @@ class FluxLoRATrainStep:
         packed = ops.flow_add_noise(self.latents, self.noise, self.timesteps, pack=True)
         # the trainer passes timestep / 1000 (stable_diffusion_model.py:2196) and the bf16 model re-scales by 1000 in
         # bf16: both happen inside the timestep-embedding kernel (t_div=1000)
+        prior = None
+        if self.prior_target:
+            net.is_active = False  # get_prior_prediction: `self.network.is_active = False`, torch.no_grad()
+            prior = self.model.engine.forward(packed, self.timesteps, self.text, self.pooled, self.guidance, self.txt_ids,
+                                              self.img_ids, save=False, t_div=1000.0)
         net.is_active = True  # `with network:` (SDTrainer.py:2229-2238 keeps it active through backward)
         try:
             eng = self.model.engine
             pred = eng.forward(packed, self.timesteps, self.text, self.pooled, self.guidance, self.txt_ids, self.img_ids,
                                save=True, t_div=1000.0)
-            if self.use_loss_options or self.mask is not None:
+            if prior is not None:
+                _, _, dpred = ops.train_loss(pred.view(self.B, -1, pred.shape[-1]), self.latents, self.noise, target=prior,
+                                             target_in_pred_layout=True, sample_weight=self.sample_weight, mask=self.mask,
+                                             pack=True, gscale=self.loss_multiplier, loss_ws=self.loss_ws)
+            elif self.use_loss_options or self.mask is not None:
                 _, _, dpred = ops.train_loss(pred.view(self.B, -1, pred.shape[-1]), self.latents, self.noise,
                                              sample_weight=self.sample_weight, mask=self.mask, pack=True,
                                              gscale=self.loss_multiplier, loss_ws=self.loss_ws)

@@ -249,7 +249,8 @@ int b200_flow_loss(b200_ctx* ctx, const void* pred, const void* latents, const v
  *   loss_per_sample[b] = sample_weight[b] * mean((pred - target)^2 * mask[b, (c), h, w])      (:916, :923-959, :987-1011;
  *     timestep weights, loss_multiplier and SNR-gamma weights are per-sample scalars: the caller multiplies them into
  *     sample_weight, fp32 [B] or NULL; mask fp32 [B, mask_channels in {1, C}, H, W] or NULL)
- *   loss_total = mean_b (:1013); dpred = bf16(d loss_total / d pred * gscale) in pred's layout (pack as b200_flow_loss).
+ *   loss_total = mean_b (:1013); dpred = bf16(d loss_total / d pred * gscale) in pred's layout (pack bit 0 as
+ *   b200_flow_loss; pack bit 1: `target` lies in pred's layout -- a prior prediction of the same model, :1211-1339).
  */
 int b200_ddpm_add_noise(b200_ctx* ctx, const void* latents, const void* noise, const void* timesteps_i64,
                         const void* alphas_cumprod_f32, int n_train, void* out, int B, int64_t per_sample, void* stream);

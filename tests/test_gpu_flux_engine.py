@@ -479,3 +479,34 @@ def test_two_ranks_nccl_equal_accumulation_over_two_samples(tmp_path):
     assert max(abs(a - b) / abs(b) for a, b in zip(mean_ddp, losses)) < 1e-4
     assert _rel(r0["params"].to(DEV), net.flat_params) < 1e-4  # fp32 atomics in the wgrad: not bit-identical
     assert abs(r0["norm"] - float(opt.grad_norm)) < 1e-3 * float(opt.grad_norm)
+
+
+def test_prior_prediction_as_target():
+    """`get_prior_prediction` (SDTrainer.py:1211-1339): the frozen model's prediction (network inactive, no grad) is the loss
+    target (`calculate_loss`: `target = prior_pred`, :619-621).  The inactive engine must equal the oracle's frozen model, and
+    the step's loss must equal mse(active prediction, prior prediction) with LoRA gradients flowing."""
+    from oracle import flux_ref, lora_ref
+    from ai_toolkit_b200 import ops
+    from ai_toolkit_b200.optimizer import B200AdamW
+    from ai_toolkit_b200.train_step import FluxLoRATrainStep, make_img_ids
+    B, hl, wl, Lt = 2, 16, 16, 24
+    model, net, onets, batch = _setup(1, 1, 2, B, hl, wl, Lt, 8, seed=31, precisions=("bf16",))
+    lat, noise, t, text, pooled = batch
+    om, on = onets["bf16"]
+    opt = B200AdamW(net, lr=0.0, weight_decay=0.0, max_grad_norm=0.0)
+    step = FluxLoRATrainStep(model, net, opt, batch_size=B, latent_shape=(16, hl, wl), text_len=Lt, use_cuda_graph=False,
+                             prior_target=True)
+    out = step.hook_train_loop(dict(latents=lat, noise=noise, timesteps=t, text_embeds=text, pooled_embeds=pooled))
+    packed = ops.flow_add_noise(lat, noise, t, pack=True)
+    args = (packed, t, text, pooled, torch.ones(B, device=DEV), torch.zeros(Lt, 3, device=DEV), make_img_ids(hl, wl, DEV))
+    with torch.no_grad():
+        prior = model.engine.forward(*args, save=False, t_div=1000.0)  # network inactive
+        with net:
+            active = model.engine.forward(*args, save=False, t_div=1000.0)
+        noisy = lora_ref.add_noise_flowmatch(lat, noise, t).to(torch.bfloat16)
+        frozen = lora_ref.flux_predict(om, noisy, t, text, pooled, 1.0, flux_ref.pack_latents, flux_ref.unpack_latents,
+                                       flux_ref.make_img_ids)  # oracle network inactive = the frozen oracle model
+    assert _rel(flux_ref.unpack_latents(prior.view(B, -1, 64), hl, wl), frozen) < 1.5e-2
+    want = torch.nn.functional.mse_loss(active.float(), prior.float()).item()
+    assert want > 0 and abs(out["loss"] - want) < 1e-5 * want + 1e-9
+    assert float(net.flat_grads.abs().sum()) > 0
