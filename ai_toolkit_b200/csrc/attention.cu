@@ -919,8 +919,10 @@ extern "C" int b200_attn_fwd_x(b200_ctx* ctx, const void* Q, const void* K, cons
   // folded into the exponent FFMA) 255.3 us = 1022 TF/s; variant 4 (16 softmax warps) 256.3 us; variant 1 278.2 us;
   // variant 2 (two streams) 304 us in round 1.  Variant 5 (attention_pp.cu: two Q tiles per CTA in ping-pong, one softmax
   // thread per row) 221.6 us = 1177 TF/s vs 257.8 us for variant 3 in the same log (gpurun_out/r2_pp.log); parity and unit
-  // tests green with it.  B200_ATTN_FWD=1|2|3|4 selects the others for A/B runs.
-  static int variant = 5;
+  // tests green with it.  Variant 6 = the same kernel with the OPTIMISTIC running maximum (no row-max pass on the common path,
+  // whole-row P held in registers until the partial sum has been checked): 209.9 us = 1243 TF/s with all exponentials on MUFU
+  // vs 221.3 us for variant 5 in the same log (gpurun_out/r2_pp2.log).  B200_ATTN_FWD=1..5 selects the others for A/B runs.
+  static int variant = 6;
   if (!configured) {
     B200_CUDA_CHECK(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwdSmem));
     B200_CUDA_CHECK(cudaFuncSetAttribute(attn_fwd2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwdSmem));

@@ -626,9 +626,9 @@ static int launch_pp2(const CUtensorMap& tq, const CUtensorMap& tk, const CUtens
 int attn_fwd_pp2_launch(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnFwdArgs& a,
                         cudaStream_t stream) {
   static int poly = -1;
-  if (poly < 0) {
-    const char* e = getenv("B200_ATTN_PP_POLY");
-    poly = (e && atoi(e) >= 0 && atoi(e) <= 3) ? atoi(e) : 1;
+  if (poly < 0) {  // measured (gpurun_out/r2_pp2.log): POLY 0 209.9 us, 1 216.5 us, 2 221.5 us -- without the max pass the
+    const char* e = getenv("B200_ATTN_PP_POLY");  // softmax is issue-bound, and the polynomial costs 5x the issue slots of MUFU
+    poly = (e && atoi(e) >= 0 && atoi(e) <= 3) ? atoi(e) : 0;
   }
   switch (poly) {
     case 0: return launch_pp2<0>(tq, tk, tv, a, stream);

@@ -283,3 +283,144 @@ def test_per_sample_multipliers_through_the_fused_engine():
         pred1 = model.engine.forward(packed, t, text, pooled, torch.ones(B, device=DEV), torch.zeros(Lt, 3, device=DEV),
                                      make_img_ids(hl, wl, DEV), save=False, t_div=1000.0)
     assert _rel(pred1, pred) > 1e-3
+
+
+class Transformer2DModel(torch.nn.Module):  # kohya_lora.py:750: the Linear / 1x1-conv targets inside a UNet
+    def __init__(self, ch, ctx_dim):
+        super().__init__()
+        self.proj_in = torch.nn.Conv2d(ch, ch, 1)
+        self.to_q = torch.nn.Linear(ch, ch, bias=False)
+        self.to_k = torch.nn.Linear(ctx_dim, ch, bias=False)
+        self.to_v = torch.nn.Linear(ctx_dim, ch, bias=False)
+        self.to_out = torch.nn.Linear(ch, ch)
+        self.proj_out = torch.nn.Conv2d(ch, ch, 1)
+
+    def forward(self, x, ctx):
+        B, C, H, W = x.shape
+        h = self.proj_in(x).flatten(2).transpose(1, 2)  # [B, HW, C]
+        q, k, v = self.to_q(h), self.to_k(ctx), self.to_v(ctx)
+        a = torch.nn.functional.scaled_dot_product_attention(q.unsqueeze(1), k.unsqueeze(1), v.unsqueeze(1)).squeeze(1)
+        h = h + self.to_out(a)
+        return x + self.proj_out(h.transpose(1, 2).reshape(B, C, H, W))
+
+
+class ResnetBlock2D(torch.nn.Module):  # kohya_lora.py:751: the 3x3-conv targets
+    def __init__(self, cin, cout):
+        super().__init__()
+        self.norm1 = torch.nn.GroupNorm(8, cin)
+        self.conv1 = torch.nn.Conv2d(cin, cout, 3, padding=1)
+        self.conv_shortcut = torch.nn.Conv2d(cin, cout, 1)
+
+    def forward(self, x):
+        return self.conv_shortcut(x) + self.conv1(torch.nn.functional.silu(self.norm1(x)))
+
+
+def _toy_unet(ch=64, ctx_dim=96):
+    cls = type("UNet2DConditionModel", (torch.nn.Module,), {})
+
+    def init(self):
+        torch.nn.Module.__init__(self)
+        self.conv_in = torch.nn.Conv2d(4, ch, 3, padding=1)
+        self.res = ResnetBlock2D(ch, ch)
+        self.attn = Transformer2DModel(ch, ctx_dim)
+        self.down = ResnetBlock2D(ch, ch)
+        self.conv_out = torch.nn.Conv2d(ch, 4, 3, padding=1)
+
+    def fwd(self, x, ctx):
+        return self.conv_out(self.down(self.attn(self.res(self.conv_in(x)), ctx)))
+
+    cls.__init__, cls.forward = init, fwd
+    return cls()
+
+
+@pytest.mark.parametrize("pred_type", ["epsilon", "v_prediction"])
+def test_unet_style_eps_training_step_plumbing(pred_type):
+    """BASELINE.json configs[0] / [1] PLUMBING (not a UNet engine): a UNet-shaped toy model whose Linear, 1x1-conv and 3x3-conv
+    layers carry kohya-format adapters (lora_dim 4, conv_lora_dim 4, alpha 2 -> scale 0.5), trained for 3 steps with the
+    eps / v path of the trainer: DDPM add_noise with integer timesteps (kernel), prediction through `LoRAModule.forward`
+    (fused GEMM for every adapted layer; the frozen non-adapted layers are torch), the fused eps / v MSE with min-SNR-gamma
+    weights (kernel), clip + AdamW (kernel) -- against the same three steps in eager PyTorch with the reference formulas."""
+    import copy
+    from ai_toolkit_b200 import LoRASpecialNetwork, calc_loss, ops
+    from ai_toolkit_b200.optimizer import B200AdamW
+    from ai_toolkit_b200.samplers import DDPMTable
+    torch.manual_seed(7)
+    unet = _toy_unet().to(DEV, torch.bfloat16).requires_grad_(False)
+    ref_unet = copy.deepcopy(unet)
+    net = LoRASpecialNetwork(None, unet, lora_dim=4, alpha=2, conv_lora_dim=4, conv_alpha=2, train_text_encoder=False,
+                             target_lin_modules=["Transformer2DModel"], target_conv_modules=["ResnetBlock2D"])
+    net.force_to(DEV, torch.float32)
+    net._update_torch_multiplier()
+    net.apply_to(None, unet, False, True)
+    names = [l.lora_name for l in net.unet_loras]
+    assert "lora_unet_attn_proj_in" in names and "lora_unet_attn_to_q" in names and "lora_unet_res_conv1" in names
+    assert all(abs(l.scale - 0.5) < 1e-9 for l in net.unet_loras)
+    with torch.no_grad():
+        for l in net.unet_loras:
+            l.lora_up.weight.normal_(0, 0.05)
+    net.mark_params_changed()
+    # eager twin: explicit A / B leaves applied with the reference formula through forward hooks on the twin's layers
+    twins = []
+    for l in net.unet_loras:
+        path = l.lora_name[len("lora_unet_"):]
+        mod = ref_unet
+        for part in (path.split("_", 1) if not path.startswith("attn_") else ["attn", path[5:]]):
+            mod = getattr(mod, part)
+        A = l.lora_down.weight.detach().clone().requires_grad_(True)
+        Bw = l.lora_up.weight.detach().clone().requires_grad_(True)
+        twins.append((mod, A, Bw, l))
+
+        def hook(m, inp, out, A=A, Bw=Bw, l=l):
+            x = inp[0].float()
+            if isinstance(m, torch.nn.Conv2d):
+                lx = F.conv2d(F.conv2d(x, A, None, m.stride, m.padding), Bw)
+            else:
+                lx = F.linear(F.linear(x, A), Bw)
+            return out + (lx * l.scale).to(out.dtype)
+
+        mod.register_forward_hook(hook)
+    rparams = [p for _, A, Bw, _ in twins for p in (A, Bw)]
+    ropt = torch.optim.AdamW(rparams, lr=1e-3, eps=1e-6, weight_decay=1e-2)
+    opt = B200AdamW(net, lr=1e-3, eps=1e-6, weight_decay=1e-2, max_grad_norm=1.0)
+    tab = DDPMTable(prediction_type=pred_type, device=DEV)
+    g = torch.Generator().manual_seed(3)
+    B = 2
+    lat = (torch.randn(B, 4, 32, 32, generator=g) * 0.18215 * 5).bfloat16().to(DEV)
+    ctx = torch.randn(B, 77, 96, generator=g).bfloat16().to(DEV)
+    mine, ref = [], []
+    for it in range(3):
+        noise = torch.randn(B, 4, 32, 32, generator=g).bfloat16().to(DEV)
+        t = tab.sample_timesteps(B, generator=g).to(DEV)
+        v = calc_loss.loss_vectors(t, is_flow_matching=False, prediction_type=pred_type, ddpm_table=tab, min_snr_gamma=5.0, device=DEV)
+        # --- B200 path
+        opt.zero_grad()
+        noisy = ops.ddpm_add_noise(lat, noise, t, tab.device_table)
+        with net:
+            pred = unet(noisy, ctx)
+            tot, _, dpred = ops.train_loss(pred.contiguous(), lat, noise, pack=False, **v)
+            pred.backward(dpred)
+        opt.step()
+        mine.append(tot.item())
+        # --- eager reference
+        ropt.zero_grad(set_to_none=True)
+        rn = tab.add_noise(lat, noise, t)
+        assert torch.equal(rn, noisy)
+        rp = ref_unet(rn, ctx)
+        target = noise if pred_type == "epsilon" else tab.get_velocity(lat, noise, t)
+        loss = F.mse_loss(rp.float(), target.float(), reduction="none").mean([1, 2, 3])
+        loss = (loss * tab.snr_weights(t, 5.0).to(DEV)).mean()
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(rparams, 1.0)
+        ropt.step()
+        ref.append(loss.item())
+    assert max(abs(a - b) / abs(b) for a, b in zip(mine, ref)) < 5e-3, (mine, ref)
+    off = 0
+    for _, A, Bw, l in twins:
+        for mine_p, ref_p in ((l.lora_down.weight, A), (l.lora_up.weight, Bw)):
+            n = ref_p.numel()
+            upd_m = net.flat_params[off:off + n] - 0  # noqa: F841
+            off += n
+            assert _rel(mine_p, ref_p) < 2e-2, l.lora_name
+    sd = net.get_state_dict(dtype=torch.float16)
+    assert "lora_unet_res_conv1.lora_down.weight" in sd and sd["lora_unet_res_conv1.lora_down.weight"].shape == (4, 64, 3, 3)
+    assert "lora_unet_attn_to_q.alpha" in sd
