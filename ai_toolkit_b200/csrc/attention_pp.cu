@@ -316,7 +316,9 @@ attn_fwd_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   if (warp == 1) tmem_dealloc<512>(tmem_base);
 }
 
-template <int POLY>
+// DBG (timing experiments only, results are WRONG): 1 = no exponentials (P = the scaled score), 2 = no softmax work at all
+// (the warps only hand the barriers on): what the MMA / barrier pipeline alone costs.  B200_ATTN_PP_DBG selects it.
+template <int POLY, int DBG = 0>
 __global__ void __launch_bounds__(kPP2Threads, 1)
 attn_fwd_pp2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                    const __grid_constant__ CUtensorMap tmV, const AttnFwdArgs g) {
@@ -488,7 +490,7 @@ attn_fwd_pp2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           for (int k2 = 0; k2 < 16; ++k2) {
             const bool poly = (k2 % 4) < POLY;
             const float2 e = ffma2(make_float2(x[2 * k2], x[2 * k2 + 1]), c22, nm2);
-            const float2 p2 = poly ? ex2_poly2(e) : make_float2(ex2(e.x), ex2(e.y));
+            const float2 p2 = DBG == 1 ? e : (poly ? ex2_poly2(e) : make_float2(ex2(e.x), ex2(e.y)));
             ls[k2 & 1] = fadd2(ls[k2 & 1], p2);
             pk[c * 16 + k2] = pack_bf16x2(p2.x, p2.y);
           }
@@ -499,10 +501,15 @@ attn_fwd_pp2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       // by many orders of magnitude without losing relative precision; only when the row's partial sum shows that the scores
       // have outgrown m_used by more than ~2^30 (or on the first block) is the exact row maximum computed and O rescaled.
       float bsum = 0.f;
-      bool need = (j == 0);
+      bool need = (j == 0) && DBG != 2;
+      if (DBG == 2) {
+        tc_fence_before();
+        mbar_arrive(&p_full[t]);
+        continue;
+      }
       if (!need) {
         bsum = pass2();
-        need = !(bsum < 1.0e9f);  // also catches inf / nan
+        need = DBG == 0 && !(bsum < 1.0e9f);  // also catches inf / nan
       }
       if (__any_sync(0xffffffffu, need)) {
         float mx = -INFINITY;
@@ -607,10 +614,10 @@ static int launch_pp(const CUtensorMap& tq, const CUtensorMap& tk, const CUtenso
   return B200_OK;
 }
 
-template <int POLY>
+template <int POLY, int DBG = 0>
 static int launch_pp2(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnFwdArgs& a,
                       cudaStream_t stream) {
-  auto kern = attn_fwd_pp2_kernel<POLY>;
+  auto kern = attn_fwd_pp2_kernel<POLY, DBG>;
   static bool configured = false;
   if (!configured) {
     B200_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kPPSmem));
@@ -630,6 +637,13 @@ int attn_fwd_pp2_launch(const CUtensorMap& tq, const CUtensorMap& tk, const CUte
     const char* e = getenv("B200_ATTN_PP_POLY");  // softmax is issue-bound, and the polynomial costs 5x the issue slots of MUFU
     poly = (e && atoi(e) >= 0 && atoi(e) <= 3) ? atoi(e) : 0;
   }
+  static int dbg = -1;
+  if (dbg < 0) {
+    const char* e = getenv("B200_ATTN_PP_DBG");
+    dbg = e ? atoi(e) : 0;
+  }
+  if (dbg == 1) return launch_pp2<0, 1>(tq, tk, tv, a, stream);
+  if (dbg == 2) return launch_pp2<0, 2>(tq, tk, tv, a, stream);
   switch (poly) {
     case 0: return launch_pp2<0>(tq, tk, tv, a, stream);
     case 2: return launch_pp2<2>(tq, tk, tv, a, stream);
