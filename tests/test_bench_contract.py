@@ -16,6 +16,9 @@ def test_flop_model_matches_baseline_md():
     assert abs(f_step / 1e12 - 172.4) < 0.1 and abs(f_lin / 1e12 - 59.50) < 0.05
     assert abs(f_attn / 1e12 - 14.87) < 0.02 and abs(f_lora / 1e12 - 0.448) < 0.002
     assert abs(bench.flux_flops(4, 64)[0] / 1e12 - 705.8) < 0.3  # rank-sweep row of BASELINE.md section 3
+    w = bench.wan_flops()  # F_lin 33.44, F_attn 33.92 -> 187.1 TFLOP
+    assert abs(w[0] / 1e12 - 187.1) < 0.1 and abs(w[1] / 1e12 - 33.44) < 0.01 and abs(w[2] / 1e12 - 33.92) < 0.01
+    assert 1 <= bench.host_cores() <= (os.cpu_count() or 1)
 
 
 def test_reference_arm_prints_the_contract_line():
