@@ -927,11 +927,16 @@ extern "C" int b200_attn_fwd_x(b200_ctx* ctx, const void* Q, const void* K, cons
     B200_CUDA_CHECK(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwdSmem));
     B200_CUDA_CHECK(cudaFuncSetAttribute(attn_fwd2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwdSmem));
     const char* e = getenv("B200_ATTN_FWD");
-    if (e && atoi(e) >= 1 && atoi(e) <= 6) variant = atoi(e);
+    if (e && atoi(e) >= 1 && atoi(e) <= 7) variant = atoi(e);
     configured = true;
   }
   AttnFwdArgs a{(bf16*)o0, ld0, (bf16*)o1, ld1, (float*)lse, B, H, L, split, scale, Lk};
   B200_REQUIRE(Lk == L || variant >= 3, "b200_attn_fwd: cross attention (Lk != L) needs forward variant 3, 4 or 5");
+  if (variant == 7) {
+    if ((rc = attn_fwd_pp3_launch(tq, tk, tv, a, reinterpret_cast<cudaStream_t>(stream)))) return rc;
+    ctx->launches.fetch_add(1);
+    return B200_OK;
+  }
   if (variant == 6) {
     if ((rc = attn_fwd_pp2_launch(tq, tk, tv, a, reinterpret_cast<cudaStream_t>(stream)))) return rc;
     ctx->launches.fetch_add(1);

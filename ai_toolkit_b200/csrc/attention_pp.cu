@@ -27,6 +27,8 @@ namespace b200 {
 
 // POLY (template): of every 4 column pairs, how many use the FMA-pipe polynomial (0 = all MUFU); B200_ATTN_PP_POLY picks it
 constexpr int kPPThreads = 384;
+constexpr int kPP3Threads = 576;  // variant 7: TMA warp, MMA warp, 16 softmax warps (two threads per row)
+constexpr int kPP3Smem = 1024 + 6 * 32768 + 32 * 8 + 2 * 1024 * 4;
 constexpr int kPP2Threads = 320;  // variant 6: no idle warps (more registers per thread for the whole-row P in registers)
 constexpr int kPPSmem = 1024 + 6 * 32768 + 32 * 8;
 
@@ -599,6 +601,302 @@ attn_fwd_pp2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   if (warp == 1) tmem_dealloc<512>(tmem_base);
 }
 
+// Variant 7: the optimistic ping-pong kernel with TWO threads per row (16 softmax warps).  Diagnostics of variant 6
+// (profiles/r2_attn_diag.log): MMA / barrier pipeline alone 170 us, whole kernel 213 us -- the one-thread-per-row softmax
+// is a serial chain on ONE active warp per scheduler.  Here thread (row, h) owns columns [64 h, 64 h + 64): half the chain, two
+// warps per scheduler and tile.  The optimistic maximum removes the per-block row-max exchange; what remains per block is one
+// flag exchange through shared memory + a 64-thread named barrier per (tile, lane quarter), which also orders "both halves have
+// read S" before either half stores its P over it.
+template <int POLY>
+__global__ void __launch_bounds__(kPP3Threads, 1)
+attn_fwd_pp3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                   const __grid_constant__ CUtensorMap tmV, const AttnFwdArgs g) {
+  pdl_launch_dependents();
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_align1024_pp(smem_raw);
+  uint8_t* sQ = smem;               // [2 tiles][2 halves of 64 head-dim columns][128 rows x 128 B]
+  uint8_t* sK = sQ + 2 * 32768;     // [2 stages]
+  uint8_t* sV = sK + 2 * 32768;     // [2 stages]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + 2 * 32768);
+  uint64_t* q_full = bars;          // 1
+  uint64_t* k_full = bars + 1;      // [2]
+  uint64_t* k_empty = bars + 3;     // [2]
+  uint64_t* v_full = bars + 5;      // [2]
+  uint64_t* v_empty = bars + 7;     // [2]
+  uint64_t* s_full = bars + 9;      // [2 tiles]
+  uint64_t* p_full = bars + 11;     // [2 tiles]
+  uint64_t* pv_done = bars + 13;    // [2 tiles]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 15);
+  float* xs = reinterpret_cast<float*>(bars + 32);  // [2 parity][2 tiles][2 halves][128 rows]: "needs the exact maximum" flags
+  float* xm = xs + 1024;                            // same shape: half-row maxima (fallback path) / final row sums
+
+  const int warp = warp_id_uniform(), lane = threadIdx.x & 31;
+  const int bh = blockIdx.y;
+  const int q0 = blockIdx.x * 256;
+  const int n_kv = (g.Lk + 127) / 128;
+  const long long row_base = static_cast<long long>(bh) * g.L;   // query rows / lse
+  const long long kv_base = static_cast<long long>(bh) * g.Lk;  // key / value rows
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmV);
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      mbar_init(q_full, 1);
+      for (int s = 0; s < 2; ++s) {
+        mbar_init(&k_full[s], 1);
+        mbar_init(&k_empty[s], 1);
+        mbar_init(&v_full[s], 1);
+        mbar_init(&v_empty[s], 1);
+        mbar_init(&s_full[s], 1);
+        mbar_init(&p_full[s], 256);
+        mbar_init(&pv_done[s], 1);
+      }
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc<512>(tmem_slot);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  pdl_wait();  // everything above touched only shared / tensor memory
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_arrive_expect_tx(q_full, 65536);
+#pragma unroll
+      for (int t = 0; t < 2; ++t) {
+        const int qrow = static_cast<int>(row_base + q0 + t * 128);
+        tma_load_2d(sQ + t * 32768, &tmQ, q_full, 0, qrow);
+        tma_load_2d(sQ + t * 32768 + 16384, &tmQ, q_full, 64, qrow);
+      }
+      for (int j = 0; j < n_kv; ++j) {
+        const int s = j & 1;
+        const uint32_t ph = (j >> 1) & 1;
+        const int kvrow = static_cast<int>(kv_base + j * 128);
+        mbar_wait(&k_empty[s], ph ^ 1u, 30);
+        mbar_arrive_expect_tx(&k_full[s], 32768);
+        tma_load_2d(sK + s * 32768, &tmK, &k_full[s], 0, kvrow);
+        tma_load_2d(sK + s * 32768 + 16384, &tmK, &k_full[s], 64, kvrow);
+        mbar_wait(&v_empty[s], ph ^ 1u, 31);
+        mbar_arrive_expect_tx(&v_full[s], 32768);
+#pragma unroll
+        for (int jc = 0; jc < 2; ++jc)
+#pragma unroll
+          for (int ih = 0; ih < 2; ++ih)
+            tma_load_2d(sV + s * 32768 + (jc * 2 + ih) * 8192, &tmV, &v_full[s], jc * 64, kvrow + ih * 64);
+      }
+    }
+  } else if (warp == 1) {
+    constexpr uint32_t idS = umma_idesc_bf16(128, 128, 0, 0);
+    constexpr uint32_t idPV = umma_idesc_bf16(128, 128, 0, 1);
+    mbar_wait(q_full, 0, 32);
+    const uint64_t dQ0 = umma_desc_sw128(smem_u32(sQ), 1024, 16);
+    const uint64_t dK0 = umma_desc_sw128(smem_u32(sK), 1024, 16);
+    const uint64_t dV0 = umma_desc_sw128(smem_u32(sV), 1024, 16384);
+    auto issue_S = [&](int t, int j) {  // S_t(j) = Q_t K_j^T into columns [128 t, 128 t + 128)
+      const uint64_t dq = dQ0 + static_cast<uint64_t>(t * (32768 >> 4));
+      const uint64_t dk = dK0 + static_cast<uint64_t>((j & 1) * (32768 >> 4));
+#pragma unroll
+      for (int kk = 0; kk < 8; ++kk) {
+        const uint32_t off = (kk >> 2) * (16384 >> 4) + 2u * (kk & 3);
+        umma_bf16_ss_w(tmem_base + static_cast<uint32_t>(t) * 128u, dq + off, dk + off, idS, kk > 0 ? 1u : 0u);
+      }
+      umma_commit_w(&s_full[t]);
+    };
+    auto issue_PV = [&](int t, int j) {  // O_t += P_t(j) V_j, A = P straight from TMEM (bf16 pairs in S_t's first 64 columns)
+      const uint64_t dv = dV0 + static_cast<uint64_t>((j & 1) * (32768 >> 4));
+#pragma unroll
+      for (int kk = 0; kk < 8; ++kk) {
+        const uint32_t off = (kk >> 2) * (8192 >> 4) + (kk & 3) * (2048 >> 4);
+        umma_bf16_ts_w(tmem_base + 256u + static_cast<uint32_t>(t) * 128u, tmem_base + static_cast<uint32_t>(t) * 128u + kk * 8,
+                       dv + off, idPV, (j > 0 || kk > 0) ? 1u : 0u);
+      }
+    };
+    mbar_wait(&k_full[0], 0, 33);
+    tc_fence_after();
+    issue_S(0, 0);
+    issue_S(1, 0);
+    umma_commit_w(&k_empty[0]);
+    for (int j = 0; j < n_kv; ++j) {
+      const int s = j & 1;
+      const uint32_t ph = (j >> 1) & 1;
+      const bool more = j + 1 < n_kv;
+      mbar_wait(&v_full[s], ph, 34);
+      if (more) mbar_wait(&k_full[s ^ 1], ((j + 1) >> 1) & 1, 35);
+      // ---- tile A
+      mbar_wait(&p_full[0], j & 1, 36);
+      tc_fence_after();
+      issue_PV(0, j);
+      umma_commit_w(&pv_done[0]);
+      if (more) issue_S(0, j + 1);
+      // ---- tile B
+      mbar_wait(&p_full[1], j & 1, 37);
+      tc_fence_after();
+      issue_PV(1, j);
+      umma_commit_w(&v_empty[s]);
+      umma_commit_w(&pv_done[1]);
+      if (more) {
+        issue_S(1, j + 1);
+        umma_commit_w(&k_empty[s ^ 1]);
+      }
+    }
+  } else {
+    // ---------------------------------------------------------------- softmax / epilogue: two threads per row
+    // softmax warps sw = warp - 2 in [0, 16): tile = sw >> 3; half h = (sw & 7) >> 2; TMEM lane quarter = warp & 3
+    const int sw = warp - 2;
+    const int t = sw >> 3;
+    const int h = (sw & 7) >> 2;
+    const int q = warp & 3;
+    const int r = q * 32 + lane;
+    const int qi = q0 + t * 128 + r;
+    const int bar_id = 1 + t * 4 + q;  // named barrier of the two warps that share these 32 rows
+    const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
+    const uint32_t tS = tmem_base + static_cast<uint32_t>(t) * 128u + lane_off;
+    const uint32_t tO = tmem_base + 256u + static_cast<uint32_t>(t) * 128u + lane_off;
+    const float c2 = g.scale * kLog2e;
+    const float2 c22 = make_float2(c2, c2);
+    const int tail = g.Lk & 127;
+    float m_used = -INFINITY, l_sum = 0.f;
+    for (int j = 0; j < n_kv; ++j) {
+      mbar_wait(&s_full[t], j & 1, 38);
+      tc_fence_after();
+      const bool ragged = (tail != 0) && (j == n_kv - 1);
+      const int par = j & 1;
+      float* my_xs = xs + ((par * 2 + t) * 2 + h) * 128 + r;
+      const float* his_xs = xs + ((par * 2 + t) * 2 + (h ^ 1)) * 128 + r;
+      float* my_xm = xm + ((par * 2 + t) * 2 + h) * 128 + r;
+      const float* his_xm = xm + ((par * 2 + t) * 2 + (h ^ 1)) * 128 + r;
+      uint32_t a[32], b[32], pk[32];
+      // my 64 columns of P into registers + their partial sum; S stays intact in TMEM
+      auto pass2 = [&]() -> float {
+        const float2 nm2 = make_float2(-m_used, -m_used);
+        float2 ls[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
+        tmem_ld_32x32(tS + h * 64, a);
+        tmem_ld_32x32(tS + h * 64 + 32, b);
+        tmem_ld_wait();
+        if (ragged) {
+          mask32(a, tail - h * 64);
+          mask32(b, tail - h * 64 - 32);
+        }
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          const float* x = reinterpret_cast<const float*>(c ? b : a);
+#pragma unroll
+          for (int k2 = 0; k2 < 16; ++k2) {
+            const bool poly = (k2 % 4) < POLY;
+            const float2 e = ffma2(make_float2(x[2 * k2], x[2 * k2 + 1]), c22, nm2);
+            const float2 p2 = poly ? ex2_poly2(e) : make_float2(ex2(e.x), ex2(e.y));
+            ls[k2 & 1] = fadd2(ls[k2 & 1], p2);
+            pk[c * 16 + k2] = pack_bf16x2(p2.x, p2.y);
+          }
+        }
+        return (ls[0].x + ls[0].y) + (ls[1].x + ls[1].y);
+      };
+      float bsum = 0.f;
+      bool need = (j == 0);
+      if (!need) {
+        bsum = pass2();
+        need = !(bsum < 1.0e9f);  // also catches inf / nan
+      }
+      *my_xs = need ? 1.0f : 0.0f;
+      asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");  // both halves have READ their S columns and published their flag
+      need = need || (*his_xs != 0.0f);                           // row-level decision: identical in both threads of the row
+      if (__any_sync(0xffffffffu, need)) {                        // same 32 rows in both warps -> same branch in both warps
+        float mx = -INFINITY;
+        tmem_ld_32x32(tS + h * 64, a);
+        tmem_ld_32x32(tS + h * 64 + 32, b);
+        tmem_ld_wait();
+        if (ragged) {
+          mask32(a, tail - h * 64);
+          mask32(b, tail - h * 64 - 32);
+        }
+        mx = max32(a, mx);
+        mx = max32(b, mx);
+        *my_xm = mx * c2;
+        asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
+        const float m_new = fmaxf(m_used, fmaxf(mx * c2, *his_xm));
+        const bool grow = need && (m_new > m_used);
+        const float f = grow ? ex2(m_used - m_new) : 1.0f;  // first block: ex2(-inf) = 0
+        if (grow) {
+          m_used = m_new;
+          l_sum *= f;
+        }
+        if (j > 0) {  // O_t must be stable: P V_t(j-1) is the newest MMA accumulating into it
+          mbar_wait(&pv_done[t], (j - 1) & 1, 39);
+          tc_fence_after();
+#pragma unroll 1
+          for (int c = 0; c < 2; ++c) {
+            uint32_t o[32];
+            tmem_ld_32x32(tO + h * 64 + c * 32, o);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * f);
+            tmem_st_32x32(tO + h * 64 + c * 32, o);
+          }
+          tmem_st_wait();
+        }
+        bsum = pass2();
+        asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");  // the partner has re-read its S columns: P may overwrite them
+      }
+      l_sum += bsum;
+      // my 64 K-elements of P = 32-bit columns [32 h, 32 h + 32) of the S region
+      tmem_st_32x16(tS + h * 32, *reinterpret_cast<const uint32_t(*)[16]>(&pk[0]));
+      tmem_st_32x16(tS + h * 32 + 16, *reinterpret_cast<const uint32_t(*)[16]>(&pk[16]));
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(&p_full[t]);
+    }
+    // combine the two half-row sums (m_used is identical in both threads of a row)
+    {
+      const int par = n_kv & 1;
+      float* my_xm = xm + ((par * 2 + t) * 2 + h) * 128 + r;
+      const float* his_xm = xm + ((par * 2 + t) * 2 + (h ^ 1)) * 128 + r;
+      *my_xm = l_sum;
+      asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
+      l_sum += *his_xm;
+    }
+    mbar_wait(&pv_done[t], (n_kv - 1) & 1, 40);
+    tc_fence_after();
+    const float inv = 1.0f / l_sum;
+    const bool live = qi < g.L;
+    bf16* orow = nullptr;
+    if (live) {
+      const int bb = bh / g.H, hh = bh % g.H;
+      if (qi < g.split)
+        orow = g.o0 + (static_cast<size_t>(bb) * g.split + qi) * g.ld0 + hh * 128 + h * 64;
+      else
+        orow = g.o1 + (static_cast<size_t>(bb) * (g.L - g.split) + (qi - g.split)) * g.ld1 + hh * 128 + h * 64;
+      if (h == 0) g.lse[row_base + qi] = (m_used + log2f(l_sum)) * kLn2;
+    }
+#pragma unroll 1
+    for (int c = 0; c < 2; ++c) {  // tcgen05.ld is warp-collective: every lane loads, only live rows store
+      uint32_t o[32];
+      tmem_ld_32x32(tO + h * 64 + c * 32, o);
+      tmem_ld_wait();
+      if (live) {
+#pragma unroll
+        for (int k8 = 0; k8 < 4; ++k8) {
+          uint4 u;
+          u.x = pack_bf16x2(__uint_as_float(o[k8 * 8 + 0]) * inv, __uint_as_float(o[k8 * 8 + 1]) * inv);
+          u.y = pack_bf16x2(__uint_as_float(o[k8 * 8 + 2]) * inv, __uint_as_float(o[k8 * 8 + 3]) * inv);
+          u.z = pack_bf16x2(__uint_as_float(o[k8 * 8 + 4]) * inv, __uint_as_float(o[k8 * 8 + 5]) * inv);
+          u.w = pack_bf16x2(__uint_as_float(o[k8 * 8 + 6]) * inv, __uint_as_float(o[k8 * 8 + 7]) * inv);
+          *reinterpret_cast<uint4*>(orow + c * 32 + k8 * 8) = u;
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (warp == 1) tmem_dealloc<512>(tmem_base);
+}
+
 template <int POLY>
 static int launch_pp(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnFwdArgs& a,
                      cudaStream_t stream) {
@@ -627,6 +925,36 @@ static int launch_pp2(const CUtensorMap& tq, const CUtensorMap& tk, const CUtens
   B200_KLAUNCH(kern, grid, kPP2Threads, kPPSmem, stream, tq, tk, tv, a);
   B200_CUDA_CHECK(cudaGetLastError());
   return B200_OK;
+}
+
+template <int POLY>
+static int launch_pp3(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnFwdArgs& a,
+                      cudaStream_t stream) {
+  auto kern = attn_fwd_pp3_kernel<POLY>;
+  static bool configured = false;
+  if (!configured) {
+    B200_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kPP3Smem));
+    configured = true;
+  }
+  dim3 grid((a.L + 255) / 256, a.B * a.H);
+  B200_KLAUNCH(kern, grid, kPP3Threads, kPP3Smem, stream, tq, tk, tv, a);
+  B200_CUDA_CHECK(cudaGetLastError());
+  return B200_OK;
+}
+
+// variant 7: optimistic ping-pong, two threads per row
+int attn_fwd_pp3_launch(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnFwdArgs& a,
+                        cudaStream_t stream) {
+  static int poly = -1;
+  if (poly < 0) {
+    const char* e = getenv("B200_ATTN_PP_POLY");
+    poly = (e && atoi(e) >= 0 && atoi(e) <= 3) ? atoi(e) : 0;
+  }
+  switch (poly) {
+    case 1: return launch_pp3<1>(tq, tk, tv, a, stream);
+    case 2: return launch_pp3<2>(tq, tk, tv, a, stream);
+    default: return launch_pp3<0>(tq, tk, tv, a, stream);
+  }
 }
 
 // variant 6: the ping-pong kernel with the OPTIMISTIC running maximum (no row-max pass on the common path)

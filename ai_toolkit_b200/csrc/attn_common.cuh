@@ -134,6 +134,8 @@ int attn_fwd_r2_launch(int variant, const CUtensorMap& tq, const CUtensorMap& tk
 // variant 5: two Q tiles per CTA in ping-pong (attention_pp.cu)
 int attn_fwd_pp_launch(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnFwdArgs& a,
                        cudaStream_t stream);
+int attn_fwd_pp3_launch(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnFwdArgs& a,
+                        cudaStream_t stream);
 int attn_fwd_pp2_launch(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnFwdArgs& a,
                         cudaStream_t stream);
 int attn_bwd_r2_launch(int variant, const CUtensorMap& k128, const CUtensorMap& v128, const CUtensorMap& q64,

@@ -128,3 +128,29 @@ def test_cross_attention_fwd_bwd(B, H, Lq, Lk):
     for name, g, r in (("dQ", dQ, dq_ref), ("dK", dK, dk_ref), ("dV", dV, dv_ref)):
         assert not torch.isnan(g.float()).any(), name
         assert _rel(g, r) < 1.5e-2, (name, _rel(g, r))
+
+
+@pytest.mark.parametrize("L,Lk", [(640, 640), (300, 900)])
+def test_attention_scores_growing_along_the_sequence(L, Lk):
+    """The default forward keeps an OPTIMISTIC running maximum (the exact row maximum is only computed on the first block or
+    when a row's partial sum exceeds 1e9).  Scores that grow by hundreds of log2 units from one KV block to the next force that
+    fallback on every block, and rows whose large scores come FIRST exercise the opposite case (tiny later terms)."""
+    from ai_toolkit_b200 import attention
+    torch.manual_seed(5)
+    B, H = 1, 2
+    Q = (torch.randn(B, H, L, 128, device=DEV) * 3.0).bfloat16()
+    K = torch.randn(B, H, Lk, 128, device=DEV)
+    ramp = torch.linspace(0.2, 12.0, Lk, device=DEV).view(1, 1, Lk, 1)
+    K[:, 0] = K[:, 0] * ramp[:, 0]            # head 0: scores grow along the keys
+    K[:, 1] = K[:, 1] * ramp.flip(2)[:, 0]    # head 1: the largest scores come first
+    K = K.bfloat16()
+    V = torch.randn(B, H, Lk, 128, device=DEV).bfloat16()
+    o1 = torch.full((B * L, H * 128), float("nan"), device=DEV, dtype=torch.bfloat16)
+    lse = attention.fwd(Q, K, V, None, o1, 0)
+    q, k, v = Q.float(), K.float(), V.float()
+    s = (q @ k.transpose(-1, -2)) / math.sqrt(128)
+    assert float(s.max()) > 200  # far beyond what exp2 could hold without the running maximum
+    o_ref = (torch.softmax(s, -1) @ v).transpose(1, 2).reshape(B, L, H * 128)
+    assert torch.isfinite(o1.float()).all() and torch.isfinite(lse).all()
+    assert _rel(o1.view(B, L, -1), o_ref) < 1e-2
+    assert (lse - torch.logsumexp(s, -1)).abs().max().item() < 5e-2
