@@ -1009,8 +1009,13 @@ extern "C" int b200_attn_bwd_x(b200_ctx* ctx, const void* Q, const void* K, cons
   }
   dim3 grid((L + 127) / 128, B * H);
   // dK/dV pass: keys / values stationary (length Lk), queries streamed (L); dQ pass: the other way round
-  AttnBwdArgs akv{(const float*)lse, (const float*)delta, nullptr, nullptr, (bf16*)dV, (bf16*)dK, Lk, scale, L};
-  AttnBwdArgs aq{(const float*)lse, (const float*)delta, (const bf16*)Q, (const bf16*)dOh, (bf16*)dQ, nullptr, L, scale, Lk};
+  static int bwd_dbg = -1;
+  if (bwd_dbg < 0) {
+    const char* e = getenv("B200_ATTN_BWD_DBG");
+    bwd_dbg = e ? atoi(e) : 0;
+  }
+  AttnBwdArgs akv{(const float*)lse, (const float*)delta, nullptr, nullptr, (bf16*)dV, (bf16*)dK, Lk, scale, L, bwd_dbg};
+  AttnBwdArgs aq{(const float*)lse, (const float*)delta, (const bf16*)Q, (const bf16*)dOh, (bf16*)dQ, nullptr, L, scale, Lk, bwd_dbg};
   B200_REQUIRE(Lk == L || variant == 2 || variant == 3, "b200_attn_bwd: cross attention (Lk != L) needs backward variant 2 or 3");
   if (variant >= 2) {
     if ((rc = attn_bwd_r2_launch(variant, k128, v128, q64, d64, q128, d128, k64, v64, akv, aq, B, H, st))) return rc;

@@ -562,6 +562,11 @@ attn_bwd_r2_kernel(const __grid_constant__ CUtensorMap tmR0, const __grid_consta
       }
       mbar_wait(&x_full[gq], xph, 25000 + i + 100000 * MODE_KV);
       tc_fence_after();
+      if (g.dbg == 2) {  // timing experiment: the MMA / barrier pipeline without any softmax work
+        tc_fence_before();
+        mbar_arrive(&pb_full[gq]);
+        continue;
+      }
       const int nvalid = g.Lt - (i * 64 + hh * CW);  // columns of my part that exist (<= 0: none)
       uint32_t pp[CW / 2], dd[CW / 2];             // packed bf16 pairs of my columns: P and dS
       uint32_t sv[2][16], dv[2][16];               // two chunks in flight (ping-pong)

@@ -110,6 +110,7 @@ struct AttnBwdArgs {
   int L;   // length of the STATIONARY side (MODE_KV: keys / values; MODE_Q: queries)
   float scale;
   int Lt;  // length of the STREAMED side (MODE_KV: queries; MODE_Q: keys / values); == L for self / joint attention
+  int dbg; // timing experiments only (B200_ATTN_BWD_DBG=2): skip the softmax work, hand the barriers on (results are wrong)
 };
 
 

@@ -149,7 +149,7 @@ def test_attention_scores_growing_along_the_sequence(L, Lk):
     lse = attention.fwd(Q, K, V, None, o1, 0)
     q, k, v = Q.float(), K.float(), V.float()
     s = (q @ k.transpose(-1, -2)) / math.sqrt(128)
-    assert float(s.max()) > 200  # far beyond what exp2 could hold without the running maximum
+    assert float(s.max()) > 100  # natural-log units: far beyond what exp2 could hold without the running maximum
     o_ref = (torch.softmax(s, -1) @ v).transpose(1, 2).reshape(B, L, H * 128)
     assert torch.isfinite(o1.float()).all() and torch.isfinite(lse).all()
     assert _rel(o1.view(B, L, -1), o_ref) < 1e-2
