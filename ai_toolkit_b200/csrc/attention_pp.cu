@@ -148,20 +148,20 @@ attn_fwd_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     auto issue_S = [&](int t, int j) {  // S_t(j) = Q_t K_j^T into columns [128 t, 128 t + 128)
       const uint64_t dq = dQ0 + static_cast<uint64_t>(t * (32768 >> 4));
       const uint64_t dk = dK0 + static_cast<uint64_t>((j & 1) * (32768 >> 4));
-#pragma unroll
-      for (int kk = 0; kk < 8; ++kk) {
-        const uint32_t off = (kk >> 2) * (16384 >> 4) + 2u * (kk & 3);
-        umma_bf16_ss_w(tmem_base + static_cast<uint32_t>(t) * 128u, dq + off, dk + off, idS, kk > 0 ? 1u : 0u);
+      {  // one elect for the 8 k-steps (attn_common.cuh): both operands K-major, halves of 64 head-dim columns 16 KB apart
+        constexpr int HH = 16384 >> 4;
+        umma_bf16_ss_w_x8<2, 4, 6, HH, HH + 2, HH + 4, HH + 6, 2, 4, 6, HH, HH + 2, HH + 4, HH + 6>(
+            tmem_base + static_cast<uint32_t>(t) * 128u, dq, dk, idS, 0u);
       }
       umma_commit_w(&s_full[t]);
     };
     auto issue_PV = [&](int t, int j) {  // O_t += P_t(j) V_j, A = P straight from TMEM (bf16 pairs in S_t's first 64 columns)
       const uint64_t dv = dV0 + static_cast<uint64_t>((j & 1) * (32768 >> 4));
-#pragma unroll
-      for (int kk = 0; kk < 8; ++kk) {
-        const uint32_t off = (kk >> 2) * (8192 >> 4) + (kk & 3) * (2048 >> 4);
-        umma_bf16_ts_w(tmem_base + 256u + static_cast<uint32_t>(t) * 128u, tmem_base + static_cast<uint32_t>(t) * 128u + kk * 8,
-                       dv + off, idPV, (j > 0 || kk > 0) ? 1u : 0u);
+      {  // V MN-major: k-steps 2 KB apart inside a 64-row half, halves 8 KB apart
+        constexpr int VS = 2048 >> 4, VH = 8192 >> 4;
+        umma_bf16_ts_w_x8<8, 16, 24, 32, 40, 48, 56, VS, 2 * VS, 3 * VS, VH, VH + VS, VH + 2 * VS, VH + 3 * VS>(
+            tmem_base + 256u + static_cast<uint32_t>(t) * 128u, tmem_base + static_cast<uint32_t>(t) * 128u, dv, idPV,
+            j > 0 ? 1u : 0u);
       }
     };
     mbar_wait(&k_full[0], 0, 33);
@@ -412,20 +412,20 @@ attn_fwd_pp2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     auto issue_S = [&](int t, int j) {  // S_t(j) = Q_t K_j^T into columns [128 t, 128 t + 128)
       const uint64_t dq = dQ0 + static_cast<uint64_t>(t * (32768 >> 4));
       const uint64_t dk = dK0 + static_cast<uint64_t>((j & 1) * (32768 >> 4));
-#pragma unroll
-      for (int kk = 0; kk < 8; ++kk) {
-        const uint32_t off = (kk >> 2) * (16384 >> 4) + 2u * (kk & 3);
-        umma_bf16_ss_w(tmem_base + static_cast<uint32_t>(t) * 128u, dq + off, dk + off, idS, kk > 0 ? 1u : 0u);
+      {  // one elect for the 8 k-steps (attn_common.cuh): both operands K-major, halves of 64 head-dim columns 16 KB apart
+        constexpr int HH = 16384 >> 4;
+        umma_bf16_ss_w_x8<2, 4, 6, HH, HH + 2, HH + 4, HH + 6, 2, 4, 6, HH, HH + 2, HH + 4, HH + 6>(
+            tmem_base + static_cast<uint32_t>(t) * 128u, dq, dk, idS, 0u);
       }
       umma_commit_w(&s_full[t]);
     };
     auto issue_PV = [&](int t, int j) {  // O_t += P_t(j) V_j, A = P straight from TMEM (bf16 pairs in S_t's first 64 columns)
       const uint64_t dv = dV0 + static_cast<uint64_t>((j & 1) * (32768 >> 4));
-#pragma unroll
-      for (int kk = 0; kk < 8; ++kk) {
-        const uint32_t off = (kk >> 2) * (8192 >> 4) + (kk & 3) * (2048 >> 4);
-        umma_bf16_ts_w(tmem_base + 256u + static_cast<uint32_t>(t) * 128u, tmem_base + static_cast<uint32_t>(t) * 128u + kk * 8,
-                       dv + off, idPV, (j > 0 || kk > 0) ? 1u : 0u);
+      {  // V MN-major: k-steps 2 KB apart inside a 64-row half, halves 8 KB apart
+        constexpr int VS = 2048 >> 4, VH = 8192 >> 4;
+        umma_bf16_ts_w_x8<8, 16, 24, 32, 40, 48, 56, VS, 2 * VS, 3 * VS, VH, VH + VS, VH + 2 * VS, VH + 3 * VS>(
+            tmem_base + 256u + static_cast<uint32_t>(t) * 128u, tmem_base + static_cast<uint32_t>(t) * 128u, dv, idPV,
+            j > 0 ? 1u : 0u);
       }
     };
     mbar_wait(&k_full[0], 0, 33);
@@ -701,20 +701,20 @@ attn_fwd_pp3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     auto issue_S = [&](int t, int j) {  // S_t(j) = Q_t K_j^T into columns [128 t, 128 t + 128)
       const uint64_t dq = dQ0 + static_cast<uint64_t>(t * (32768 >> 4));
       const uint64_t dk = dK0 + static_cast<uint64_t>((j & 1) * (32768 >> 4));
-#pragma unroll
-      for (int kk = 0; kk < 8; ++kk) {
-        const uint32_t off = (kk >> 2) * (16384 >> 4) + 2u * (kk & 3);
-        umma_bf16_ss_w(tmem_base + static_cast<uint32_t>(t) * 128u, dq + off, dk + off, idS, kk > 0 ? 1u : 0u);
+      {  // one elect for the 8 k-steps (attn_common.cuh): both operands K-major, halves of 64 head-dim columns 16 KB apart
+        constexpr int HH = 16384 >> 4;
+        umma_bf16_ss_w_x8<2, 4, 6, HH, HH + 2, HH + 4, HH + 6, 2, 4, 6, HH, HH + 2, HH + 4, HH + 6>(
+            tmem_base + static_cast<uint32_t>(t) * 128u, dq, dk, idS, 0u);
       }
       umma_commit_w(&s_full[t]);
     };
     auto issue_PV = [&](int t, int j) {  // O_t += P_t(j) V_j, A = P straight from TMEM (bf16 pairs in S_t's first 64 columns)
       const uint64_t dv = dV0 + static_cast<uint64_t>((j & 1) * (32768 >> 4));
-#pragma unroll
-      for (int kk = 0; kk < 8; ++kk) {
-        const uint32_t off = (kk >> 2) * (8192 >> 4) + (kk & 3) * (2048 >> 4);
-        umma_bf16_ts_w(tmem_base + 256u + static_cast<uint32_t>(t) * 128u, tmem_base + static_cast<uint32_t>(t) * 128u + kk * 8,
-                       dv + off, idPV, (j > 0 || kk > 0) ? 1u : 0u);
+      {  // V MN-major: k-steps 2 KB apart inside a 64-row half, halves 8 KB apart
+        constexpr int VS = 2048 >> 4, VH = 8192 >> 4;
+        umma_bf16_ts_w_x8<8, 16, 24, 32, 40, 48, 56, VS, 2 * VS, 3 * VS, VH, VH + VS, VH + 2 * VS, VH + 3 * VS>(
+            tmem_base + 256u + static_cast<uint32_t>(t) * 128u, tmem_base + static_cast<uint32_t>(t) * 128u, dv, idPV,
+            j > 0 ? 1u : 0u);
       }
     };
     mbar_wait(&k_full[0], 0, 33);

@@ -441,6 +441,17 @@ attn_bwd_r2_kernel(const __grid_constant__ CUtensorMap tmR0, const __grid_consta
       tc_fence_after();
       const uint64_t d0 = dTk + static_cast<uint64_t>(st * (32768 >> 4));
       const uint64_t d1 = d0 + (16384 >> 4);
+      if (g.dbg != 3) {
+        // offsets of the k-steps: A K-major [128 x 128] as two 64-column halves 16 KB apart, B [64 x 128] halves 8 KB apart
+        constexpr int AH = 16384 >> 4, BH = 8192 >> 4;
+        if (MODE_KV) {
+          umma_bf16_ss_w_x8<2, 4, 6, AH, AH + 2, AH + 4, AH + 6, 2, 4, 6, BH, BH + 2, BH + 4, BH + 6>(X0(xb), dR0, d0, idA, 0u);
+          umma_bf16_ss_w_x8<2, 4, 6, AH, AH + 2, AH + 4, AH + 6, 2, 4, 6, BH, BH + 2, BH + 4, BH + 6>(X1(xb), dR1, d1, idA, 0u);
+        } else {
+          umma_bf16_ts_w_x8<8, 16, 24, 32, 40, 48, 56, 2, 4, 6, BH, BH + 2, BH + 4, BH + 6>(X0(xb), tR0, d0, idA, 0u);
+          umma_bf16_ts_w_x8<8, 16, 24, 32, 40, 48, 56, 2, 4, 6, BH, BH + 2, BH + 4, BH + 6>(X1(xb), tR1, d1, idA, 0u);
+        }
+      } else {
 #pragma unroll
       for (int kk = 0; kk < 8; ++kk) {
         const uint32_t offa = (kk >> 2) * (16384 >> 4) + 2u * (kk & 3);
@@ -459,6 +470,7 @@ attn_bwd_r2_kernel(const __grid_constant__ CUtensorMap tmR0, const __grid_consta
         else
           umma_bf16_ts_w(X1(xb), tR1 + kk * 8, d1 + offb, idA, kk > 0 ? 1u : 0u);
       }
+      }
       umma_commit_w(&x_full[xb]);
     };
     auto issue_B = [&](int i) {
@@ -469,17 +481,28 @@ attn_bwd_r2_kernel(const __grid_constant__ CUtensorMap tmR0, const __grid_consta
       const uint64_t m1 = m0 + (16384 >> 4);                                // T1 tile
       const uint32_t acc = i > 0 ? 1u : 0u;
       const int xb = i & 1;
-      if (MODE_KV) {
-#pragma unroll
-        for (int kk = 0; kk < 4; ++kk)  // dV += P^T dO_i
-          umma_bf16_ts_w(tA0, X0(xb) + pcol(kk), m1 + kk * (2048 >> 4), idB, (kk > 0) ? 1u : acc);
-#pragma unroll
-        for (int kk = 0; kk < 4; ++kk)  // dK += dS^T Q_i
-          umma_bf16_ts_w(tA1, X1(xb) + pcol(kk), m0 + kk * (2048 >> 4), idB, (kk > 0) ? 1u : acc);
+      if (g.dbg != 3) {
+        constexpr int MS = 2048 >> 4;                       // MN-major k-steps of the streamed tile are 2 KB apart
+        constexpr int P1 = NH == 1 ? 8 : 8, P2 = NH == 1 ? 16 : 48, P3 = NH == 1 ? 24 : 56;  // pcol(kk)
+        if (MODE_KV) {
+          umma_bf16_ts_w_x4<P1, P2, P3, MS, 2 * MS, 3 * MS>(tA0, X0(xb), m1, idB, acc);  // dV += P^T dO_i
+          umma_bf16_ts_w_x4<P1, P2, P3, MS, 2 * MS, 3 * MS>(tA1, X1(xb), m0, idB, acc);  // dK += dS^T Q_i
+        } else {
+          umma_bf16_ts_w_x4<P1, P2, P3, MS, 2 * MS, 3 * MS>(tA0, X1(xb), m0, idB, acc);  // dQ += dS K_j
+        }
       } else {
-#pragma unroll
-        for (int kk = 0; kk < 4; ++kk)  // dQ += dS K_j
-          umma_bf16_ts_w(tA0, X1(xb) + pcol(kk), m0 + kk * (2048 >> 4), idB, (kk > 0) ? 1u : acc);
+        if (MODE_KV) {
+  #pragma unroll
+          for (int kk = 0; kk < 4; ++kk)  // dV += P^T dO_i
+            umma_bf16_ts_w(tA0, X0(xb) + pcol(kk), m1 + kk * (2048 >> 4), idB, (kk > 0) ? 1u : acc);
+  #pragma unroll
+          for (int kk = 0; kk < 4; ++kk)  // dK += dS^T Q_i
+            umma_bf16_ts_w(tA1, X1(xb) + pcol(kk), m0 + kk * (2048 >> 4), idB, (kk > 0) ? 1u : acc);
+        } else {
+  #pragma unroll
+          for (int kk = 0; kk < 4; ++kk)  // dQ += dS K_j
+            umma_bf16_ts_w(tA0, X1(xb) + pcol(kk), m0 + kk * (2048 >> 4), idB, (kk > 0) ? 1u : acc);
+        }
       }
       umma_commit_w(&t_empty[st]);
     };

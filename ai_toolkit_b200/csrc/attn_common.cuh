@@ -88,6 +88,86 @@ __device__ __forceinline__ float2 fadd2(float2 a, float2 b) {
   return d;
 }
 
+
+// ---- batched issue: ONE elect.sync for a whole K loop -------------------------------------------------------------------
+// The per-instruction path above costs ~13 SASS instructions (ELECT, VOTEU, 5 x R2UR ...) per tcgen05.mma; for the M 128 x
+// N 64 MMAs of the backward (32 cycles on the tensor pipe) that is as long as the MMA itself, and the diagnostics show the
+// backward bound by its MMA / barrier pipeline (750 of 795 us without any softmax work).  Here the elected lane is chosen once
+// and the n descriptors are base + compile-time offsets computed inside the asm block.
+template <int OA1, int OA2, int OA3, int OA4, int OA5, int OA6, int OA7, int OB1, int OB2, int OB3, int OB4, int OB5, int OB6, int OB7>
+__device__ __forceinline__ void umma_bf16_ss_w_x8(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                                   uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred e, p, t;\n\t.reg .b64 da, db;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "setp.eq.b32 t, %3, %3;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "add.s64 da, %1, %5;\n\tadd.s64 db, %2, %12;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, t;\n\t"
+      "add.s64 da, %1, %6;\n\tadd.s64 db, %2, %13;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, t;\n\t"
+      "add.s64 da, %1, %7;\n\tadd.s64 db, %2, %14;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, t;\n\t"
+      "add.s64 da, %1, %8;\n\tadd.s64 db, %2, %15;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, t;\n\t"
+      "add.s64 da, %1, %9;\n\tadd.s64 db, %2, %16;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, t;\n\t"
+      "add.s64 da, %1, %10;\n\tadd.s64 db, %2, %17;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, t;\n\t"
+      "add.s64 da, %1, %11;\n\tadd.s64 db, %2, %18;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, t;\n\t"
+      "}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "n"(OA1), "n"(OA2), "n"(OA3), "n"(OA4), "n"(OA5), "n"(OA6), "n"(OA7), "n"(OB1), "n"(OB2), "n"(OB3), "n"(OB4), "n"(OB5), "n"(OB6), "n"(OB7)
+      : "memory");
+}
+template <int OA1, int OA2, int OA3, int OA4, int OA5, int OA6, int OA7, int OB1, int OB2, int OB3, int OB4, int OB5, int OB6, int OB7>
+__device__ __forceinline__ void umma_bf16_ts_w_x8(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc,
+                                                   uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred e, p, t;\n\t.reg .b32 ta;\n\t.reg .b64 db;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "setp.eq.b32 t, %3, %3;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+      "add.u32 ta, %1, %5;\n\tadd.s64 db, %2, %12;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], [ta], db, %3, t;\n\t"
+      "add.u32 ta, %1, %6;\n\tadd.s64 db, %2, %13;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], [ta], db, %3, t;\n\t"
+      "add.u32 ta, %1, %7;\n\tadd.s64 db, %2, %14;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], [ta], db, %3, t;\n\t"
+      "add.u32 ta, %1, %8;\n\tadd.s64 db, %2, %15;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], [ta], db, %3, t;\n\t"
+      "add.u32 ta, %1, %9;\n\tadd.s64 db, %2, %16;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], [ta], db, %3, t;\n\t"
+      "add.u32 ta, %1, %10;\n\tadd.s64 db, %2, %17;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], [ta], db, %3, t;\n\t"
+      "add.u32 ta, %1, %11;\n\tadd.s64 db, %2, %18;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], [ta], db, %3, t;\n\t"
+      "}"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "n"(OA1), "n"(OA2), "n"(OA3), "n"(OA4), "n"(OA5), "n"(OA6), "n"(OA7), "n"(OB1), "n"(OB2), "n"(OB3), "n"(OB4), "n"(OB5), "n"(OB6), "n"(OB7)
+      : "memory");
+}
+template <int OA1, int OA2, int OA3, int OB1, int OB2, int OB3>
+__device__ __forceinline__ void umma_bf16_ts_w_x4(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc,
+                                                   uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred e, p, t;\n\t.reg .b32 ta;\n\t.reg .b64 db;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "setp.eq.b32 t, %3, %3;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+      "add.u32 ta, %1, %5;\n\tadd.s64 db, %2, %8;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], [ta], db, %3, t;\n\t"
+      "add.u32 ta, %1, %6;\n\tadd.s64 db, %2, %9;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], [ta], db, %3, t;\n\t"
+      "add.u32 ta, %1, %7;\n\tadd.s64 db, %2, %10;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], [ta], db, %3, t;\n\t"
+      "}"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "n"(OA1), "n"(OA2), "n"(OA3), "n"(OB1), "n"(OB2), "n"(OB3)
+      : "memory");
+}
+
 struct AttnFwdArgs {
   bf16* o0;
   int ld0;
