@@ -103,6 +103,13 @@ SIGNATURES = {
     "b200_im2col": (c_int, [_V, _V, _V, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _V]),
     "b200_col2im": (c_int, [_V, _V, _V, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _V]),
     "b200_mask_rows": (c_int, [_V, _V, _I, _V, _I, _V, _I, _L, _I, _V]),
+    "b200_ln_affine_fwd": (c_int, [_V, _V, _I, _V, _V, _V, _I, _V, _V, _I, _I, _F, _V]),
+    "b200_ln_affine_bwd": (c_int, [_V, _V, _I, _V, _I, _V, _V, _V, _V, _I, _V, _I, _I, _I, _V]),
+    "b200_groupnorm_fwd": (c_int, [_V, _V, _V, _V, _V, _V, _V, _I, _I, _I, _I, _F, _I, _V]),
+    "b200_groupnorm_bwd": (c_int, [_V, _V, _V, _V, _V, _V, _V, _V, _I, _I, _I, _I, _I, _V]),
+    "b200_geglu_fwd": (c_int, [_V, _V, _I, _V, _I, _L, _I, _V]),
+    "b200_geglu_bwd": (c_int, [_V, _V, _I, _V, _I, _V, _I, _L, _I, _V]),
+    "b200_heads_pad": (c_int, [_V, _V, _V, _I, _I, _I, _I, _I, _I, _V]),
     "b200_flow_add_noise": (c_int, [_V, _V, _V, _V, _V, _I, _I, _I, _I, _I, _V]),
     "b200_flow_loss": (c_int, [_V, _V, _V, _V, _V, _V, _V, _I, _I, _I, _I, _I, _F, _V]),
     "b200_grad_sumsq": (c_int, [_V, _V, _L, _V, _V]),

@@ -95,6 +95,76 @@ def rms_rope_bwd(dY, x, weight, cos, sin, rstd, dx, B, Lseg, seq_off=0, mode=1):
     return dx
 
 
+def ln_affine_fwd(x, weight, bias, eps=1e-5, out=None):
+    """LayerNorm(x) * weight + bias over the last dim of x [M, D] bf16 (any D % 8 == 0) -> (y, mean, rstd)."""
+    M, D = x.shape
+    out = torch.empty((M, D), device=x.device, dtype=torch.bfloat16) if out is None else out
+    mean = torch.empty(M, device=x.device, dtype=torch.float32)
+    rstd = torch.empty(M, device=x.device, dtype=torch.float32)
+    cabi.call("b200_ln_affine_fwd", _p(x), _ld(x), _p(weight), _p(bias), _p(out), _ld(out), _p(mean), _p(rstd), int(M), int(D),
+              float(eps), device=_dev(x))
+    return out, mean, rstd
+
+
+def ln_affine_bwd(dy, x, mean, rstd, weight, dres=None, out=None):
+    M, D = x.shape
+    out = torch.empty((M, D), device=x.device, dtype=torch.bfloat16) if out is None else out
+    cabi.call("b200_ln_affine_bwd", _p(dy), _ld(dy), _p(x), _ld(x), _p(mean), _p(rstd), _p(weight), _p(dres), _ld(dres), _p(out),
+              _ld(out), int(M), int(D), device=_dev(x))
+    return out
+
+
+def groupnorm_fwd(x, weight, bias, groups=32, eps=1e-5, silu=False):
+    """x [B, C, H, W] bf16 contiguous -> (y like x, mean [B*G], rstd [B*G])."""
+    B, C = x.shape[0], x.shape[1]
+    HW = x.numel() // (B * C)
+    out = torch.empty_like(x)
+    mean = torch.empty(B * groups, device=x.device, dtype=torch.float32)
+    rstd = torch.empty(B * groups, device=x.device, dtype=torch.float32)
+    cabi.call("b200_groupnorm_fwd", _p(x), _p(weight), _p(bias), _p(out), _p(mean), _p(rstd), int(B), int(C), int(HW),
+              int(groups), float(eps), int(bool(silu)), device=_dev(x))
+    return out, mean, rstd
+
+
+def groupnorm_bwd(dy, x, weight, bias, mean, rstd, groups=32, silu=False):
+    B, C = x.shape[0], x.shape[1]
+    HW = x.numel() // (B * C)
+    dx = torch.empty_like(x)
+    cabi.call("b200_groupnorm_bwd", _p(dy), _p(x), _p(weight), _p(bias), _p(mean), _p(rstd), _p(dx), int(B), int(C), int(HW),
+              int(groups), int(bool(silu)), device=_dev(x))
+    return dx
+
+
+def geglu_fwd(proj, out=None):
+    """proj [M, 2F] = (hidden | gate) -> hidden * gelu(gate) [M, F]."""
+    M, F2 = proj.shape
+    F = F2 // 2
+    out = torch.empty((M, F), device=proj.device, dtype=torch.bfloat16) if out is None else out
+    cabi.call("b200_geglu_fwd", _p(proj), _ld(proj), _p(out), _ld(out), int(M), int(F), device=_dev(proj))
+    return out
+
+
+def geglu_bwd(dy, proj, out=None):
+    M, F2 = proj.shape
+    out = torch.empty_like(proj) if out is None else out
+    cabi.call("b200_geglu_bwd", _p(dy), _ld(dy), _p(proj), _ld(proj), _p(out), _ld(out), int(M), int(F2 // 2), device=_dev(proj))
+    return out
+
+
+def heads_pad(x, out, B, L, head_dim):
+    """x [B*L, >= H*head_dim] view -> out [B, H, L, 128] (zero-padded heads)."""
+    cabi.call("b200_heads_pad", _p(x), _p(out), int(x.stride(0)), int(B), int(L), int(out.shape[1]), int(head_dim), 1,
+              device=_dev(x))
+    return out
+
+
+def heads_unpad(hm, out, B, L, head_dim):
+    """head-major [B, H, L, 128] -> out [B*L, >= H*head_dim] view (first head_dim columns of every head)."""
+    cabi.call("b200_heads_pad", _p(hm), _p(out), int(out.stride(0)), int(B), int(L), int(hm.shape[1]), int(head_dim), 0,
+              device=_dev(hm))
+    return out
+
+
 def silu(x, out=None):
     out = torch.empty_like(x) if out is None else out
     cabi.call("b200_silu", _p(x), _p(out), x.numel(), device=_dev(x))

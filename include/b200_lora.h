@@ -278,6 +278,29 @@ int b200_mask_rows(b200_ctx* ctx, void* z, int ldz, const void* row_mask, int ld
                    int64_t rows, int cols, void* stream);
 
 /* -------------------------------------------------------------------------------------------------
+ * Row / layout kernels of the UNet `Transformer2DModel` blocks (SD1.5 / SDXL; the reference's default LoRA target,
+ * toolkit/kohya_lora.py:750; called through toolkit/stable_diffusion_model.py:2049-2055, :2260-2265).
+ * b200_ln_affine_fwd/bwd: LayerNorm with weight / bias for any D % 8 == 0 (640 / 1280 channels); bwd adds `dres`.
+ * b200_groupnorm_fwd/bwd: GroupNorm(G groups, affine, optional SiLU) over NCHW bf16; mean / rstd fp32 [B*G].
+ * b200_geglu_fwd/bwd: proj [M, 2F] = (hidden | gate) -> hidden * gelu_erf(gate) [M, F] (diffusers GEGLU) and its gradient.
+ * b200_heads_pad: [B*L, ld] with H heads of head_dim <= 128 columns <-> head-major [B,H,L,128] zero-padded (to_heads 1 / 0),
+ *   so that the head-dim-128 attention kernels serve heads of 40 / 64 / 80 (pass scale = 1/sqrt(head_dim) to them).
+ */
+int b200_ln_affine_fwd(b200_ctx* ctx, const void* x, int ldx, const void* weight, const void* bias, void* out, int ldo,
+                       void* mean, void* rstd, int M, int D, float eps, void* stream);
+int b200_ln_affine_bwd(b200_ctx* ctx, const void* dy, int lddy, const void* x, int ldx, const void* mean, const void* rstd,
+                       const void* weight, const void* dres, int lddres, void* out, int ldo, int M, int D, void* stream);
+int b200_groupnorm_fwd(b200_ctx* ctx, const void* x, const void* weight, const void* bias, void* out, void* mean, void* rstd,
+                       int B, int C, int HW, int G, float eps, int silu, void* stream);
+int b200_groupnorm_bwd(b200_ctx* ctx, const void* dy, const void* x, const void* weight, const void* bias, const void* mean,
+                       const void* rstd, void* dx, int B, int C, int HW, int G, int silu, void* stream);
+int b200_geglu_fwd(b200_ctx* ctx, const void* proj, int ldp, void* out, int ldo, int64_t M, int F, void* stream);
+int b200_geglu_bwd(b200_ctx* ctx, const void* dy, int lddy, const void* proj, int ldp, void* dproj, int lddp, int64_t M, int F,
+                   void* stream);
+int b200_heads_pad(b200_ctx* ctx, const void* src, void* dst, int ld, int B, int L, int H, int head_dim, int to_heads,
+                   void* stream);
+
+/* -------------------------------------------------------------------------------------------------
  * Optimizer over the flat fp32 LoRA parameter buffer.
  * b200_grad_sumsq: *sumsq_f64 = sum g^2.
  * b200_clip_adamw: total_norm = sqrt(sumsq) * hyper[7]; g *= min(1, max_norm / (total_norm + 1e-6))
