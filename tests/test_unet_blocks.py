@@ -180,11 +180,11 @@ def test_transformer2d_engine_matches_oracle(linear, heads, dim_head, layers, cr
     for name, dt in (("fp32", torch.float32), ("bf16", torch.bfloat16)):
         om = refs[name]
         leaves = _attach_eager_adapters(om, net)
-        xr = x.to(dt).requires_grad_(True)
+        xr = x.detach().to(dt).clone().requires_grad_(True)
         y = om(xr, ctx.to(dt))
         y.backward(dout.to(dt))
         res[name] = (y.detach(), xr.grad, torch.cat([p.grad.reshape(-1) for ab in leaves for p in ab]))
-    xm = x.clone().requires_grad_(True)
+    xm = x.detach().clone().requires_grad_(True)
     net.flat_grads.zero_()
     with net:
         y = model(xm, ctx)
