@@ -582,6 +582,181 @@ def run_b200(args):
         torch.distributed.destroy_process_group()
 
 
+# ---------------------------------------------------------------------------------------------------
+# SDXL (BASELINE.json configs[1]): hybrid arm -- see ai_toolkit_b200/unet.py
+# ---------------------------------------------------------------------------------------------------
+def run_b200_sdxl(args):
+    """configs[1]: SDXL-base LoRA r=8, 1024x1024, bs=2, one GPU.  The Transformer2DModel stacks run on this repo's kernels, the
+    frozen ResNet / sampler body is eager PyTorch (cuDNN); `config.body` says so.  `gpu_reference` = the same step with the
+    oracle's eager UNet (bf16, SDPA attention, adapters as forward hooks, torch AdamW) on the same GPU."""
+    import torch
+
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        raise SystemExit("--model sdxl is a single-GPU measurement (the UNet step has no replica plumbing)")
+    torch.cuda.set_device(0)
+    dev = torch.device("cuda", 0)
+    from ai_toolkit_b200 import LoRASpecialNetwork, cabi
+    from ai_toolkit_b200 import unet as host_unet
+    from ai_toolkit_b200.optimizer import B200AdamW
+
+    ctx = cabi.Context.get(0)
+    BS = args.batch if args.batch != 1 else 2
+    R = args.rank if args.rank != RANK else 8
+    H = W = 128
+    cfg = host_unet.sdxl_config()
+    model = host_unet.UNet2DConditionModel(cfg, device=dev).init_synthetic_(seed=0)
+    net = LoRASpecialNetwork(text_encoder=None, unet=model, lora_dim=R, alpha=R, train_unet=True, train_text_encoder=False, is_sdxl=True)
+    net.force_to(dev, torch.float32)
+    net._update_torch_multiplier()
+    net.apply_to(None, model, False, True)
+    g = torch.Generator(device=dev).manual_seed(1234)
+    with torch.no_grad():
+        for m in net.get_all_modules():
+            m.lora_up.weight.copy_(torch.randn(m.lora_up.weight.shape, generator=g, device=dev) * 0.02)
+    net.mark_params_changed()
+    opt = B200AdamW(net, lr=1e-4, betas=(0.9, 0.999), eps=1e-6, weight_decay=1e-2, max_grad_norm=1.0)
+    step = host_unet.UNetLoRATrainStep(model, net, opt, prediction_type="epsilon")
+    hg = torch.Generator().manual_seed(1234)
+    host = {
+        "latents": (torch.randn(BS, 4, H, W, generator=hg) * 0.18215 * 5).bfloat16().pin_memory(),
+        "noise": torch.randn(BS, 4, H, W, generator=hg).bfloat16().pin_memory(),
+        "timesteps": torch.randint(1, 999, (BS,), generator=hg).pin_memory(),
+        "text_embeds": torch.randn(BS, 77, 2048, generator=hg).bfloat16().pin_memory(),
+        "pooled_embeds": torch.randn(BS, 1280, generator=hg).bfloat16().pin_memory(),
+    }
+    h2d = sum(v.numel() * v.element_size() for v in host.values())
+    d = {k: (v if k == "timesteps" else v.to(dev)) for k, v in host.items()}  # (timesteps stay on the host: see UNetLoRATrainStep.run)
+
+    def run_dev():
+        return step.run(d["latents"], d["noise"], d["timesteps"], d["text_embeds"], d["pooled_embeds"])
+
+    n0 = ctx.launch_count()
+    run_dev()
+    torch.cuda.synchronize()
+    launches_per_step = ctx.launch_count() - n0
+    for _ in range(max(3, args.warmup)):
+        run_dev()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(0)
+    sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    ev0.record()
+    for _ in range(args.steps):
+        run_dev()
+    ev1.record()
+    torch.cuda.synchronize()
+    ms = ev0.elapsed_time(ev1) / args.steps
+    t0 = time.perf_counter()
+    last = None
+    for _ in range(args.steps):
+        dd = {k: (v if k == "timesteps" else v.to(dev, non_blocking=True)) for k, v in host.items()}
+        last = step.hook_train_loop(dd)
+    torch.cuda.synchronize()
+    ms_e2e = (time.perf_counter() - t0) * 1e3 / args.steps
+    sampler.stop_flag = True
+    peaks, peak_kind = measured_peaks()
+    f_step = host_unet.SDXL_STEP_FLOPS_PER_SAMPLE * BS
+    out = {
+        "metric": f"train-steps/sec SDXL-base LoRA r={R} bs={BS} 1024^2", "value": 1e3 / ms, "unit": "steps/s", "n_gpus": 1,
+        "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": "BASELINE.json configs[1]: SDXL-base LoRA r=8 bs=2 1024x1024 (latents 2x4x128x128, text 2x77x2048)",
+                   "global_batch": BS, "img_per_s": BS * 1e3 / ms, "rank": R, "lora_modules": len(net.get_all_modules()),
+                   "lora_params": int(net.n_params), "parallelism": "dp1", "cuda_graph": False,
+                   "body": "HYBRID: Transformer2DModel stacks (adapter-bearing; 70 blocks) on this repo's kernels; frozen ResnetBlock2D / "
+                           "Down/Upsample2D / conv_in/out / time embeddings = eager PyTorch (cuDNN / cuBLAS) under autograd",
+                   "l2": "per-step working set (5.1 GB weights + activations) >> 126 MB L2; no explicit flush"},
+        "impl": "b200",
+        "step_roofline": {"bound": "tensor", "f_step_tflop": f_step / 1e12, "achieved": f_step / (ms * 1e-3) / 1e12,
+                          "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
+                          "frac": f_step / (ms * 1e-3) / 1e12 / peaks["bf16_tflops_sustained"], "peak_kind": f"{peak_kind} sustained",
+                          "f_step_source": "FlopCounterMode over oracle/unet_ref.py fwd+bwd (SURVEY.md section 8d)"},
+        "roofline": None,
+        "e2e": {"value": 1e3 / ms_e2e, "unit": "steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e},
+        "gpu_launches": int(launches_per_step) * args.steps, "launches_per_step": int(launches_per_step),
+        "clocks": sampler.summary(), "loss_last": last["loss"] if last else None,
+    }
+    if not args.skip_gpu_reference:
+        del step, opt, net, model
+        import gc
+
+        gc.collect()
+        torch.cuda.empty_cache()
+        d["timesteps"] = d["timesteps"].to(dev)
+        out["gpu_reference"] = gpu_reference_leg_sdxl(dev, d, R, ms)
+    print(json.dumps(out), flush=True)
+
+
+def gpu_reference_leg_sdxl(dev, d, R, ms_ours, steps=3, warmup=2):
+    import torch
+    import torch.nn.functional as F
+
+    from oracle import unet_ref
+
+    cfg = unet_ref.sdxl_config()
+    torch.manual_seed(0)
+    with torch.device(dev):
+        om = unet_ref.UNet2DConditionModel(cfg).to(torch.bfloat16)
+    with torch.no_grad():
+        for name, p in om.named_parameters():
+            p.copy_(torch.randn(p.shape, device=dev) * 0.02 if not (("norm" in name) and name.endswith(".weight") and p.dim() == 1)
+                    else 1.0 + 0.1 * torch.randn(p.shape, device=dev))
+    om.requires_grad_(False)
+    params = []
+    for name, mod in om.named_modules():
+        if ".attentions." not in name:
+            continue
+        is_lin = isinstance(mod, torch.nn.Linear)
+        is_c1 = isinstance(mod, torch.nn.Conv2d) and mod.kernel_size == (1, 1)
+        if not (is_lin or is_c1):
+            continue
+        cin = mod.in_features if is_lin else mod.in_channels
+        cout = mod.out_features if is_lin else mod.out_channels
+        A = torch.nn.Parameter(torch.randn(R, cin, device=dev) * 0.02)
+        Bw = torch.nn.Parameter(torch.randn(cout, R, device=dev) * 0.02)
+        params += [A, Bw]
+
+        def hook(m, inp, out, A=A, Bw=Bw):  # the reference's LoRAModule.forward under bf16 autocast: org + up(down(x)) * scale
+            x = inp[0]
+            return out + F.linear(F.linear(x, A.to(x.dtype)), Bw.to(x.dtype))
+
+        mod.register_forward_hook(hook)
+    opt = torch.optim.AdamW(params, lr=1e-4, betas=(0.9, 0.999), eps=1e-6, weight_decay=1e-2)
+    B, _, H, W = d["latents"].shape
+    tid = torch.tensor([[H * 8, W * 8, 0, 0, H * 8, W * 8]] * B, device=dev, dtype=torch.float32)
+    betas = torch.linspace(0.00085 ** 0.5, 0.012 ** 0.5, 1000, device=dev) ** 2
+    ac = torch.cumprod(1 - betas, 0)
+
+    def one():
+        opt.zero_grad(set_to_none=True)
+        a = ac[d["timesteps"]]
+        noisy = (a.sqrt()[:, None, None, None] * d["latents"].float() + (1 - a).sqrt()[:, None, None, None] * d["noise"].float()).bfloat16()
+        pred = om(noisy, d["timesteps"].float(), d["text_embeds"], added_cond_kwargs={"text_embeds": d["pooled_embeds"], "time_ids": tid})[0]
+        loss = ((pred.float() - d["noise"].float()) ** 2).mean()
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(params, 1.0)
+        opt.step()
+        return loss
+
+    try:
+        for _ in range(warmup):
+            one()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            loss = one()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        return {"what": "oracle/unet_ref.py UNet, bf16 eager + SDPA, adapters as forward hooks, torch AdamW, no checkpointing",
+                "ms_per_step": ms, "steps": steps, "loss": float(loss), "speedup_of_this_repo": ms / ms_ours,
+                "peak_mem_gb": torch.cuda.max_memory_allocated() / 2 ** 30}
+    except Exception as e:  # noqa: BLE001 -- a reported side measurement must not take the main line down
+        return {"error": f"{type(e).__name__}: {e}"[:300]}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -592,14 +767,17 @@ def main():
     ap.add_argument("--skip-cpu-baseline", action="store_true")
     ap.add_argument("--skip-gpu-reference", action="store_true",
                     help="do not time the eager reference-style PyTorch step on the same GPU after the main measurement")
-    ap.add_argument("--model", default="flux", choices=["flux", "wan"],
-                    help="flux = BASELINE.json configs[2] (the headline metric); wan = configs[3] (Wan2.1-T2V-1.3B, 49x512x512)")
+    ap.add_argument("--model", default="flux", choices=["flux", "wan", "sdxl"],
+                    help="flux = BASELINE.json configs[2] (the headline metric); wan = configs[3] (Wan2.1-T2V-1.3B, 49x512x512); "
+                         "sdxl = configs[1] (hybrid: engine blocks + eager frozen body, one GPU)")
     ap.add_argument("--batch", type=int, default=1, help="samples per GPU (BASELINE.json configs[4] uses 4)")
     ap.add_argument("--rank", type=int, default=RANK, help="LoRA rank (configs[4] sweeps 4, 8, 16, 32, 64)")
     ap.add_argument("--layers", type=int, nargs=2, default=None, help="debug: override (double, single) block counts")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.model == "sdxl":
+        run_b200_sdxl(args)
     else:
         run_b200(args)
 

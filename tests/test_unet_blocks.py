@@ -200,3 +200,109 @@ def test_transformer2d_engine_matches_oracle(linear, heads, dim_head, layers, cr
         y0_ref = copy.deepcopy(unet_ref.Transformer2DModel(heads, dim_head, C, layers, cross_dim, linear)).to(DEV, torch.float32)
         y0_ref.load_state_dict({k: v.float() for k, v in model.state_dict().items()})
         assert _rel(y0, y0_ref(x.float(), ctx.float())) < 1.5e-2
+
+
+# ------------------------------------------------------------------------------------- the UNet host (ai_toolkit_b200/unet.py)
+def _tiny_cfgs():
+    from ai_toolkit_b200 import unet as host
+    kw = dict(block_out_channels=(64, 128), attn_layers=(1, 2), heads=(1, 2), cross_attention_dim=96, use_linear_projection=True,
+              addition_embed=True, addition_time_embed_dim=16, projection_class_embeddings_input_dim=32 + 6 * 16)
+    return host.UNetConfig(**kw), unet_ref.UNetConfig(**kw)
+
+
+def test_unet_host_matches_oracle_parameter_names():
+    from ai_toolkit_b200 import unet as host
+    hc, oc = _tiny_cfgs()
+    for a, b in ((hc, oc), (host.sdxl_config(), unet_ref.sdxl_config())):
+        with torch.device("meta"):
+            so = unet_ref.UNet2DConditionModel(b).state_dict()
+        sm = host.UNet2DConditionModel(a, device="meta").state_dict()
+        assert list(so.keys()) == list(sm.keys())
+        assert all(so[k].shape == sm[k].shape for k in so)
+    n_sdxl = sum(v.numel() for v in sm.values())
+    assert abs(n_sdxl - 2.567e9) < 0.01e9  # SDXL-base UNet: 2.57 B parameters
+    with pytest.raises(NotImplementedError):
+        host.UNet2DConditionModel(host.sd15_config(), device="meta")  # 160-wide heads of SD1.5's deepest levels
+    # the FLOP figure bench.py reports against (FlopCounterMode over the oracle forward + backward)
+    from torch.utils.flop_counter import FlopCounterMode
+    with torch.device("meta"):
+        om = unet_ref.UNet2DConditionModel(unet_ref.sdxl_config()).requires_grad_(False)
+        x = torch.randn(2, 4, 128, 128, requires_grad=True)
+        with FlopCounterMode(display=False) as fc:
+            y = om(x, torch.ones(2), torch.randn(2, 77, 2048),
+                   added_cond_kwargs={"text_embeds": torch.randn(2, 1280), "time_ids": torch.randn(2, 6)})[0]
+            f_fwd = fc.get_total_flops()
+            y.backward(torch.randn_like(y))
+        f_step = fc.get_total_flops()
+    assert abs(f_step / 2 - host.SDXL_STEP_FLOPS_PER_SAMPLE) < 1e6
+    _, lin, att = host.unet_flops(host.sdxl_config(), 2, 128, 128)
+    assert abs((lin + att) - f_fwd) / f_fwd < 1e-4  # the closed form restates the counter's forward
+
+
+@pytest.mark.gpu
+def test_unet_host_step_matches_oracle():
+    """Tiny SDXL-form UNet: prediction, loss and every LoRA gradient of `UNetLoRATrainStep` vs the fp32 oracle UNet with eager
+    adapters and the oracle's `calculate_loss`; then one optimizer step moves the flat parameters."""
+    from ai_toolkit_b200 import B200AdamW
+    from ai_toolkit_b200 import unet as host
+    hc, oc = _tiny_cfgs()
+    o = unet_ref.init_synthetic_(unet_ref.UNet2DConditionModel(oc), seed=3, std=0.05)
+    o.requires_grad_(False)
+    m = host.UNet2DConditionModel(hc, device=DEV)
+    m.load_state_dict(o.state_dict(), strict=True)
+    rank = 8
+    net = LoRASpecialNetwork(None, m, lora_dim=rank, alpha=4, train_text_encoder=False)
+    net.force_to(DEV, torch.float32)
+    net._update_torch_multiplier()
+    net.apply_to(None, m, False, True)
+    g = torch.Generator().manual_seed(4)
+    with torch.no_grad():
+        for lora in net.unet_loras:
+            lora.lora_up.weight.copy_(torch.randn(lora.lora_up.weight.shape, generator=g) * 0.05)
+    net.mark_params_changed()
+    assert len(net.unet_loras) == (2 + 1 + 3) * 2 + 10 * (2 * 1 + 2 + 3 * 2 + 2 * 3)  # proj_in/out + 10 Linears per block
+    B, H, W = 2, 16, 16
+    lat = torch.randn(B, 4, H, W, generator=g).bfloat16().to(DEV)
+    noise = torch.randn(B, 4, H, W, generator=g).bfloat16().to(DEV)
+    text = torch.randn(B, 77, 96, generator=g).bfloat16().to(DEV)
+    pooled = torch.randn(B, 32, generator=g).bfloat16().to(DEV)
+    ts = torch.tensor([37, 801], device=DEV, dtype=torch.int64)
+    opt = B200AdamW(net, lr=1e-3)
+    step = host.UNetLoRATrainStep(m, net, opt, prediction_type="epsilon")
+    p0 = net.flat_params.clone()
+
+    res = {}
+    for name, dt in (("fp32", torch.float32), ("bf16", torch.bfloat16)):
+        om = copy.deepcopy(o).to(DEV, dt)
+        leaves = []
+        name_to_mod = {("lora_unet_" + n.replace(".", "_")): mod for n, mod in om.named_modules()}
+        for lora in net.unet_loras:
+            mod = name_to_mod[lora.lora_name]
+            A = lora.lora_down.weight.detach().clone().requires_grad_(True)
+            Bw = lora.lora_up.weight.detach().clone().requires_grad_(True)
+            leaves.append((A, Bw))
+
+            def hook(mm, inp, out, A=A, Bw=Bw, s=lora.scale):
+                return out + (F.linear(F.linear(inp[0].float(), A), Bw) * s).to(out.dtype)
+
+            mod.register_forward_hook(hook)
+        noisy = step.table.add_noise_ref(lat.float(), noise.float(), ts).to(dt) if hasattr(step.table, "add_noise_ref") else None
+        if noisy is None:
+            ac = step.table.alphas_cumprod.to(DEV)[ts].float()
+            noisy = (ac.sqrt()[:, None, None, None] * lat.float() + (1 - ac).sqrt()[:, None, None, None] * noise.float())
+            noisy = noisy.to(torch.bfloat16).to(dt)  # the kernel rounds the noisy latents to bf16 (the reference's train dtype)
+        pred = om(noisy, ts.float(), text.to(dt), added_cond_kwargs={"text_embeds": pooled.to(dt), "time_ids": step.time_ids(B, H, W)})[0]
+        loss = ((pred.float() - noise.float()) ** 2).mean()
+        loss.backward()
+        res[name] = (loss.detach(), torch.cat([p.grad.reshape(-1) for ab in leaves for p in ab]))
+    tot = step.run(lat, noise, ts, text, pooled)
+    gm = net.flat_grads[:res["fp32"][1].numel()]
+    # (run() already stepped the optimizer; the gradients are still in the flat buffer until the next zero_grad)
+    e_l = abs(tot.item() - res["fp32"][0].item()) / res["fp32"][0].item()
+    fl_l = abs(res["bf16"][0].item() - res["fp32"][0].item()) / res["fp32"][0].item()
+    e_g, fl_g = _rel(gm, res["fp32"][1]), _rel(res["bf16"][1], res["fp32"][1])
+    print(f"[unet host] loss {tot.item():.6f} vs {res['fp32'][0].item():.6f} rel {e_l:.3e} (floor {fl_l:.3e}); dA/dB {e_g:.3e} (floor {fl_g:.3e})")
+    assert e_l < max(2e-3, 1.5 * fl_l) and e_g < max(2e-3, 1.5 * fl_g)
+    assert not torch.equal(net.flat_params, p0)
+    out = step.hook_train_loop(dict(latents=lat, noise=noise, timesteps=ts, text_embeds=text, pooled_embeds=pooled))
+    assert out["loss"] > 0 and out["loss"] == out["loss"]
