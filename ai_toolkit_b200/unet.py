@@ -277,48 +277,104 @@ def unet_flops(cfg: UNetConfig, B, H, W, Lc=77):
 
 
 class UNetLoRATrainStep:
-    """One optimizer step of UNet (SDXL / SD1.5-style) LoRA training: see the module docstring.  No CUDA graph: the frozen body is
-    eager PyTorch under autograd."""
+    """One optimizer step of UNet (SDXL / SD1.5-style) LoRA training: see the module docstring.
 
-    def __init__(self, unet, network, optimizer, *, prediction_type="epsilon", min_snr_gamma=None, snr_gamma=None):
+    `use_cuda_graph=True`: the batch lives in static device buffers and the WHOLE step (zero-grad, add_noise, eager frozen body +
+    engine blocks forward, loss, autograd backward, clip + AdamW + re-pack) is captured into one CUDA graph after two eager
+    steps -- SDXL has ~5,500 launches of this repo's kernels plus the eager body's per step, and the host cannot issue them
+    as fast as the GPU retires them (measured: 132 ms eager-launched).  The per-sample loss coefficients are host table
+    gathers (as in the reference) copied into static device vectors before the replay."""
+
+    def __init__(self, unet, network, optimizer, *, prediction_type="epsilon", min_snr_gamma=None, snr_gamma=None,
+                 use_cuda_graph=False):
         self.unet, self.network, self.optimizer = unet, network, optimizer
         self.dev = unet.device
         self.table = DDPMTable(prediction_type=prediction_type, device=self.dev)
         self.min_snr_gamma, self.snr_gamma = min_snr_gamma, snr_gamma
+        self.use_cuda_graph = use_cuda_graph
         self.loss_host = torch.zeros(1, dtype=torch.float32)
         if torch.device(self.dev).type == "cuda":
             self.loss_host = self.loss_host.pin_memory()
+        self.buf = None
+        self._graph = None
+        self._warm = 0
 
     def time_ids(self, B, H, W):
         """`get_time_ids_from_latents` (stable_diffusion_model.py:1824-1852): (h, w, 0, 0, h, w) in pixels."""
         return torch.tensor([[H * 8, W * 8, 0, 0, H * 8, W * 8]] * B, device=self.dev, dtype=torch.float32)
 
-    def run(self, latents, noise, timesteps, text_embeds, pooled_embeds=None, loss_multiplier=None):
-        """latents / noise [B, 4, H, W] bf16, timesteps int64 [B] (a HOST tensor keeps the step free of device->host syncs: the
-        per-sample loss coefficients are table gathers done on the host, as the reference does them), text_embeds [B, 77, Dc]
-        bf16 (+ pooled [B, 1280] for SDXL).  Returns the device loss scalar."""
-        net, opt = self.network, self.optimizer
+    # -- static batch buffers ---------------------------------------------------------------------------------------
+    def load_batch(self, latents, noise, timesteps, text_embeds, pooled_embeds=None, loss_multiplier=None):
+        """Host (pinned) or device tensors -> the static device buffers (asynchronous copies on the current stream).
+        `timesteps` int64 [B]: pass a HOST tensor to keep the step free of device->host syncs."""
         B, _, H, W = latents.shape
-        opt.zero_grad()
-        t_host = timesteps
-        if timesteps.device.type == "cpu":
-            timesteps = timesteps.to(self.dev, non_blocking=True)
-        noisy = ops.ddpm_add_noise(latents, noise, timesteps, self.table.device_table)
-        v = calc_loss.loss_vectors(t_host, is_flow_matching=False, prediction_type=self.table.prediction_type,
+        if self.buf is None:
+            dev = self.dev
+            self.buf = {
+                "latents": torch.empty(latents.shape, device=dev, dtype=torch.bfloat16),
+                "noise": torch.empty(noise.shape, device=dev, dtype=torch.bfloat16),
+                "timesteps": torch.empty(B, device=dev, dtype=torch.int64),
+                "text": torch.empty(text_embeds.shape, device=dev, dtype=torch.bfloat16),
+                "pooled": None if pooled_embeds is None else torch.empty(pooled_embeds.shape, device=dev, dtype=torch.bfloat16),
+                "time_ids": self.time_ids(B, H, W),
+                "coef_noise": torch.ones(B, device=dev), "coef_latent": torch.zeros(B, device=dev),
+                "sample_weight": torch.ones(B, device=dev), "loss_ws": torch.zeros(B + 1, device=dev),
+            }
+        b = self.buf
+        if tuple(latents.shape) != tuple(b["latents"].shape):
+            raise ValueError(f"batch shape {tuple(latents.shape)} differs from the step's static buffers {tuple(b['latents'].shape)}")
+        b["latents"].copy_(latents, non_blocking=True)
+        b["noise"].copy_(noise, non_blocking=True)
+        b["timesteps"].copy_(timesteps, non_blocking=True)
+        b["text"].copy_(text_embeds, non_blocking=True)
+        if pooled_embeds is not None:
+            b["pooled"].copy_(pooled_embeds, non_blocking=True)
+        v = calc_loss.loss_vectors(timesteps, is_flow_matching=False, prediction_type=self.table.prediction_type,
                                    ddpm_table=self.table, min_snr_gamma=self.min_snr_gamma, snr_gamma=self.snr_gamma,
-                                   loss_multiplier=loss_multiplier, device=self.dev)
+                                   loss_multiplier=loss_multiplier, device="cpu")
+        for k in ("coef_noise", "coef_latent", "sample_weight"):
+            if v[k] is None:
+                b[k].fill_(1.0)
+            else:
+                src = v[k].pin_memory() if torch.device(self.dev).type == "cuda" else v[k]
+                b[k].copy_(src, non_blocking=True)
+
+    def _step(self):
+        net, opt, b = self.network, self.optimizer, self.buf
+        opt.zero_grad()
+        noisy = ops.ddpm_add_noise(b["latents"], b["noise"], b["timesteps"], self.table.device_table)
         added = None
         if self.unet.cfg.addition_embed:
-            added = {"text_embeds": pooled_embeds, "time_ids": self.time_ids(B, H, W)}
+            added = {"text_embeds": b["pooled"], "time_ids": b["time_ids"]}
         net.is_active = True
         try:
-            pred = self.unet(noisy, timesteps.float(), text_embeds, added_cond_kwargs=added)[0]
-            tot, _, dpred = ops.train_loss(pred.contiguous(), latents, noise, pack=False, **v)
+            pred = self.unet(noisy, b["timesteps"].float(), b["text"], added_cond_kwargs=added)[0]
+            _, _, dpred = ops.train_loss(pred.contiguous(), b["latents"], b["noise"], coef_noise=b["coef_noise"],
+                                         coef_latent=b["coef_latent"], sample_weight=b["sample_weight"], pack=False,
+                                         loss_ws=b["loss_ws"])
             pred.backward(dpred)
         finally:
             net.is_active = False
         opt.step()
-        return tot
+
+    def run(self, latents=None, noise=None, timesteps=None, text_embeds=None, pooled_embeds=None, loss_multiplier=None):
+        """latents / noise [B, 4, H, W] bf16, timesteps int64 [B], text_embeds [B, 77, Dc] bf16 (+ pooled [B, 1280] for SDXL);
+        with no arguments the resident batch is stepped again.  Returns the device loss scalar (no host sync)."""
+        if latents is not None:
+            self.load_batch(latents, noise, timesteps, text_embeds, pooled_embeds, loss_multiplier)
+        B = self.buf["latents"].shape[0]
+        self.optimizer.sync_hyper()
+        if not self.use_cuda_graph or self._warm < 2:
+            self._step()
+            self._warm += 1
+            return self.buf["loss_ws"][B:B + 1]
+        if self._graph is None:
+            torch.cuda.synchronize()
+            self._graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self._graph):
+                self._step()
+        self._graph.replay()
+        return self.buf["loss_ws"][B:B + 1]
 
     def hook_train_loop(self, batch) -> OrderedDict:
         loss = self.run(batch["latents"], batch["noise"], batch["timesteps"], batch["text_embeds"], batch.get("pooled_embeds"))

@@ -58,6 +58,32 @@ def test_col_reduce_gate():
     assert _rel(dgate, want) < 1e-4
 
 
+@pytest.mark.parametrize("M,rps", [(996, 498), (1030, 515), (77, 77)])
+def test_col_reduce_ragged_rows(M, rps):
+    """The 16-byte kernel loads 4 rows at a time with a clamped tail: sample boundaries / tails that are not multiples of 4."""
+    from ai_toolkit_b200 import ops
+    torch.manual_seed(1)
+    D = 3072
+    S = (M + rps - 1) // rps
+    a = torch.randn(M, D, device=DEV).bfloat16()
+    b = torch.randn(M, D, device=DEV).bfloat16()
+    mean = torch.randn(M, device=DEV) * 0.1
+    rstd = torch.rand(M, device=DEV) + 0.5
+    idx = torch.arange(M, device=DEV) // rps
+    sums = torch.zeros(S, 2 * D, device=DEV)
+    ops.col_reduce(a, rps, b=b, mean=mean, rstd=rstd, sum_a=sums[:, :D], sum_ab=sums[:, D:])
+    xh = (b.float() - mean[:, None]) * rstd[:, None]
+    want_a = torch.zeros(S, D, device=DEV).index_add_(0, idx, a.float())
+    want_ab = torch.zeros(S, D, device=DEV).index_add_(0, idx, a.float() * xh)
+    assert _rel(sums[:, :D], want_a) < 1e-5 and _rel(sums[:, D:], want_ab) < 1e-5
+    gate = torch.randn(S, D, device=DEV).bfloat16()
+    out = torch.full((M + 1, D), 7.0, device=DEV).bfloat16()
+    dg = torch.zeros(S, D, device=DEV)
+    ops.col_reduce(a, rps, b=b, g=gate, mul_out=out[:M], sum_ab=dg)
+    assert torch.equal(out[:M], (a.float() * gate.float()[idx]).bfloat16()) and bool((out[M] == 7.0).all())
+    assert _rel(dg, torch.zeros(S, D, device=DEV).index_add_(0, idx, a.float() * b.float())) < 1e-5
+
+
 def _rope_ref(x, cos, sin):
     xr, xi = x.reshape(*x.shape[:-1], -1, 2).unbind(-1)
     rot = torch.stack([-xi, xr], dim=-1).flatten(-2)

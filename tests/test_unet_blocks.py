@@ -243,7 +243,7 @@ def test_unet_host_matches_oracle_parameter_names():
 def test_unet_host_step_matches_oracle():
     """Tiny SDXL-form UNet: prediction, loss and every LoRA gradient of `UNetLoRATrainStep` vs the fp32 oracle UNet with eager
     adapters and the oracle's `calculate_loss`; then one optimizer step moves the flat parameters."""
-    from ai_toolkit_b200 import B200AdamW
+    from ai_toolkit_b200.optimizer import B200AdamW
     from ai_toolkit_b200 import unet as host
     hc, oc = _tiny_cfgs()
     o = unet_ref.init_synthetic_(unet_ref.UNet2DConditionModel(oc), seed=3, std=0.05)
@@ -304,5 +304,43 @@ def test_unet_host_step_matches_oracle():
     print(f"[unet host] loss {tot.item():.6f} vs {res['fp32'][0].item():.6f} rel {e_l:.3e} (floor {fl_l:.3e}); dA/dB {e_g:.3e} (floor {fl_g:.3e})")
     assert e_l < max(2e-3, 1.5 * fl_l) and e_g < max(2e-3, 1.5 * fl_g)
     assert not torch.equal(net.flat_params, p0)
-    out = step.hook_train_loop(dict(latents=lat, noise=noise, timesteps=ts, text_embeds=text, pooled_embeds=pooled))
+    out = step.hook_train_loop(dict(latents=lat, noise=noise, timesteps=ts.cpu(), text_embeds=text, pooled_embeds=pooled))
     assert out["loss"] > 0 and out["loss"] == out["loss"]
+
+
+@pytest.mark.gpu
+def test_unet_host_step_cuda_graph_equals_eager():
+    """The whole-step CUDA graph (eager frozen body + engine blocks + autograd backward + optimizer) replays the eager step:
+    same losses and same flat parameters after 5 steps on changing batches (fp32 atomics in the wgrads: tolerance, not bits)."""
+    from ai_toolkit_b200.optimizer import B200AdamW
+    from ai_toolkit_b200 import unet as host
+    hc, _ = _tiny_cfgs()
+    runs = {}
+    for graph in (False, True):
+        m = host.UNet2DConditionModel(hc, device=DEV).init_synthetic_(seed=5, std=0.05)
+        net = LoRASpecialNetwork(None, m, lora_dim=4, alpha=4, train_text_encoder=False)
+        net.force_to(DEV, torch.float32)
+        net._update_torch_multiplier()
+        net.apply_to(None, m, False, True)
+        g = torch.Generator().manual_seed(6)
+        with torch.no_grad():
+            for lora in net.unet_loras:
+                lora.lora_down.weight.copy_(torch.randn(lora.lora_down.weight.shape, generator=g) * 0.05)
+                lora.lora_up.weight.copy_(torch.randn(lora.lora_up.weight.shape, generator=g) * 0.05)
+        net.mark_params_changed()
+        opt = B200AdamW(net, lr=1e-3, max_grad_norm=1.0)
+        step = host.UNetLoRATrainStep(m, net, opt, prediction_type="v_prediction", min_snr_gamma=5.0, use_cuda_graph=graph)
+        losses = []
+        for i in range(5):
+            lat = torch.randn(2, 4, 16, 16, generator=g).bfloat16()
+            noise = torch.randn(2, 4, 16, 16, generator=g).bfloat16()
+            text = torch.randn(2, 77, 96, generator=g).bfloat16()
+            pooled = torch.randn(2, 32, generator=g).bfloat16()
+            ts = torch.randint(1, 999, (2,), generator=g)
+            losses.append(step.hook_train_loop(dict(latents=lat, noise=noise, timesteps=ts, text_embeds=text, pooled_embeds=pooled))["loss"])
+        assert (step._graph is not None) == graph
+        runs[graph] = (losses, net.flat_params.clone())
+    le, lg = runs[False][0], runs[True][0]
+    print("[unet graph] eager", le, "graph", lg)
+    assert all(abs(a - b) / abs(a) < 2e-3 for a, b in zip(le, lg))
+    assert _rel(runs[True][1], runs[False][1]) < 2e-3
