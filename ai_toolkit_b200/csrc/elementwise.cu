@@ -11,8 +11,6 @@
 //   QK RMSNorm ................. extensions_built_in/diffusion_models/chroma/src/layers.py:72-91
 //   RoPE ....................... extensions_built_in/diffusion_models/chroma/src/math.py:33-51
 //   timestep embedding ......... extensions_built_in/diffusion_models/chroma/src/layers.py:30-53
-#include <cstdlib>
-
 #include "common.cuh"
 #include "ctx.h"
 
@@ -36,35 +34,53 @@ __device__ __forceinline__ void st8(bf16* p, const float (&v)[8]) {
 // LayerNorm (no affine, eps) + modulation:  y = bf16( bf16( bf16((x-mean)*rstd) * bf16(1+scale) ) + shift )
 // NCH = D / 256 (each lane owns NCH chunks of 8 consecutive elements, chunk c at column c*256 + lane*8).
 // ------------------------------------------------------------------------------------------------
+// Round 2: the row is STAGED IN SHARED MEMORY by cp.async (16 bytes per lane and chunk, no registers), read once for the
+// statistics and once for the output -- round 1 held fp32 copies in registers (124 / 254 registers at D = 3072), i.e. ONE
+// 8-warp block per SM whose warps all load, then all compute, then all store: 2.4-2.6 TB/s (profiles/r2_time_rows.log).
+// Each lane reads back only the bytes it copied itself, so no barrier is needed beyond cp.async.wait_all.  Same arithmetic
+// in the same order as round 1.
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
 template <int NCH>
-__global__ void __launch_bounds__(256) ln_modulate_fwd_kernel(const bf16* __restrict__ x, int ldx, const bf16* __restrict__ shift,
+__global__ void __launch_bounds__(256, NCH <= 12 ? 2 : 1) ln_modulate_fwd_kernel(const bf16* __restrict__ x, int ldx, const bf16* __restrict__ shift,
                                                               const bf16* __restrict__ scale, int ldmod,
                                                               int rows_per_sample, bf16* __restrict__ out, int ldo,
                                                               float* __restrict__ mean_out, float* __restrict__ rstd_out,
                                                               int M, float eps) {
+  extern __shared__ __align__(16) uint8_t ln_rows[];
   pdl_grid_sync();
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= M) return;
   constexpr int D = NCH * 256;
-  float v[NCH][8];
+  bf16* sx = reinterpret_cast<bf16*>(ln_rows) + (threadIdx.x >> 5) * D;
   const bf16* xr = x + static_cast<size_t>(row) * ldx;
+#pragma unroll
+  for (int c = 0; c < NCH; ++c) cp_async16(sx + c * 256 + lane * 8, xr + c * 256 + lane * 8);
+  cp_async_wait_all();
   float s = 0.f;
 #pragma unroll
   for (int c = 0; c < NCH; ++c) {
-    ld8(xr + c * 256 + lane * 8, v[c]);
+    float v[8];
+    ld8(sx + c * 256 + lane * 8, v);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) s += v[c][i];
+    for (int i = 0; i < 8; ++i) s += v[i];
   }
   const float mean = warp_sum(s) * (1.0f / D);
   float q = 0.f;
 #pragma unroll
-  for (int c = 0; c < NCH; ++c)
+  for (int c = 0; c < NCH; ++c) {
+    float v[8];
+    ld8(sx + c * 256 + lane * 8, v);
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      const float d = v[c][i] - mean;
+      const float d = v[i] - mean;
       q += d * d;
     }
+  }
   const float rstd = rsqrtf(warp_sum(q) * (1.0f / D) + eps);
   if (lane == 0) {
     if (mean_out) mean_out[row] = mean;
@@ -77,13 +93,14 @@ __global__ void __launch_bounds__(256) ln_modulate_fwd_kernel(const bf16* __rest
 #pragma unroll
   for (int c = 0; c < NCH; ++c) {
     const int col = c * 256 + lane * 8;
-    float o[8];
+    float v[8], o[8];
     float a[8], b[8];
+    ld8(sx + col, v);
     if (sc) ld8(sc + col, a);
     if (sh) ld8(sh + col, b);
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      float y = bf16_round((v[c][i] - mean) * rstd);
+      float y = bf16_round((v[i] - mean) * rstd);
       if (sc) y = bf16_round(y * bf16_round(1.0f + a[i]));
       if (sh) y = bf16_round(y + b[i]);
       o[i] = y;
@@ -95,35 +112,45 @@ __global__ void __launch_bounds__(256) ln_modulate_fwd_kernel(const bf16* __rest
 // Backward of the above w.r.t. x, fused with the residual-stream gradient:
 //   dxhat = dy * (1 + scale);  dx = rstd * (dxhat - mean(dxhat) - xhat * mean(dxhat * xhat));  out = dres + dx
 template <int NCH>
-__global__ void __launch_bounds__(256) ln_modulate_bwd_kernel(const bf16* __restrict__ dy, int lddy, const bf16* __restrict__ x,
+__global__ void __launch_bounds__(256, NCH <= 12 ? 2 : 1) ln_modulate_bwd_kernel(const bf16* __restrict__ dy, int lddy, const bf16* __restrict__ x,
                                                               int ldx, const float* __restrict__ mean_in,
                                                               const float* __restrict__ rstd_in,
                                                               const bf16* __restrict__ scale, int ldmod,
                                                               int rows_per_sample, const bf16* __restrict__ dres, int lddres,
                                                               bf16* __restrict__ out, int ldo, int M) {
+  extern __shared__ __align__(16) uint8_t ln_rows[];
   pdl_grid_sync();
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= M) return;
   constexpr int D = NCH * 256;
+  bf16* sx = reinterpret_cast<bf16*>(ln_rows) + (threadIdx.x >> 5) * (2 * D);
+  bf16* sg = sx + D;
+#pragma unroll
+  for (int c = 0; c < NCH; ++c) {
+    const int col = c * 256 + lane * 8;
+    cp_async16(sx + col, x + static_cast<size_t>(row) * ldx + col);
+    cp_async16(sg + col, dy + static_cast<size_t>(row) * lddy + col);
+  }
   const float mean = mean_in[row], rstd = rstd_in[row];
   const int sample = row / rows_per_sample;
   const bf16* sc = scale ? scale + static_cast<size_t>(sample) * ldmod : nullptr;
-  float xh[NCH][8], g[NCH][8];
+  cp_async_wait_all();
   float s1 = 0.f, s2 = 0.f;
 #pragma unroll
   for (int c = 0; c < NCH; ++c) {
     const int col = c * 256 + lane * 8;
-    float xv[8], a[8];
-    ld8(x + static_cast<size_t>(row) * ldx + col, xv);
-    ld8(dy + static_cast<size_t>(row) * lddy + col, g[c]);
+    float xv[8], gv[8], a[8];
+    ld8(sx + col, xv);
+    ld8(sg + col, gv);
     if (sc) ld8(sc + col, a);
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      xh[c][i] = (xv[i] - mean) * rstd;
-      if (sc) g[c][i] *= bf16_round(1.0f + a[i]);
-      s1 += g[c][i];
-      s2 += g[c][i] * xh[c][i];
+      const float xh = (xv[i] - mean) * rstd;
+      float gg = gv[i];
+      if (sc) gg *= bf16_round(1.0f + a[i]);
+      s1 += gg;
+      s2 += gg * xh;
     }
   }
   s1 = warp_sum(s1) * (1.0f / D);
@@ -131,11 +158,17 @@ __global__ void __launch_bounds__(256) ln_modulate_bwd_kernel(const bf16* __rest
 #pragma unroll
   for (int c = 0; c < NCH; ++c) {
     const int col = c * 256 + lane * 8;
-    float o[8], r[8];
+    float xv[8], gv[8], a[8], o[8], r[8];
     if (dres) ld8(dres + static_cast<size_t>(row) * lddres + col, r);
+    ld8(sx + col, xv);
+    ld8(sg + col, gv);
+    if (sc) ld8(sc + col, a);  // (the per-sample scale row is L1 / L2 resident)
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      float d = rstd * (g[c][i] - s1 - xh[c][i] * s2);
+      const float xh = (xv[i] - mean) * rstd;
+      float gg = gv[i];
+      if (sc) gg *= bf16_round(1.0f + a[i]);
+      const float d = rstd * (gg - s1 - xh * s2);
       o[i] = dres ? d + r[i] : d;
     }
     st8(out + static_cast<size_t>(row) * ldo + col, o);
@@ -148,6 +181,8 @@ __global__ void __launch_bounds__(256) ln_modulate_bwd_kernel(const bf16* __rest
 //   sum_ab[s, d] += sum_rows a[m, d] * f(b[m, d]),   f(b) = (b - mean[m]) * rstd[m]  or  b
 //   mul_out[m, d] = bf16(a[m, d] * g[s, d])                                  (optional)
 // Block: 256 threads = 256 column pairs (512 columns) x ROWS rows of one sample; fp32 atomics to [S, D].
+// (Round 2 tried a 16-byte-per-thread variant, 128 threads x 8 columns x 32 rows with 4 rows of loads in flight: slower on the
+// B200 -- 22.6 vs 15.9 us back-to-back, 38.9 vs 30.7 us L2-flushed at M = 4608, D = 3072 (profiles/r2_time_rows.log) -- removed.)
 // ------------------------------------------------------------------------------------------------
 constexpr int kColRows = 64;
 __global__ void __launch_bounds__(256) col_reduce_kernel(const bf16* __restrict__ a, int lda, const bf16* __restrict__ b, int ldb,
@@ -190,74 +225,6 @@ __global__ void __launch_bounds__(256) col_reduce_kernel(const bf16* __restrict_
   if (sum_ab) {
     atomicAdd(sum_ab + static_cast<size_t>(sample) * ldsum + col, sb0);
     atomicAdd(sum_ab + static_cast<size_t>(sample) * ldsum + col + 1, sb1);
-  }
-}
-
-// 16-byte variant (round 2): the kernel above keeps only ~24 KB of loads in flight per SM (4-byte loads, 4 rows unrolled) and
-// measured 2.3 TB/s.  Here a thread owns 8 consecutive columns, a block 1024 columns x 32 rows, and the loads of 4 rows
-// (a and b: 8 x 16 B per thread) are issued before the first use.
-constexpr int kColRows8 = 32;
-template <bool HAS_STATS, bool HAS_MUL>
-__global__ void __launch_bounds__(128) col_reduce8_kernel(const bf16* __restrict__ a, int lda, const bf16* __restrict__ b, int ldb,
-                                                          const float* __restrict__ mean, const float* __restrict__ rstd,
-                                                          const bf16* __restrict__ g, int ldg, bf16* __restrict__ mul_out,
-                                                          int ldmul, float* __restrict__ sum_a, float* __restrict__ sum_ab,
-                                                          int ldsum, int rows_per_sample, int M, int D) {
-  pdl_grid_sync();
-  const int col = (blockIdx.x * 128 + threadIdx.x) * 8;
-  if (col >= D) return;
-  const int chunks_per_sample = (rows_per_sample + kColRows8 - 1) / kColRows8;
-  const int sample = blockIdx.y / chunks_per_sample;
-  const int r0 = sample * rows_per_sample + (blockIdx.y % chunks_per_sample) * kColRows8;
-  const int r1 = min(min(r0 + kColRows8, (sample + 1) * rows_per_sample), M);
-  float gv[8];
-  if (HAS_MUL) ld8(g + static_cast<size_t>(sample) * ldg + col, gv);
-  float sa[8], sb[8];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) sa[i] = sb[i] = 0.f;
-  for (int r = r0; r < r1; r += 4) {
-    uint4 ua[4], ub[4];
-    float mu[4], rs[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int rr = min(r + j, r1 - 1);  // clamped: the duplicate rows of a ragged tail are skipped below
-      ua[j] = *reinterpret_cast<const uint4*>(a + static_cast<size_t>(rr) * lda + col);
-      ub[j] = *reinterpret_cast<const uint4*>(b + static_cast<size_t>(rr) * ldb + col);
-      if (HAS_STATS) {
-        mu[j] = mean[rr];
-        rs[j] = rstd[rr];
-      }
-    }
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      if (r + j >= r1) break;
-      const uint32_t wa[4] = {ua[j].x, ua[j].y, ua[j].z, ua[j].w};
-      const uint32_t wb[4] = {ub[j].x, ub[j].y, ub[j].z, ub[j].w};
-      float o[8];
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const float2 av = unpack_bf16x2(wa[k]);
-        float2 bv = unpack_bf16x2(wb[k]);
-        if (HAS_STATS) {
-          bv.x = (bv.x - mu[j]) * rs[j];
-          bv.y = (bv.y - mu[j]) * rs[j];
-        }
-        sa[2 * k] += av.x;
-        sa[2 * k + 1] += av.y;
-        sb[2 * k] += av.x * bv.x;
-        sb[2 * k + 1] += av.y * bv.y;
-        if (HAS_MUL) {
-          o[2 * k] = av.x * gv[2 * k];
-          o[2 * k + 1] = av.y * gv[2 * k + 1];
-        }
-      }
-      if (HAS_MUL) st8(mul_out + static_cast<size_t>(r + j) * ldmul + col, o);
-    }
-  }
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    if (sum_a) atomicAdd(sum_a + static_cast<size_t>(sample) * ldsum + col + i, sa[i]);
-    if (sum_ab) atomicAdd(sum_ab + static_cast<size_t>(sample) * ldsum + col + i, sb[i]);
   }
 }
 
@@ -449,8 +416,17 @@ extern "C" int b200_ln_modulate_fwd(b200_ctx* ctx, const void* x, int ldx, const
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const int grid = (M + 7) / 8;
 #define CALL(N_)                                                                                                         \
-  B200_KLAUNCH(ln_modulate_fwd_kernel<N_>, grid, 256, 0, st, (const bf16*)x, ldx, (const bf16*)shift, (const bf16*)scale, ldmod, \
-                                                   rows_per_sample, (bf16*)out, ldo, (float*)mean, (float*)rstd, M, eps)
+  do {                                                                                                                   \
+    auto kern = ln_modulate_fwd_kernel<N_>;                                                                              \
+    constexpr int kSm = 8 * N_ * 256 * 2;                                                                                \
+    static bool configured = false;                                                                                      \
+    if (!configured) {                                                                                                   \
+      B200_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSm));                     \
+      configured = true;                                                                                                 \
+    }                                                                                                                    \
+    B200_KLAUNCH(kern, grid, 256, kSm, st, (const bf16*)x, ldx, (const bf16*)shift, (const bf16*)scale, ldmod,           \
+                 rows_per_sample, (bf16*)out, ldo, (float*)mean, (float*)rstd, M, eps);                                  \
+  } while (0)
   B200_LN_DISPATCH(D, CALL)
 #undef CALL
   B200_CUDA_CHECK(cudaGetLastError());
@@ -467,10 +443,19 @@ extern "C" int b200_ln_modulate_bwd(b200_ctx* ctx, const void* dy, int lddy, con
   B200_REQUIRE(lddy % 8 == 0 && ldx % 8 == 0 && ldo % 8 == 0 && rows_per_sample > 0, "b200_ln_modulate_bwd: alignment");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const int grid = (M + 7) / 8;
-#define CALL(N_)                                                                                                      \
-  B200_KLAUNCH(ln_modulate_bwd_kernel<N_>, grid, 256, 0, st, (const bf16*)dy, lddy, (const bf16*)x, ldx, (const float*)mean,  \
-                                                   (const float*)rstd, (const bf16*)scale, ldmod, rows_per_sample,  \
-                                                   (const bf16*)dres, lddres, (bf16*)out, ldo, M)
+#define CALL(N_)                                                                                                         \
+  do {                                                                                                                   \
+    auto kern = ln_modulate_bwd_kernel<N_>;                                                                              \
+    constexpr int kSm = 8 * 2 * N_ * 256 * 2;                                                                            \
+    static bool configured = false;                                                                                      \
+    if (!configured) {                                                                                                   \
+      B200_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSm));                     \
+      configured = true;                                                                                                 \
+    }                                                                                                                    \
+    B200_KLAUNCH(kern, grid, 256, kSm, st, (const bf16*)dy, lddy, (const bf16*)x, ldx, (const float*)mean,               \
+                 (const float*)rstd, (const bf16*)scale, ldmod, rows_per_sample, (const bf16*)dres, lddres, (bf16*)out,  \
+                 ldo, M);                                                                                                \
+  } while (0)
   B200_LN_DISPATCH(D, CALL)
 #undef CALL
   B200_CUDA_CHECK(cudaGetLastError());
@@ -488,32 +473,6 @@ extern "C" int b200_col_reduce(b200_ctx* ctx, const void* a, int lda, const void
   B200_REQUIRE((mean == nullptr) == (rstd == nullptr), "b200_col_reduce: mean and rstd go together");
   if (mul_out) B200_REQUIRE(g != nullptr, "b200_col_reduce: mul_out needs g");
   const int samples = (M + rows_per_sample - 1) / rows_per_sample;
-  auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
-  static int narrow = -1;  // B200_COL_REDUCE_NARROW=1: the round-1 4-byte kernel (A/B timing)
-  if (narrow < 0) {
-    const char* e = getenv("B200_COL_REDUCE_NARROW");
-    narrow = (e && atoi(e) == 1) ? 1 : 0;
-  }
-  if (!narrow && b && D % 8 == 0 && lda % 8 == 0 && ldb % 8 == 0 && al16(a) && al16(b) &&
-      (!mul_out || (ldmul % 8 == 0 && ldg % 8 == 0 && al16(mul_out) && al16(g)))) {
-    const int chunks8 = (rows_per_sample + kColRows8 - 1) / kColRows8;
-    dim3 grid8((D / 8 + 127) / 128, samples * chunks8);
-#define CR8(ST, MU)                                                                                                     \
-  do {                                                                                                                  \
-    auto kern8 = col_reduce8_kernel<ST, MU>;                                                                            \
-    B200_KLAUNCH(kern8, grid8, 128, 0, reinterpret_cast<cudaStream_t>(stream), (const bf16*)a, lda, (const bf16*)b, ldb, \
-                 (const float*)mean, (const float*)rstd, (const bf16*)g, ldg, (bf16*)mul_out, ldmul, (float*)sum_a,       \
-                 (float*)sum_ab, ldsum, rows_per_sample, M, D);                                                          \
-  } while (0)
-    if (mean && mul_out) CR8(true, true);
-    else if (mean) CR8(true, false);
-    else if (mul_out) CR8(false, true);
-    else CR8(false, false);
-#undef CR8
-    B200_CUDA_CHECK(cudaGetLastError());
-    ctx->launches.fetch_add(1);
-    return B200_OK;
-  }
   const int chunks = (rows_per_sample + kColRows - 1) / kColRows;
   dim3 grid((D / 2 + 255) / 256, samples * chunks);
   B200_KLAUNCH(col_reduce_kernel, grid, 256, 0, reinterpret_cast<cudaStream_t>(stream), 

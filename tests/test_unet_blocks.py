@@ -260,7 +260,8 @@ def test_unet_host_step_matches_oracle():
         for lora in net.unet_loras:
             lora.lora_up.weight.copy_(torch.randn(lora.lora_up.weight.shape, generator=g) * 0.05)
     net.mark_params_changed()
-    assert len(net.unet_loras) == (2 + 1 + 3) * 2 + 10 * (2 * 1 + 2 + 3 * 2 + 2 * 3)  # proj_in/out + 10 Linears per block
+    # 11 Transformer2DModels (2 + 2 down, 1 mid, 3 + 3 up) x proj_in/out + 17 BasicTransformerBlocks x 10 Linears
+    assert len(net.unet_loras) == 2 * 11 + 10 * (2 * 1 + 2 * 2 + 1 * 2 + 3 * 2 + 3 * 1)
     B, H, W = 2, 16, 16
     lat = torch.randn(B, 4, H, W, generator=g).bfloat16().to(DEV)
     noise = torch.randn(B, 4, H, W, generator=g).bfloat16().to(DEV)
