@@ -13,6 +13,8 @@ Shared by the per-module autograd path (`autograd.lora_linear`, the drop-in for
 """
 from __future__ import annotations
 
+import os
+
 import torch
 
 from . import cabi, ops
@@ -20,6 +22,18 @@ from .cabi import gemm_bf16
 
 RANK_PAD = 64
 GEMV_MAX_ROWS = 8
+RANK_SIMT_MAX = 16
+_RANK_SIMT = os.environ.get("B200_RANK_SIMT", "1") != "0"  # 0: every rank-side product on the tensor-core skinny kernel (A/B)
+
+
+def rank_side(x2, w, out, r_live, *, trans_b=False, alpha=1.0, row_alpha=None, rows_per_sample=0):
+    """Zc = bf16(c * X A_pack^T) or (trans_b) T = bf16(c * dY B_pack): streaming of X with 2 r FLOP per element.  Live ranks
+    <= 16 run on the CUDA-core kernel (csrc/rank_simt.cu), larger ones / fused groups with more live columns on the
+    cluster split-K tcgen05 skinny GEMM -- the same arithmetic either way (fp32 accumulate, one bf16 rounding)."""
+    if _RANK_SIMT and 0 < r_live <= RANK_SIMT_MAX and x2.stride(1) == 1 and x2.data_ptr() % 16 == 0 and x2.stride(0) % 8 == 0 \
+            and x2.shape[1] % 8 == 0:
+        return ops.rank_gemm(x2, w, out, r_live, trans_w=trans_b, alpha=alpha, row_alpha=row_alpha, rows_per_sample=rows_per_sample)
+    return gemm_bf16(x2, w, out, trans_b=trans_b, alpha=alpha, row_alpha=row_alpha, rows_per_sample=rows_per_sample)
 
 
 def wgrad_splits(tokens: int, features: int, sm_count: int = 148) -> int:
@@ -69,7 +83,7 @@ def linear_fwd(lin, x2, out, *, lora=None, zc_out=None, zc_hook=None, **epi):
         return None
     alpha, row_alpha, rps = lora_coeff(lora, x2.shape[0])
     zc = zc_out if zc_out is not None else torch.empty((x2.shape[0], RANK_PAD), device=x2.device, dtype=torch.bfloat16)
-    gemm_bf16(x2, lora.a_pack, zc, alpha=alpha, row_alpha=row_alpha, rows_per_sample=rps)  # cluster split-K skinny GEMM
+    rank_side(x2, lora.a_pack, zc, lora.lora_dim, alpha=alpha, row_alpha=row_alpha, rows_per_sample=rps)
     if zc_hook is not None:  # dropout / rank-dropout masks on the rank-side activation (network_mixins.py:211-226)
         zc_hook(zc)
     gemm_bf16(x2, W, out, a1=zc, b1=lora.b_pack, bias=lin.bias, **epi)
@@ -86,7 +100,7 @@ def linear_bwd(lin, dy, x2, zc, dx_out, *, lora=None, n_slices=None, t_hook=None
     if lora is not None:
         alpha, row_alpha, rps = lora_coeff(lora, dy.shape[0])
         t = torch.empty((dy.shape[0], RANK_PAD), device=dy.device, dtype=torch.bfloat16)
-        gemm_bf16(dy, lora.b_pack, t, trans_b=True, alpha=alpha, row_alpha=row_alpha, rows_per_sample=rps)
+        rank_side(dy, lora.b_pack, t, lora.lora_dim, trans_b=True, alpha=alpha, row_alpha=row_alpha, rows_per_sample=rps)
         if t_hook is not None:
             t_hook(t)
     if dx_out is not None:
@@ -138,7 +152,7 @@ def group_fwd(group, lins, x2, out, **epi):
     W, bias = fuse_linear_weights(lins)
     alpha, row_alpha, rps = lora_coeff(group.loras[0], x2.shape[0])
     zc = torch.empty((x2.shape[0], RANK_PAD), device=x2.device, dtype=torch.bfloat16)
-    gemm_bf16(x2, group.a_fused, zc, alpha=alpha, row_alpha=row_alpha, rows_per_sample=rps)
+    rank_side(x2, group.a_fused, zc, group.r * len(group.loras), alpha=alpha, row_alpha=row_alpha, rows_per_sample=rps)
     gemm_bf16(x2, W, out, a1=zc, b1=group.b_fused, bias=bias, **epi)
     return zc
 
@@ -148,7 +162,7 @@ def group_bwd(group, lins, dy, x2, zc, dx_out, **epi):
     W, _ = fuse_linear_weights(lins)
     alpha, row_alpha, rps = lora_coeff(group.loras[0], dy.shape[0])
     t = torch.empty((dy.shape[0], RANK_PAD), device=dy.device, dtype=torch.bfloat16)
-    gemm_bf16(dy, group.b_fused, t, trans_b=True, alpha=alpha, row_alpha=row_alpha, rows_per_sample=rps)
+    rank_side(dy, group.b_fused, t, group.r * len(group.loras), trans_b=True, alpha=alpha, row_alpha=row_alpha, rows_per_sample=rps)
     if dx_out is not None:
         gemm_bf16(dy, W, dx_out, a1=t, b1=group.a_fused, trans_b=True, **epi)
     r = group.r
