@@ -23,6 +23,8 @@ GEMM_2CTA_N256 = 2
 GEMM_1CTA_N128 = 3
 GEMM_1CTA_N64 = 4
 GEMM_SKINNY_CLUSTER = 5
+GEMM_1CTA_N160 = 6
+GEMM_1CTA_N192 = 7
 
 
 class B200Error(RuntimeError):

@@ -314,7 +314,7 @@ struct GemmCfg {
   static constexpr uint32_t A_BYTES = BM * BK * 2;
   static constexpr uint32_t B_BYTES = BNL * BK * 2;
   static constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int TMEM_COLS = 2 * BN;
+  static constexpr int TMEM_COLS = 2 * BN <= 64 ? 64 : (2 * BN <= 128 ? 128 : (2 * BN <= 256 ? 256 : 512));  // two accumulators, BN apart
   static constexpr size_t EPI_SCRATCH = 8 * 2048;  // per epilogue warp: 32 x 64 B transpose buffer
   static constexpr size_t SMEM_BYTES = 1024 + static_cast<size_t>(STAGES) * STAGE_BYTES + EPI_SCRATCH + (2 * STAGES + 4) * 8 + 16;
   static_assert(BN % 16 == 0 && BN >= 32 && BN <= 256, "invalid UMMA N");
@@ -693,7 +693,29 @@ extern "C" int b200_gemm_bf16(b200_ctx* ctx, const b200_gemm_desc* d, void* stre
         const char* e = getenv("B200_GEMM_PAIR_MIN");
         pair_min = (e && atoi(e) > 0) ? atoi(e) : ctx->sm_count / 2;
       }
-      if (pair_tiles < pair_min) config = B200_GEMM_1CTA_N128;
+      if (pair_tiles < pair_min) {
+        config = B200_GEMM_1CTA_N128;
+        // wave quantisation of the 128-row tiles: cost = waves x tile width.  SDXL's [2048, 1280] outputs are 160 tiles of
+        // 128 x 128 on 148 SMs (2 waves, the second one 8 % full); 128 x 160 tiles make it one wave.  B200_GEMM_WAVE_TUNE=0: off
+        static int wave_tune = -1;
+        if (wave_tune < 0) {
+          const char* e = getenv("B200_GEMM_WAVE_TUNE");
+          wave_tune = (e && e[0] == '0') ? 0 : 1;
+        }
+        if (wave_tune && !f32 && !d->trans_a) {
+          const long long mt = (d->M + 127) / 128;
+          auto cost = [&](int bn) {
+            const long long tiles = mt * ((d->N + bn - 1) / bn);
+            return ((tiles + ctx->sm_count - 1) / ctx->sm_count) * bn;
+          };
+          long long best = cost(128);
+          if (!d->trans_b && cost(160) < best) {
+            best = cost(160);
+            config = B200_GEMM_1CTA_N160;
+          }
+          if (cost(192) < best) config = B200_GEMM_1CTA_N192;
+        }
+      }
     }
   }
 
@@ -735,6 +757,8 @@ extern "C" int b200_gemm_bf16(b200_ctx* ctx, const b200_gemm_desc* d, void* stre
     case B200_GEMM_2CTA_N256: cg = 2; bn = 256; break;
     case B200_GEMM_1CTA_N128: cg = 1; bn = 128; break;
     case B200_GEMM_1CTA_N64: cg = 1; bn = 64; break;
+    case B200_GEMM_1CTA_N160: cg = 1; bn = 160; break;
+    case B200_GEMM_1CTA_N192: cg = 1; bn = 192; break;
     default: set_error("b200_gemm_bf16: unknown config %d", config); return B200_ERR_INVALID;
   }
   {
@@ -785,6 +809,9 @@ extern "C" int b200_gemm_bf16(b200_ctx* ctx, const b200_gemm_desc* d, void* stre
   B200_LAUNCH(1, 256, 4, 0, 1);
   B200_LAUNCH(1, 128, 6, 0, 0);
   B200_LAUNCH(1, 128, 6, 0, 1);
+  B200_LAUNCH(1, 160, 5, 0, 0);
+  B200_LAUNCH(1, 192, 5, 0, 0);
+  B200_LAUNCH(1, 192, 5, 0, 1);
   B200_LAUNCH(1, 64, 8, 0, 0);    // rank-side: Z = X A^T
   B200_LAUNCH(1, 64, 8, 0, 1);    // rank-side: T = dY B
   B200_LAUNCH(1, 64, 8, 1, 1);    // wgrad:     dB = dY^T Z, dA^T = X^T T

@@ -33,8 +33,9 @@ template <int RK, int TRANS>
 __global__ void __launch_bounds__(128) rank_simt_kernel(const bf16* __restrict__ X, int ldx, const bf16* __restrict__ Wt, int ldw,
                                                         bf16* __restrict__ out, int ldo, int M, int K, float alpha,
                                                         const float* __restrict__ row_alpha, int rows_per_sample) {
-  constexpr int R = RK == 16 ? 4 : 8;
+  constexpr int R = RK == 4 ? 8 : 4;
   constexpr int NV = R * RK;       // accumulators per lane (64 or 32)
+  constexpr int DEPTH = R == 4 ? 3 : 2;  // chunks of X in flight per lane (v1 had 1: 1.4 TB/s, latency-bound)
   constexpr int P = RK / 8 ? RK / 8 : 1;  // 16-byte parts of the live columns of one B_pack row (TRANS = 1; RK = 4: half a part)
   __shared__ __align__(16) uint4 wsm[2][RK * 32];  // chunk slice, lane-major: TRANS 0: [j][lane]; TRANS 1: [e][p][lane] (RK >= 8)
   pdl_grid_sync();
@@ -86,70 +87,76 @@ __global__ void __launch_bounds__(128) rank_simt_kernel(const bf16* __restrict__
   for (int i = 0; i < R; ++i)
 #pragma unroll
     for (int j = 0; j < RK / 2; ++j) acc[i][j] = make_float2(0.f, 0.f);
-  uint4 xn[R];
+  uint4 xq[DEPTH][R];
   stage(0, 0);
-  load_x(0, xn);
+#pragma unroll
+  for (int u = 0; u < DEPTH; ++u) load_x(u, xq[u]);  // (chunks past K load nothing and read as zeros)
   __syncthreads();
-  for (int c = 0; c < nchunk; ++c) {
-    const int b = c & 1;
-    float x[R][8];
+  for (int c0 = 0; c0 < nchunk; c0 += DEPTH) {
 #pragma unroll
-    for (int i = 0; i < R; ++i) {
-      const float2 a0 = unpack_bf16x2(xn[i].x), a1 = unpack_bf16x2(xn[i].y), a2 = unpack_bf16x2(xn[i].z), a3 = unpack_bf16x2(xn[i].w);
-      x[i][0] = a0.x; x[i][1] = a0.y; x[i][2] = a1.x; x[i][3] = a1.y; x[i][4] = a2.x; x[i][5] = a2.y; x[i][6] = a3.x; x[i][7] = a3.y;
-    }
-    if (c + 1 < nchunk) {
-      load_x(c + 1, xn);       // in flight while this chunk is computed
-      stage(c + 1, b ^ 1);     // buffer b ^ 1 was last read in iteration c - 1 (barrier at the end of it)
-    }
-    if (TRANS == 0) {
+    for (int u = 0; u < DEPTH; ++u) {
+      const int c = c0 + u;
+      if (c < nchunk) {  // block-uniform
+        const int b = c & 1;
+        float x[R][8];
 #pragma unroll
-      for (int jp = 0; jp < RK / 2; ++jp) {
-        const uint4 w0 = wsm[b][(2 * jp) * 32 + lane], w1 = wsm[b][(2 * jp + 1) * 32 + lane];
-        const uint32_t u0[4] = {w0.x, w0.y, w0.z, w0.w}, u1[4] = {w1.x, w1.y, w1.z, w1.w};
+        for (int i = 0; i < R; ++i) {
+          const float2 a0 = unpack_bf16x2(xq[u][i].x), a1 = unpack_bf16x2(xq[u][i].y), a2 = unpack_bf16x2(xq[u][i].z),
+                       a3 = unpack_bf16x2(xq[u][i].w);
+          x[i][0] = a0.x; x[i][1] = a0.y; x[i][2] = a1.x; x[i][3] = a1.y; x[i][4] = a2.x; x[i][5] = a2.y; x[i][6] = a3.x; x[i][7] = a3.y;
+        }
+        load_x(c + DEPTH, xq[u]);              // refill this slot: DEPTH chunks in flight while this one is computed
+        if (c + 1 < nchunk) stage(c + 1, b ^ 1);  // buffer b ^ 1 was last read in iteration c - 1 (barrier at the end of it)
+        if (TRANS == 0) {
 #pragma unroll
-        for (int eh = 0; eh < 4; ++eh) {
-          const float2 a = unpack_bf16x2(u0[eh]), bb = unpack_bf16x2(u1[eh]);  // (A[j][e], A[j][e+1]), (A[j+1][e], A[j+1][e+1])
-          const float2 p0 = make_float2(a.x, bb.x), p1 = make_float2(a.y, bb.y);
+          for (int jp = 0; jp < RK / 2; ++jp) {
+            const uint4 w0 = wsm[b][(2 * jp) * 32 + lane], w1 = wsm[b][(2 * jp + 1) * 32 + lane];
+            const uint32_t u0[4] = {w0.x, w0.y, w0.z, w0.w}, u1[4] = {w1.x, w1.y, w1.z, w1.w};
 #pragma unroll
-          for (int i = 0; i < R; ++i) {
-            acc[i][jp] = ffma2(make_float2(x[i][2 * eh], x[i][2 * eh]), p0, acc[i][jp]);
-            acc[i][jp] = ffma2(make_float2(x[i][2 * eh + 1], x[i][2 * eh + 1]), p1, acc[i][jp]);
+            for (int eh = 0; eh < 4; ++eh) {
+              const float2 a = unpack_bf16x2(u0[eh]), bb = unpack_bf16x2(u1[eh]);  // (A[j][e], A[j][e+1]), (A[j+1][e], A[j+1][e+1])
+              const float2 p0 = make_float2(a.x, bb.x), p1 = make_float2(a.y, bb.y);
+#pragma unroll
+              for (int i = 0; i < R; ++i) {
+                acc[i][jp] = ffma2(make_float2(x[i][2 * eh], x[i][2 * eh]), p0, acc[i][jp]);
+                acc[i][jp] = ffma2(make_float2(x[i][2 * eh + 1], x[i][2 * eh + 1]), p1, acc[i][jp]);
+              }
+            }
+          }
+        } else if (RK >= 8) {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+#pragma unroll
+            for (int p = 0; p < P; ++p) {
+              const uint4 w = wsm[b][(e * P + p) * 32 + lane];  // B_pack[k_e][8 p .. 8 p + 7]: rank pairs as packed words
+              const uint32_t uw[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                const float2 wp = unpack_bf16x2(uw[q]);
+#pragma unroll
+                for (int i = 0; i < R; ++i) acc[i][p * 4 + q] = ffma2(make_float2(x[i][e], x[i][e]), wp, acc[i][p * 4 + q]);
+              }
+            }
+          }
+        } else {
+#pragma unroll
+          for (int e2 = 0; e2 < 4; ++e2) {
+            const uint4 w = wsm[b][e2 * 32 + lane];  // rows e = 2 e2 (x, y) and 2 e2 + 1 (z, w)
+            const uint32_t uw[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+            for (int h = 0; h < 2; ++h)
+#pragma unroll
+              for (int q = 0; q < 2; ++q) {
+                const float2 wp = unpack_bf16x2(uw[h * 2 + q]);
+#pragma unroll
+                for (int i = 0; i < R; ++i)
+                  acc[i][q] = ffma2(make_float2(x[i][2 * e2 + h], x[i][2 * e2 + h]), wp, acc[i][q]);
+              }
           }
         }
-      }
-    } else if (RK >= 8) {
-#pragma unroll
-      for (int e = 0; e < 8; ++e) {
-#pragma unroll
-        for (int p = 0; p < P; ++p) {
-          const uint4 w = wsm[b][(e * P + p) * 32 + lane];  // B_pack[k_e][8 p .. 8 p + 7]: rank pairs as packed words
-          const uint32_t u[4] = {w.x, w.y, w.z, w.w};
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const float2 wp = unpack_bf16x2(u[q]);
-#pragma unroll
-            for (int i = 0; i < R; ++i) acc[i][p * 4 + q] = ffma2(make_float2(x[i][e], x[i][e]), wp, acc[i][p * 4 + q]);
-          }
-        }
-      }
-    } else {
-#pragma unroll
-      for (int e2 = 0; e2 < 4; ++e2) {
-        const uint4 w = wsm[b][e2 * 32 + lane];  // rows e = 2 e2 (x, y) and 2 e2 + 1 (z, w)
-        const uint32_t u[4] = {w.x, w.y, w.z, w.w};
-#pragma unroll
-        for (int h = 0; h < 2; ++h)
-#pragma unroll
-          for (int q = 0; q < 2; ++q) {
-            const float2 wp = unpack_bf16x2(u[h * 2 + q]);
-#pragma unroll
-            for (int i = 0; i < R; ++i)
-              acc[i][q] = ffma2(make_float2(x[i][2 * e2 + h], x[i][2 * e2 + h]), wp, acc[i][q]);
-          }
+        __syncthreads();  // buffer b free for chunk c + 2, buffer b ^ 1 complete for chunk c + 1
       }
     }
-    __syncthreads();  // buffer b free for chunk c + 2, buffer b ^ 1 complete for chunk c + 1
   }
   if (row0 >= M) return;
   // ---- reduce over the lanes: the (row, rank) accumulators are scattered, lane l ends with NV / 32 of the totals
@@ -208,7 +215,7 @@ extern "C" int b200_rank_gemm(b200_ctx* ctx, const void* X, int ldx, const void*
                    (reinterpret_cast<uintptr_t>(out) & 7u) == 0, "b200_rank_gemm: operand alignment");
   if (row_alpha) B200_REQUIRE(rows_per_sample > 0, "b200_rank_gemm: row_alpha needs rows_per_sample");
   const int RK = r_live <= 4 ? 4 : (r_live <= 8 ? 8 : 16);
-  const int R = RK == 16 ? 4 : 8;
+  const int R = RK == 4 ? 8 : 4;
   const int warps = (M + R - 1) / R;
   // 4 warps per block when that still gives every SM a block, else 2 (small M: more blocks in flight)
   const int wpb = (warps / 4 >= ctx->sm_count) ? 4 : 2;

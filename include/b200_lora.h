@@ -40,6 +40,8 @@ extern "C" {
 #define B200_GEMM_1CTA_N128 3
 #define B200_GEMM_1CTA_N64 4 /* skinny (rank-side) GEMM, optional split-K       */
 #define B200_GEMM_SKINNY_CLUSTER 5 /* N <= 64, bf16 out: split-K over a CTA cluster, DSMEM reduce */
+#define B200_GEMM_1CTA_N160 6 /* 128x160 / 128x192 tiles: AUTO picks them when 128x128 tiles would leave a nearly empty */
+#define B200_GEMM_1CTA_N192 7 /* second wave (e.g. SDXL's 2048 x 1280 outputs: 160 tiles on 148 SMs); N160: B K-major only */
 
 typedef struct b200_ctx b200_ctx;
 

@@ -38,6 +38,10 @@ CASES = [
     (512, 3072, 3072, 0, "auxin", 2), (1160, 1544, 1032, 64, "bias", 2), (384, 768, 512, 64, "bias", 3),
     (200, 48, 328, 0, "", 4), (4608, 64, 3072, 0, "alpha", 4),
     (4608, 3072, 3072, 64, "bias", 2), (4608, 3072, 15360, 64, "bias,gate,res", 2),
+    # 128 x 160 / 128 x 192 tiles (round 2: SDXL's 2048-token levels) explicitly, ragged edges, and through AUTO (config 0)
+    (2048, 1280, 1280, 64, "bias,res", 6), (2048, 1280, 5120, 64, "bias,res", 7), (200, 328, 264, 64, "bias", 6),
+    (1160, 1544, 1032, 64, "bias,gelu,auxout", 7), (2048, 1280, 1280, 64, "bias,res", 0), (2048, 10240, 1280, 64, "bias", 0),
+    (154, 1280, 2048, 64, "", 0),
 ]
 
 
@@ -78,7 +82,9 @@ def test_forward_nt(M, N, K0, K1, flags, config):
 
 
 @pytest.mark.parametrize("M,N,K0,K1,config", [(256, 256, 128, 0, 1), (200, 328, 264, 64, 1), (512, 3072, 3072, 64, 2),
-                                              (4608, 3072, 12288, 64, 2), (4608, 64, 3072, 0, 4), (384, 768, 512, 64, 3)])
+                                              (4608, 3072, 12288, 64, 2), (4608, 64, 3072, 0, 4), (384, 768, 512, 64, 3),
+                                              (2048, 1280, 1280, 64, 7), (200, 328, 264, 64, 7), (2048, 1280, 10240, 64, 0),
+                                              (2048, 5120, 1280, 64, 0)])
 def test_dgrad_trans_b(M, N, K0, K1, config):
     """dX = dY W: B operands stored [K, N] (N contiguous) and consumed MN-major, no transposed copy."""
     from ai_toolkit_b200 import cabi
