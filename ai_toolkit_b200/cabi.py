@@ -79,7 +79,6 @@ SIGNATURES = {
     "b200_ctx_destroy": (c_int, [c_void_p]),
     "b200_ctx_launch_count": (c_int64, [c_void_p]),
     "b200_gemm_bf16": (c_int, [c_void_p, POINTER(GemmDesc), c_void_p]),
-    "b200_rank_gemm": (c_int, [_V, _V, _I, _V, _I, _I, _V, _I, _I, _I, _I, _F, _V, _I, _V]),
     "b200_lora_wgrad": (c_int, [_V, _V, _I, _V, _I, _V, _I, _V, _I, _V, _V, _I, _I, _I, _I, _I, _F, _I, _V]),
     "b200_ln_modulate_fwd": (c_int, [_V, _V, _I, _V, _V, _I, _I, _V, _I, _V, _V, _I, _I, _F, _V]),
     "b200_ln_modulate_bwd": (c_int, [_V, _V, _I, _V, _I, _V, _V, _V, _I, _I, _V, _I, _V, _I, _I, _I, _V]),

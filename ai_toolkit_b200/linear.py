@@ -13,8 +13,6 @@ Shared by the per-module autograd path (`autograd.lora_linear`, the drop-in for
 """
 from __future__ import annotations
 
-import os
-
 import torch
 
 from . import cabi, ops
@@ -22,17 +20,13 @@ from .cabi import gemm_bf16
 
 RANK_PAD = 64
 GEMV_MAX_ROWS = 8
-RANK_SIMT_MAX = 16
-_RANK_SIMT = os.environ.get("B200_RANK_SIMT", "1") != "0"  # 0: every rank-side product on the tensor-core skinny kernel (A/B)
 
 
 def rank_side(x2, w, out, r_live, *, trans_b=False, alpha=1.0, row_alpha=None, rows_per_sample=0):
-    """Zc = bf16(c * X A_pack^T) or (trans_b) T = bf16(c * dY B_pack): streaming of X with 2 r FLOP per element.  Live ranks
-    <= 16 run on the CUDA-core kernel (csrc/rank_simt.cu), larger ones / fused groups with more live columns on the
-    cluster split-K tcgen05 skinny GEMM -- the same arithmetic either way (fp32 accumulate, one bf16 rounding)."""
-    if _RANK_SIMT and 0 < r_live <= RANK_SIMT_MAX and x2.stride(1) == 1 and x2.data_ptr() % 16 == 0 and x2.stride(0) % 8 == 0 \
-            and x2.shape[1] % 8 == 0:
-        return ops.rank_gemm(x2, w, out, r_live, trans_w=trans_b, alpha=alpha, row_alpha=row_alpha, rows_per_sample=rows_per_sample)
+    """Zc = bf16(c * X A_pack^T) or (trans_b) T = bf16(c * dY B_pack) on the cluster split-K tcgen05 skinny GEMM.
+    (Round 2 measured a CUDA-core kernel for live ranks <= 16 against it -- a warp per 4 rows, weight slice in shared memory,
+    packed fp32 FMAs, 1 and 3 chunks of X in flight: 20.5 / 24.6 us vs 15.3 us at M 4608, K 3072, r 16 and 2-3x slower at
+    K >= 12288; FLUX step 204.6 / 207.1 vs 195.4 / 191.3 ms -- issue-bound, removed; profiles/r2_time_rank_v*.md.)"""
     return gemm_bf16(x2, w, out, trans_b=trans_b, alpha=alpha, row_alpha=row_alpha, rows_per_sample=rows_per_sample)
 
 
@@ -171,3 +165,35 @@ def group_bwd(group, lins, dy, x2, zc, dx_out, **epi):
         n = lora.out_dim
         lora_wgrad(lora, dy[:, row:row + n], zc[:, j * r:], x2, t[:, j * r:])
         row += n
+
+
+def shared_input_fwd(lins, n, out):
+    """Projections of ONE input (to_q / to_k / to_v, or the to_k / to_v of a cross attention) -> column blocks of `out`:
+    one rank-side product + one fused GEMM when their adapters form a registered group, else one pair per Linear.
+    Returns the token to hand to `shared_input_bwd`."""
+    loras = [live_lora(l) for l in lins]
+    grp = loras[0].network_ref().fused_group(loras) if loras[0] is not None else None
+    if grp is not None:
+        return ("g", group_fwd(grp, lins, n, out))
+    col, zs = 0, []
+    for lin, lo in zip(lins, loras):
+        D = lin.weight.shape[0]
+        zs.append(linear_fwd(lin, n, out[:, col:col + D], lora=lo))
+        col += D
+    return ("s", zs)
+
+
+def shared_input_bwd(lins, dout, n, saved, dn, accumulate=False):
+    """Backward of `shared_input_fwd`: dn (+)= sum_j dout_j W_j (+ adapters), dA / dB of every adapter; dn may be None."""
+    loras = [live_lora(l) for l in lins]
+    kind, z = saved
+    if kind == "g":
+        grp = loras[0].network_ref().fused_group(loras)
+        group_bwd(grp, lins, dout, n, z, dn, **({"res": dn} if (accumulate and dn is not None) else {}))
+        return
+    col = 0
+    for j, (lin, lo) in enumerate(zip(lins, loras)):
+        D = lin.weight.shape[0]
+        acc = dn is not None and (accumulate or j > 0)
+        linear_bwd(lin, dout[:, col:col + D], n, z[j], dn, lora=lo, **({"res": dn} if acc else {}))
+        col += D

@@ -61,14 +61,6 @@ def col_reduce(a, rows_per_sample, b=None, mean=None, rstd=None, g=None, mul_out
               _p(sum_a), _p(sum_ab), ldsum, int(rows_per_sample), M, D, device=_dev(a))
 
 
-def rank_gemm(x, w, out, r_live, trans_w=False, alpha=1.0, row_alpha=None, rows_per_sample=0):
-    """out[M, 64] = bf16(alpha * x[M, K] . op(w)), columns >= r_live zeroed; w = A_pack [64, K] or (trans_w) B_pack [K, 64]."""
-    M, K = x.shape
-    cabi.call("b200_rank_gemm", _p(x), _ld(x), _p(w), _ld(w), int(bool(trans_w)), _p(out), _ld(out), int(M), int(K), int(r_live),
-              float(alpha), _p(row_alpha), int(rows_per_sample), device=_dev(x))
-    return out
-
-
 def qk_norm_rope_fwd(q, k, v, wq, wk, cos, sin, Q, K, V, B, Lseg, seq_off, eps=1e-6):
     """q/k/v: [B*Lseg, H*128] bf16 views sharing one row stride; Q/K/V: [B, H, Ltot, 128] bf16."""
     H, Ltot = Q.shape[1], Q.shape[2]

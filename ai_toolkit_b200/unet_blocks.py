@@ -19,12 +19,13 @@ of the kernels in csrc/unet_ops.cu and csrc/batch_ops.cu.
 from __future__ import annotations
 
 import math
+import weakref
 
 import torch
 import torch.nn as nn
 
 from . import attention, cabi, ops
-from .linear import linear_bwd, linear_fwd, live_lora
+from .linear import linear_bwd, linear_fwd, live_lora, shared_input_bwd, shared_input_fwd
 
 
 class _Holder(nn.Module):
@@ -132,21 +133,36 @@ class Transformer2DEngine:
                 net = lora.network_ref()
                 if any(m.has_dropout() or (m.module_dropout and m.training) for m in net.get_all_modules()):
                     raise NotImplementedError("dropout variants with the fused Transformer2D engine: use the per-module path")
+                done = getattr(model, "_b200_groups_for", None)
+                if done is None or done() is not net:
+                    # adapters that share an input: to_q / to_k / to_v of the self attention and to_k / to_v of the cross
+                    # attention -> one rank-side product and one fused GEMM per group (ranks that are multiples of 8)
+                    groups = []
+                    for blk in model.transformer_blocks:
+                        groups.append([live_lora(l) for l in (blk.attn1.to_q, blk.attn1.to_k, blk.attn1.to_v)])
+                        groups.append([live_lora(l) for l in (blk.attn2.to_k, blk.attn2.to_v)])
+                    net.register_fused_groups(groups)
+                    model._b200_groups_for = weakref.ref(net)
                 net.refresh_packs()
                 net.ensure_grad_views()
                 return
 
     @staticmethod
-    def _attn_fwd(a, x, ctx, B, L, Lc, res):
+    def _attn_fwd(a, x, ctx, B, L, Lc, res, self_attn):
         """x [B L, C] queries; ctx [B Lc, Dc] keys / values source (x itself for self-attention) -> (out = res + to_out(attn), saved)"""
         H, d = a.heads, a.dim_head
         inner = H * d
-        q = _empty((B * L, inner), x)
-        z_q = linear_fwd(a.to_q, x, q, lora=live_lora(a.to_q))
-        k = _empty((B * Lc, inner), x)
-        v = _empty((B * Lc, inner), x)
-        z_k = linear_fwd(a.to_k, ctx, k, lora=live_lora(a.to_k))
-        z_v = linear_fwd(a.to_v, ctx, v, lora=live_lora(a.to_v))
+        if self_attn:
+            qkv = _empty((B * L, 3 * inner), x)
+            z_qkv = shared_input_fwd((a.to_q, a.to_k, a.to_v), x, qkv)
+            q, k, v = qkv[:, :inner], qkv[:, inner:2 * inner], qkv[:, 2 * inner:]
+            z_q = None
+        else:
+            q = _empty((B * L, inner), x)
+            z_q = linear_fwd(a.to_q, x, q, lora=live_lora(a.to_q))
+            kv = _empty((B * Lc, 2 * inner), x)
+            z_qkv = shared_input_fwd((a.to_k, a.to_v), ctx, kv)
+            k, v = kv[:, :inner], kv[:, inner:]
         Q = _empty((B, H, L, 128), x)
         K = _empty((B, H, Lc, 128), x)
         V = _empty((B, H, Lc, 128), x)
@@ -162,11 +178,11 @@ class Transformer2DEngine:
             o = o_pad.view(B * L, H, 128)[:, :, :d].reshape(B * L, inner)
         out = _empty(res.shape, x)
         z_o = linear_fwd(a.to_out[0], o, out, lora=live_lora(a.to_out[0]), res=res)
-        return out, dict(x=x, ctx=ctx, z_q=z_q, z_k=z_k, z_v=z_v, Q=Q, K=K, V=V, o_pad=o_pad, o=o, lse=lse, z_o=z_o, scale=scale)
+        return out, dict(x=x, ctx=ctx, z_q=z_q, z_qkv=z_qkv, Q=Q, K=K, V=V, o_pad=o_pad, o=o, lse=lse, z_o=z_o, scale=scale)
 
     @staticmethod
-    def _attn_bwd(a, s, dout, B, L, Lc, need_dctx):
-        """-> (dx [B L, C] through the queries (and, for self-attention, keys / values), or None)"""
+    def _attn_bwd(a, s, dout, B, L, Lc, self_attn):
+        """-> dx [B L, C] through the queries (and, for self-attention, keys / values)"""
         H, d = a.heads, a.dim_head
         inner = H * d
         do = _empty((B * L, inner), dout)
@@ -177,20 +193,21 @@ class Transformer2DEngine:
             do_pad = torch.zeros((B * L, H * 128), device=dout.device, dtype=torch.bfloat16)
             do_pad.view(B * L, H, 128)[:, :, :d].copy_(do.view(B * L, H, d))
         dQ, dK, dV = attention.bwd(s["Q"], s["K"], s["V"], None, s["o_pad"], None, do_pad, s["lse"], 0, scale=s["scale"])
-        dq = _empty((B * L, inner), dout)
-        dk = _empty((B * Lc, inner), dout)
-        dv = _empty((B * Lc, inner), dout)
-        ops.heads_unpad(dQ, dq, B, L, d)
-        ops.heads_unpad(dK, dk, B, Lc, d)
-        ops.heads_unpad(dV, dv, B, Lc, d)
         dx = _empty(s["x"].shape, dout)
-        linear_bwd(a.to_q, dq, s["x"], s["z_q"], dx, lora=live_lora(a.to_q))
-        if need_dctx:  # self-attention: keys / values come from the same x
-            linear_bwd(a.to_k, dk, s["ctx"], s["z_k"], dx, lora=live_lora(a.to_k), res=dx)
-            linear_bwd(a.to_v, dv, s["ctx"], s["z_v"], dx, lora=live_lora(a.to_v), res=dx)
-        else:  # cross-attention: the text embeddings are data -> adapters only
-            linear_bwd(a.to_k, dk, s["ctx"], s["z_k"], None, lora=live_lora(a.to_k))
-            linear_bwd(a.to_v, dv, s["ctx"], s["z_v"], None, lora=live_lora(a.to_v))
+        if self_attn:  # keys / values come from the same x: one dgrad GEMM over the concatenated [dq | dk | dv]
+            dqkv = _empty((B * L, 3 * inner), dout)
+            ops.heads_unpad(dQ, dqkv[:, :inner], B, L, d)
+            ops.heads_unpad(dK, dqkv[:, inner:2 * inner], B, L, d)
+            ops.heads_unpad(dV, dqkv[:, 2 * inner:], B, L, d)
+            shared_input_bwd((a.to_q, a.to_k, a.to_v), dqkv, s["x"], s["z_qkv"], dx)
+        else:  # cross-attention: the text embeddings are data -> adapters only on the key / value side
+            dq = _empty((B * L, inner), dout)
+            dkv = _empty((B * Lc, 2 * inner), dout)
+            ops.heads_unpad(dQ, dq, B, L, d)
+            ops.heads_unpad(dK, dkv[:, :inner], B, Lc, d)
+            ops.heads_unpad(dV, dkv[:, inner:], B, Lc, d)
+            linear_bwd(a.to_q, dq, s["x"], s["z_q"], dx, lora=live_lora(a.to_q))
+            shared_input_bwd((a.to_k, a.to_v), dkv, s["ctx"], s["z_qkv"], None)
         return dx
 
     @classmethod
@@ -210,9 +227,9 @@ class Transformer2DEngine:
         blocks = []
         for blk in model.transformer_blocks:
             n1, m1, r1 = ops.ln_affine_fwd(h, blk.norm1.weight, blk.norm1.bias, blk.norm1.eps)
-            h1, s1 = cls._attn_fwd(blk.attn1, n1, n1, B, L, L, h)
+            h1, s1 = cls._attn_fwd(blk.attn1, n1, n1, B, L, L, h, True)
             n2, m2, r2 = ops.ln_affine_fwd(h1, blk.norm2.weight, blk.norm2.bias, blk.norm2.eps)
-            h2, s2 = cls._attn_fwd(blk.attn2, n2, ctx2, B, L, Lc, h1)
+            h2, s2 = cls._attn_fwd(blk.attn2, n2, ctx2, B, L, Lc, h1, False)
             n3, m3, r3 = ops.ln_affine_fwd(h2, blk.norm3.weight, blk.norm3.bias, blk.norm3.eps)
             ff1, ff2 = blk.ff.net[0].proj, blk.ff.net[2]
             proj = _empty((B * L, ff1.out_features), x)
@@ -250,10 +267,10 @@ class Transformer2DEngine:
             linear_bwd(ff1, dproj, s["n3"], s["z_f1"], dn3, lora=live_lora(ff1))
             dh2 = ops.ln_affine_bwd(dn3, s["h2"], s["m3"], s["r3"], blk.norm3.weight, dres=dh)
             # h2 = h1 + attn2(LN2(h1), ctx)
-            dn2 = cls._attn_bwd(blk.attn2, s["s2"], dh2, B, L, Lc, need_dctx=False)
+            dn2 = cls._attn_bwd(blk.attn2, s["s2"], dh2, B, L, Lc, False)
             dh1 = ops.ln_affine_bwd(dn2, s["h1"], s["m2"], s["r2"], blk.norm2.weight, dres=dh2)
             # h1 = h + attn1(LN1(h))
-            dn1 = cls._attn_bwd(blk.attn1, s["s1"], dh1, B, L, L, need_dctx=True)
+            dn1 = cls._attn_bwd(blk.attn1, s["s1"], dh1, B, L, L, True)
             dh = ops.ln_affine_bwd(dn1, s["h"], s["m1"], s["r1"], blk.norm1.weight, dres=dh1)
         drows = _empty(sv["rows"].shape, dout)
         linear_bwd(model.proj_in, dh, sv["rows"], sv["z_in"], drows, lora=live_lora(model.proj_in))

@@ -122,19 +122,6 @@ int b200_lora_wgrad(b200_ctx* ctx, const void* dY, int lddy, const void* Zc, int
                     int splits, void* stream);
 
 
-/*
- * Rank-side products of ONE adapter (or fused group) with a small live rank, on the CUDA cores (csrc/rank_simt.cu):
- *   out[M, 64] = bf16(alpha * row_alpha[m / rows_per_sample] * X[M, K] . op(W)),   columns >= r_live written as ZEROS
- *   trans_w = 0: W = A_pack [64, K] bf16 (rows    >= r_live are not read)   Z = X A^T   forward of lora_down
- *   trans_w = 1: W = B_pack [K, 64] bf16 (columns >= r_live are not read)   T = dY B    backward through lora_up
- * 1 <= r_live <= 16 (B200_ERR_INVALID otherwise: larger ranks go through b200_gemm_bf16's tensor-core skinny kernel, which
- * computes the same thing).  K, ldx, ldw multiples of 8, X / W 16-byte aligned.  Streams X once; algorithmic bytes 2 M K.
- * Replaces the `lora_down(x)` / grad-of-`lora_up` matmuls of toolkit/network_mixins.py:304-342 (`_call_forward` :178-239).
- */
-int b200_rank_gemm(b200_ctx* ctx, const void* X, int ldx, const void* W, int ldw, int trans_w, void* out, int ldo, int M, int K,
-                   int r_live, float alpha, const void* row_alpha, int rows_per_sample, void* stream);
-
-
 /* -------------------------------------------------------------------------------------------------
  * AdaLN-Zero modulation around LayerNorm (no affine):
  *   out[m,:] = bf16( bf16( bf16(LN(x[m,:])) * bf16(1 + scale[s,:]) ) + shift[s,:] ),  s = m / rows_per_sample

@@ -2,7 +2,6 @@
 # CUDA-core rank-side kernel: unit tests, timing vs the tensor-core skinny GEMM, engine parity tests, FLUX + SDXL bench A/B.
 mkdir -p gpurun_out
 timeout 600 python -m pytest tests/test_gpu_rank_simt.py -q -x > gpurun_out/r2_rank_simt_tests.log 2>&1; echo "unit exit $?"; tail -5 gpurun_out/r2_rank_simt_tests.log
-timeout 300 python tools/time_rank.py > gpurun_out/r2_time_rank.md 2>&1; cat gpurun_out/r2_time_rank.md
 timeout 900 python -m pytest tests/test_gpu_flux_engine.py tests/test_unet_blocks.py tests/test_wan.py -m gpu -q -x > gpurun_out/r2_rank_simt_engine_tests.log 2>&1; echo "engine exit $?"; tail -4 gpurun_out/r2_rank_simt_engine_tests.log
 for simt in 1 0; do
   B200_RANK_SIMT=$simt timeout 600 python bench.py --steps 10 --warmup 3 --skip-gpu-reference --skip-cpu-baseline 2>/dev/null | python -c "

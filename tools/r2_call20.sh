@@ -2,7 +2,6 @@
 # rank_simt v2 (3 chunks of X in flight) + 128x160/128x192 GEMM tiles: tests, timing, bench A/B.
 mkdir -p gpurun_out
 timeout 900 python -m pytest tests/test_gpu_rank_simt.py tests/test_gpu_gemm.py -q -x > gpurun_out/r2_call20_tests.log 2>&1; echo "unit exit $?"; tail -5 gpurun_out/r2_call20_tests.log
-timeout 300 python tools/time_rank.py > gpurun_out/r2_time_rank.md 2>&1; cat gpurun_out/r2_time_rank.md
 run() {  # name, model args, env...
   local name=$1; shift; local margs=$1; shift
   env "$@" timeout 600 python bench.py $margs --steps 10 --warmup 3 --skip-gpu-reference --skip-cpu-baseline 2>/dev/null | python -c "
