@@ -19,19 +19,19 @@ def _p(t):
     return None if t is None else c_void_p(t.data_ptr())
 
 
-def fwd(Q, K, V, o0, o1, split, scale=None):
+def fwd(Q, K, V, o0, o1, split, scale=None, head_live=128):
     """-> lse [B, H, L] fp32 (natural log).  o0 [B*split, ld0] / o1 [B*(L-split), ld1] bf16 views (first H*128 cols)."""
     B, H, L, Dh = Q.shape
     Lk = K.shape[2]  # != L: cross attention (Wan2.1 text cross-attention)
     lse = torch.empty((B, H, L), device=Q.device, dtype=torch.float32)
     ld0 = int(o0.stride(0)) if o0 is not None else 0
     ld1 = int(o1.stride(0))
-    cabi.call("b200_attn_fwd_x", _p(Q), _p(K), _p(V), _p(o0), ld0, _p(o1), ld1, _p(lse), int(B), int(H), int(L), int(Lk),
-              int(split), float(1.0 / math.sqrt(Dh) if scale is None else scale), device=Q.device.index)
+    cabi.call("b200_attn_fwd_xd", _p(Q), _p(K), _p(V), _p(o0), ld0, _p(o1), ld1, _p(lse), int(B), int(H), int(L), int(Lk),
+              int(split), float(1.0 / math.sqrt(Dh) if scale is None else scale), int(head_live), device=Q.device.index)
     return lse
 
 
-def bwd(Q, K, V, o0, o1, do0, do1, lse, split, scale=None):
+def bwd(Q, K, V, o0, o1, do0, do1, lse, split, scale=None, head_live=128):
     """-> dQ, dK, dV [B, H, L, 128] bf16."""
     B, H, L, Dh = Q.shape
     dQ = torch.empty_like(Q)
@@ -43,7 +43,7 @@ def bwd(Q, K, V, o0, o1, do0, do1, lse, split, scale=None):
     ld1 = int(o1.stride(0))
     ldd0 = int(do0.stride(0)) if do0 is not None else 0
     ldd1 = int(do1.stride(0))
-    cabi.call("b200_attn_bwd_x", _p(Q), _p(K), _p(V), _p(o0), ld0, _p(o1), ld1, _p(do0), ldd0, _p(do1), ldd1, _p(lse),
+    cabi.call("b200_attn_bwd_xd", _p(Q), _p(K), _p(V), _p(o0), ld0, _p(o1), ld1, _p(do0), ldd0, _p(do1), ldd1, _p(lse),
               _p(delta), _p(dOh), _p(dQ), _p(dK), _p(dV), int(B), int(H), int(L), int(K.shape[2]), int(split),
-              float(1.0 / math.sqrt(Dh) if scale is None else scale), device=Q.device.index)
+              float(1.0 / math.sqrt(Dh) if scale is None else scale), int(head_live), device=Q.device.index)
     return dQ, dK, dV

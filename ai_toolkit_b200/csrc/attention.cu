@@ -898,13 +898,20 @@ static int attn_maps(b200_ctx* ctx, const void* p, uint64_t rows, uint32_t box_r
 
 extern "C" int b200_attn_fwd(b200_ctx* ctx, const void* Q, const void* K, const void* V, void* o0, int ld0, void* o1, int ld1,
                              void* lse, int B, int H, int L, int split, float scale, void* stream) {
-  return b200_attn_fwd_x(ctx, Q, K, V, o0, ld0, o1, ld1, lse, B, H, L, L, split, scale, stream);
+  return b200_attn_fwd_xd(ctx, Q, K, V, o0, ld0, o1, ld1, lse, B, H, L, L, split, scale, 128, stream);
 }
 
 extern "C" int b200_attn_fwd_x(b200_ctx* ctx, const void* Q, const void* K, const void* V, void* o0, int ld0, void* o1,
                                int ld1, void* lse, int B, int H, int L, int Lk, int split, float scale, void* stream) {
+  return b200_attn_fwd_xd(ctx, Q, K, V, o0, ld0, o1, ld1, lse, B, H, L, Lk, split, scale, 128, stream);
+}
+
+extern "C" int b200_attn_fwd_xd(b200_ctx* ctx, const void* Q, const void* K, const void* V, void* o0, int ld0, void* o1,
+                                int ld1, void* lse, int B, int H, int L, int Lk, int split, float scale, int head_live,
+                                void* stream) {
   int rc = check_ctx(ctx);
   if (rc) return rc;
+  B200_REQUIRE(head_live == 128 || head_live == 64, "b200_attn_fwd: head_live %d (128, or 64 = zero-padded half heads)", head_live);
   B200_REQUIRE(Q && K && V && o1 && lse && B > 0 && H > 0 && L > 0 && Lk > 0, "b200_attn_fwd: bad args");
   B200_REQUIRE(split >= 0 && split <= L && (split == 0 || o0 != nullptr), "b200_attn_fwd: bad split %d", split);
   B200_REQUIRE(ld1 % 8 == 0 && (split == 0 || ld0 % 8 == 0), "b200_attn_fwd: output leading dims must be multiples of 8");
@@ -930,7 +937,8 @@ extern "C" int b200_attn_fwd_x(b200_ctx* ctx, const void* Q, const void* K, cons
     if (e && atoi(e) >= 1 && atoi(e) <= 7) variant = atoi(e);
     configured = true;
   }
-  AttnFwdArgs a{(bf16*)o0, ld0, (bf16*)o1, ld1, (float*)lse, B, H, L, split, scale, Lk};
+  AttnFwdArgs a{(bf16*)o0, ld0, (bf16*)o1, ld1, (float*)lse, B, H, L, split, scale, Lk, head_live};
+  B200_REQUIRE(head_live == 128 || variant == 6, "b200_attn_fwd: head_live 64 needs forward variant 6 (the default)");
   B200_REQUIRE(Lk == L || variant >= 3, "b200_attn_fwd: cross attention (Lk != L) needs forward variant 3, 4 or 5");
   if (variant == 7) {
     if ((rc = attn_fwd_pp3_launch(tq, tk, tv, a, reinterpret_cast<cudaStream_t>(stream)))) return rc;
@@ -966,16 +974,25 @@ extern "C" int b200_attn_bwd(b200_ctx* ctx, const void* Q, const void* K, const 
                              const void* o1, int ld1, const void* do0, int ldd0, const void* do1, int ldd1, const void* lse,
                              void* delta, void* dOh, void* dQ, void* dK, void* dV, int B, int H, int L, int split,
                              float scale, void* stream) {
-  return b200_attn_bwd_x(ctx, Q, K, V, o0, ld0, o1, ld1, do0, ldd0, do1, ldd1, lse, delta, dOh, dQ, dK, dV, B, H, L, L, split,
-                         scale, stream);
+  return b200_attn_bwd_xd(ctx, Q, K, V, o0, ld0, o1, ld1, do0, ldd0, do1, ldd1, lse, delta, dOh, dQ, dK, dV, B, H, L, L, split,
+                          scale, 128, stream);
 }
 
 extern "C" int b200_attn_bwd_x(b200_ctx* ctx, const void* Q, const void* K, const void* V, const void* o0, int ld0,
                                const void* o1, int ld1, const void* do0, int ldd0, const void* do1, int ldd1, const void* lse,
                                void* delta, void* dOh, void* dQ, void* dK, void* dV, int B, int H, int L, int Lk, int split,
                                float scale, void* stream) {
+  return b200_attn_bwd_xd(ctx, Q, K, V, o0, ld0, o1, ld1, do0, ldd0, do1, ldd1, lse, delta, dOh, dQ, dK, dV, B, H, L, Lk, split,
+                          scale, 128, stream);
+}
+
+extern "C" int b200_attn_bwd_xd(b200_ctx* ctx, const void* Q, const void* K, const void* V, const void* o0, int ld0,
+                                const void* o1, int ld1, const void* do0, int ldd0, const void* do1, int ldd1, const void* lse,
+                                void* delta, void* dOh, void* dQ, void* dK, void* dV, int B, int H, int L, int Lk, int split,
+                                float scale, int head_live, void* stream) {
   int rc = check_ctx(ctx);
   if (rc) return rc;
+  B200_REQUIRE(head_live == 128 || head_live == 64, "b200_attn_bwd: head_live %d (128, or 64 = zero-padded half heads)", head_live);
   B200_REQUIRE(Q && K && V && o1 && do1 && lse && delta && dOh && dQ && dK && dV, "b200_attn_bwd: null argument");
   B200_REQUIRE(B > 0 && H > 0 && L > 0 && Lk > 0 && split >= 0 && split <= L && (split == 0 || (o0 && do0)), "b200_attn_bwd: bad shape");
   B200_REQUIRE(ld1 % 4 == 0 && ldd1 % 4 == 0 && ld0 % 4 == 0 && ldd0 % 4 == 0, "b200_attn_bwd: leading dims %% 4");
@@ -1014,8 +1031,10 @@ extern "C" int b200_attn_bwd_x(b200_ctx* ctx, const void* Q, const void* K, cons
     const char* e = getenv("B200_ATTN_BWD_DBG");
     bwd_dbg = e ? atoi(e) : 0;
   }
-  AttnBwdArgs akv{(const float*)lse, (const float*)delta, nullptr, nullptr, (bf16*)dV, (bf16*)dK, Lk, scale, L, bwd_dbg};
-  AttnBwdArgs aq{(const float*)lse, (const float*)delta, (const bf16*)Q, (const bf16*)dOh, (bf16*)dQ, nullptr, L, scale, Lk, bwd_dbg};
+  AttnBwdArgs akv{(const float*)lse, (const float*)delta, nullptr, nullptr, (bf16*)dV, (bf16*)dK, Lk, scale, L, bwd_dbg, head_live};
+  AttnBwdArgs aq{(const float*)lse, (const float*)delta, (const bf16*)Q, (const bf16*)dOh, (bf16*)dQ, nullptr, L, scale, Lk, bwd_dbg, head_live};
+  B200_REQUIRE(head_live == 128 || ((variant == 2 || variant == 3) && bwd_dbg != 3),
+               "b200_attn_bwd: head_live 64 needs backward variant 2 (the default) or 3");
   B200_REQUIRE(Lk == L || variant == 2 || variant == 3, "b200_attn_bwd: cross attention (Lk != L) needs backward variant 2 or 3");
   if (variant >= 2) {
     if ((rc = attn_bwd_r2_launch(variant, k128, v128, q64, d64, q128, d128, k64, v64, akv, aq, B, H, st))) return rc;

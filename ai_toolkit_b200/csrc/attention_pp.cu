@@ -378,33 +378,37 @@ attn_fwd_pp2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
 
   if (warp == 0) {
     if (lane == 0) {
-      mbar_arrive_expect_tx(q_full, 65536);
+      const bool full_d = g.dlive != 64;  // dlive 64: the second 64 head-dim columns are zero padding, never loaded / multiplied
+      mbar_arrive_expect_tx(q_full, full_d ? 65536 : 32768);
 #pragma unroll
       for (int t = 0; t < 2; ++t) {
         const int qrow = static_cast<int>(row_base + q0 + t * 128);
         tma_load_2d(sQ + t * 32768, &tmQ, q_full, 0, qrow);
-        tma_load_2d(sQ + t * 32768 + 16384, &tmQ, q_full, 64, qrow);
+        if (full_d) tma_load_2d(sQ + t * 32768 + 16384, &tmQ, q_full, 64, qrow);
       }
       for (int j = 0; j < n_kv; ++j) {
         const int s = j & 1;
         const uint32_t ph = (j >> 1) & 1;
         const int kvrow = static_cast<int>(kv_base + j * 128);
         mbar_wait(&k_empty[s], ph ^ 1u, 30);
-        mbar_arrive_expect_tx(&k_full[s], 32768);
+        mbar_arrive_expect_tx(&k_full[s], full_d ? 32768 : 16384);
         tma_load_2d(sK + s * 32768, &tmK, &k_full[s], 0, kvrow);
-        tma_load_2d(sK + s * 32768 + 16384, &tmK, &k_full[s], 64, kvrow);
+        if (full_d) tma_load_2d(sK + s * 32768 + 16384, &tmK, &k_full[s], 64, kvrow);
         mbar_wait(&v_empty[s], ph ^ 1u, 31);
-        mbar_arrive_expect_tx(&v_full[s], 32768);
+        mbar_arrive_expect_tx(&v_full[s], full_d ? 32768 : 16384);
 #pragma unroll
         for (int jc = 0; jc < 2; ++jc)
 #pragma unroll
           for (int ih = 0; ih < 2; ++ih)
-            tma_load_2d(sV + s * 32768 + (jc * 2 + ih) * 8192, &tmV, &v_full[s], jc * 64, kvrow + ih * 64);
+            if (jc == 0 || full_d) tma_load_2d(sV + s * 32768 + (jc * 2 + ih) * 8192, &tmV, &v_full[s], jc * 64, kvrow + ih * 64);
       }
     }
   } else if (warp == 1) {
     constexpr uint32_t idS = umma_idesc_bf16(128, 128, 0, 0);
-    constexpr uint32_t idPV = umma_idesc_bf16(128, 128, 0, 1);
+    constexpr uint32_t idPV128 = umma_idesc_bf16(128, 128, 0, 1);
+    constexpr uint32_t idPV64 = umma_idesc_bf16(128, 64, 0, 1);  // N = 64: the first MN-major atom of V = head-dim columns 0..63
+    const bool full_d = g.dlive != 64;
+    const uint32_t idPV = full_d ? idPV128 : idPV64;
     mbar_wait(q_full, 0, 32);
     const uint64_t dQ0 = umma_desc_sw128(smem_u32(sQ), 1024, 16);
     const uint64_t dK0 = umma_desc_sw128(smem_u32(sK), 1024, 16);
@@ -414,8 +418,11 @@ attn_fwd_pp2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       const uint64_t dk = dK0 + static_cast<uint64_t>((j & 1) * (32768 >> 4));
       {  // one elect for the 8 k-steps (attn_common.cuh): both operands K-major, halves of 64 head-dim columns 16 KB apart
         constexpr int HH = 16384 >> 4;
-        umma_bf16_ss_w_x8<2, 4, 6, HH, HH + 2, HH + 4, HH + 6, 2, 4, 6, HH, HH + 2, HH + 4, HH + 6>(
-            tmem_base + static_cast<uint32_t>(t) * 128u, dq, dk, idS, 0u);
+        if (full_d)
+          umma_bf16_ss_w_x8<2, 4, 6, HH, HH + 2, HH + 4, HH + 6, 2, 4, 6, HH, HH + 2, HH + 4, HH + 6>(
+              tmem_base + static_cast<uint32_t>(t) * 128u, dq, dk, idS, 0u);
+        else  // the contraction over the zero half contributes nothing
+          umma_bf16_ss_w_x4<2, 4, 6, 2, 4, 6>(tmem_base + static_cast<uint32_t>(t) * 128u, dq, dk, idS, 0u);
       }
       umma_commit_w(&s_full[t]);
     };
@@ -580,8 +587,13 @@ attn_fwd_pp2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
 #pragma unroll 1
     for (int c = 0; c < 4; ++c) {  // tcgen05.ld is warp-collective: every lane loads, only live rows store
       uint32_t o[32];
-      tmem_ld_32x32(tO + c * 32, o);
-      tmem_ld_wait();
+      if (g.dlive == 64 && c >= 2) {  // padded head-dim columns: the accumulator was never written there -> exact zeros
+#pragma unroll
+        for (int i = 0; i < 32; ++i) o[i] = 0u;
+      } else {
+        tmem_ld_32x32(tO + c * 32, o);
+        tmem_ld_wait();
+      }
       if (live) {
 #pragma unroll
         for (int k8 = 0; k8 < 4; ++k8) {

@@ -422,7 +422,10 @@ attn_bwd_r2_kernel(const __grid_constant__ CUtensorMap tmR0, const __grid_consta
   } else if (warp == 1) {
     // converged MMA warp, elected issue (common.cuh)
     constexpr uint32_t idA = umma_idesc_bf16(128, 64, 0, 0);
-    constexpr uint32_t idB = umma_idesc_bf16(128, 128, 0, 1);
+    constexpr uint32_t idB128 = umma_idesc_bf16(128, 128, 0, 1);
+    constexpr uint32_t idB64 = umma_idesc_bf16(128, 64, 0, 1);  // N = 64: head-dim columns 0..63 (first MN-major atom of the streamed tile)
+    const bool full_d = g.dlive != 64;  // 64: the second half of the head dim is zero padding -> contractions / outputs over it skipped
+    const uint32_t idB = full_d ? idB128 : idB64;
     if (MODE_KV)
       mbar_wait(r_full, 0, 21);
     else
@@ -444,7 +447,15 @@ attn_bwd_r2_kernel(const __grid_constant__ CUtensorMap tmR0, const __grid_consta
       if (g.dbg != 3) {
         // offsets of the k-steps: A K-major [128 x 128] as two 64-column halves 16 KB apart, B [64 x 128] halves 8 KB apart
         constexpr int AH = 16384 >> 4, BH = 8192 >> 4;
-        if (MODE_KV) {
+        if (!full_d) {  // contraction over head-dim columns 0..63 only
+          if (MODE_KV) {
+            umma_bf16_ss_w_x4<2, 4, 6, 2, 4, 6>(X0(xb), dR0, d0, idA, 0u);
+            umma_bf16_ss_w_x4<2, 4, 6, 2, 4, 6>(X1(xb), dR1, d1, idA, 0u);
+          } else {
+            umma_bf16_ts_w_x4<8, 16, 24, 2, 4, 6>(X0(xb), tR0, d0, idA, 0u);
+            umma_bf16_ts_w_x4<8, 16, 24, 2, 4, 6>(X1(xb), tR1, d1, idA, 0u);
+          }
+        } else if (MODE_KV) {
           umma_bf16_ss_w_x8<2, 4, 6, AH, AH + 2, AH + 4, AH + 6, 2, 4, 6, BH, BH + 2, BH + 4, BH + 6>(X0(xb), dR0, d0, idA, 0u);
           umma_bf16_ss_w_x8<2, 4, 6, AH, AH + 2, AH + 4, AH + 6, 2, 4, 6, BH, BH + 2, BH + 4, BH + 6>(X1(xb), dR1, d1, idA, 0u);
         } else {
@@ -672,8 +683,13 @@ attn_bwd_r2_kernel(const __grid_constant__ CUtensorMap tmR0, const __grid_consta
 #pragma unroll 1
       for (int c = 0; c < CB / 32; ++c) {
         uint32_t v[32];
-        tmem_ld_32x32(ta + lane_off + cb * CB + c * 32, v);
-        tmem_ld_wait();
+        if (g.dlive == 64 && cb * CB + c * 32 >= 64) {  // padded head-dim columns: never accumulated -> exact zeros
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = 0u;
+        } else {
+          tmem_ld_32x32(ta + lane_off + cb * CB + c * 32, v);
+          tmem_ld_wait();
+        }
         if (ri < g.L) {
           bf16* orow = out + (row_base + ri) * 128 + cb * CB + c * 32;
 #pragma unroll

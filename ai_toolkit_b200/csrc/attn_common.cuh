@@ -149,6 +149,25 @@ __device__ __forceinline__ void umma_bf16_ts_w_x8(uint32_t tmem_d, uint32_t tmem
       : "memory");
 }
 template <int OA1, int OA2, int OA3, int OB1, int OB2, int OB3>
+__device__ __forceinline__ void umma_bf16_ss_w_x4(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                                   uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred e, p, t;\n\t.reg .b64 da, db;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "setp.eq.b32 t, %3, %3;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "add.s64 da, %1, %5;\n\tadd.s64 db, %2, %8;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, t;\n\t"
+      "add.s64 da, %1, %6;\n\tadd.s64 db, %2, %9;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, t;\n\t"
+      "add.s64 da, %1, %7;\n\tadd.s64 db, %2, %10;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, t;\n\t"
+      "}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "n"(OA1), "n"(OA2), "n"(OA3), "n"(OB1), "n"(OB2), "n"(OB3)
+      : "memory");
+}
+template <int OA1, int OA2, int OA3, int OB1, int OB2, int OB3>
 __device__ __forceinline__ void umma_bf16_ts_w_x4(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc,
                                                    uint32_t accumulate) {
   asm volatile(
@@ -177,6 +196,8 @@ struct AttnFwdArgs {
   int B, H, L, split;
   float scale;
   int Lk;  // key / value length (== L for self / joint attention; != L for cross attention: fwd variants 3, 4, 5 only)
+  int dlive;  // 128, or 64: only the first 64 head-dim columns of Q / K / V are non-zero (heads of <= 64 channels zero-padded to
+              // 128, SDXL / SD1.5): the MMAs skip the zero half (variant 6 forward, variants 2 / 3 backward)
 };
 
 
@@ -191,6 +212,7 @@ struct AttnBwdArgs {
   float scale;
   int Lt;  // length of the STREAMED side (MODE_KV: queries; MODE_Q: keys / values); == L for self / joint attention
   int dbg; // timing experiments only (B200_ATTN_BWD_DBG=2): skip the softmax work, hand the barriers on (results are wrong)
+  int dlive;  // 128 or 64 (see AttnFwdArgs)
 };
 
 

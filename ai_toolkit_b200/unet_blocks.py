@@ -171,14 +171,15 @@ class Transformer2DEngine:
         ops.heads_pad(v, V, B, Lc, d)
         o_pad = _empty((B * L, H * 128), x)  # the attention kernels write 128 columns per head, token-major
         scale = 1.0 / math.sqrt(d)
-        lse = attention.fwd(Q, K, V, None, o_pad, 0, scale=scale)
+        live = 64 if d <= 64 else 128  # zero-padded half heads: the kernels skip the padding
+        lse = attention.fwd(Q, K, V, None, o_pad, 0, scale=scale, head_live=live)
         if d == 128:
             o = o_pad
         else:  # drop the zero columns: [B L, H, 128] -> [B L, H d]
             o = o_pad.view(B * L, H, 128)[:, :, :d].reshape(B * L, inner)
         out = _empty(res.shape, x)
         z_o = linear_fwd(a.to_out[0], o, out, lora=live_lora(a.to_out[0]), res=res)
-        return out, dict(x=x, ctx=ctx, z_q=z_q, z_qkv=z_qkv, Q=Q, K=K, V=V, o_pad=o_pad, o=o, lse=lse, z_o=z_o, scale=scale)
+        return out, dict(x=x, ctx=ctx, z_q=z_q, z_qkv=z_qkv, Q=Q, K=K, V=V, o_pad=o_pad, o=o, lse=lse, z_o=z_o, scale=scale, live=live)
 
     @staticmethod
     def _attn_bwd(a, s, dout, B, L, Lc, self_attn):
@@ -192,7 +193,7 @@ class Transformer2DEngine:
         else:
             do_pad = torch.zeros((B * L, H * 128), device=dout.device, dtype=torch.bfloat16)
             do_pad.view(B * L, H, 128)[:, :, :d].copy_(do.view(B * L, H, d))
-        dQ, dK, dV = attention.bwd(s["Q"], s["K"], s["V"], None, s["o_pad"], None, do_pad, s["lse"], 0, scale=s["scale"])
+        dQ, dK, dV = attention.bwd(s["Q"], s["K"], s["V"], None, s["o_pad"], None, do_pad, s["lse"], 0, scale=s["scale"], head_live=s["live"])
         dx = _empty(s["x"].shape, dout)
         if self_attn:  # keys / values come from the same x: one dgrad GEMM over the concatenated [dq | dk | dv]
             dqkv = _empty((B * L, 3 * inner), dout)

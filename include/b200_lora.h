@@ -189,6 +189,16 @@ int b200_attn_bwd_x(b200_ctx* ctx, const void* Q, const void* K, const void* V, 
                     int ld1, const void* do0, int ldd0, const void* do1, int ldd1, const void* lse, void* delta, void* dOh,
                     void* dQ, void* dK, void* dV, int B, int H, int L, int Lk, int split, float scale, void* stream);
 
+/* `_xd`: the same with `head_live` = 128, or 64 when only the first 64 of the 128 head-dim columns of Q / K / V are non-zero (heads
+ * of <= 64 channels zero-padded to the kernels' 128: SDXL's 64, SD1.5's 40): every MMA then skips the zero half of its
+ * contraction / output (S, dP: K-steps 0..3; P V, dV, dK, dQ: N = 64) and the forward does not load it; the padded output columns
+ * are written as zeros.  Default forward (6) / backward (2, 3) variants only. */
+int b200_attn_fwd_xd(b200_ctx* ctx, const void* Q, const void* K, const void* V, void* o0, int ld0, void* o1, int ld1,
+                     void* lse, int B, int H, int L, int Lk, int split, float scale, int head_live, void* stream);
+int b200_attn_bwd_xd(b200_ctx* ctx, const void* Q, const void* K, const void* V, const void* o0, int ld0, const void* o1,
+                     int ld1, const void* do0, int ldd0, const void* do1, int ldd1, const void* lse, void* delta, void* dOh,
+                     void* dQ, void* dK, void* dV, int B, int H, int L, int Lk, int split, float scale, int head_live, void* stream);
+
 /* Wan2.1 attention pre-processing (toolkit/models/wan21/wan_attn.py:34-61): RMSNorm ACROSS heads (one RMS over the whole
  * inner dimension H*128, diffusers qk_norm="rms_norm_across_heads") + RoPE on interleaved pairs (cos/sin [Ltot,128] fp32, NULL:
  * no rotation = the cross-attention) + re-layout of ONE tensor x [B*Lseg, ld] to head-major out [B,H,Ltot,128].

@@ -154,3 +154,45 @@ def test_attention_scores_growing_along_the_sequence(L, Lk):
     assert torch.isfinite(o1.float()).all() and torch.isfinite(lse).all()
     assert _rel(o1.view(B, L, -1), o_ref) < 1e-2
     assert (lse - torch.logsumexp(s, -1)).abs().max().item() < 5e-2
+
+
+@pytest.mark.parametrize("B,H,Lq,Lk,d", [(2, 5, 1024, 1024, 64), (1, 10, 4096, 4096, 64), (2, 3, 600, 77, 64), (1, 2, 300, 300, 40)])
+def test_attention_zero_padded_half_heads_skip_the_padding(B, H, Lq, Lk, d):
+    """head_live = 64 (`b200_attn_fwd_xd / _bwd_xd`): heads of <= 64 channels zero-padded to 128 (SDXL 64, SD1.5 40).  The kernels
+    skip the zero half of every contraction / output; the kept half is the same sequence of MMAs, so the results must equal the
+    head_live = 128 run on the same padded tensors BIT FOR BIT, the padded output columns are exact zeros over NaN-filled buffers,
+    and both match the fp32 reference."""
+    from ai_toolkit_b200 import attention
+    torch.manual_seed(Lq + Lk + d)
+    def pad(x):
+        out = torch.zeros(*x.shape[:-1], 128, device=DEV, dtype=torch.bfloat16)
+        out[..., :d] = x
+        return out
+    Q = pad(torch.randn(B, H, Lq, d, device=DEV).bfloat16())
+    K = pad(torch.randn(B, H, Lk, d, device=DEV).bfloat16())
+    V = pad(torch.randn(B, H, Lk, d, device=DEV).bfloat16())
+    D = H * 128
+    scale = d ** -0.5
+    dO = pad(torch.randn(B, Lq, H, d, device=DEV).bfloat16()).reshape(B * Lq, D)
+    res = {}
+    for live in (128, 64):
+        o1 = torch.full((B * Lq, D), float("nan"), device=DEV, dtype=torch.bfloat16)
+        lse = attention.fwd(Q, K, V, None, o1, 0, scale=scale, head_live=live)
+        dQ, dK, dV = attention.bwd(Q, K, V, None, o1, None, dO, lse, 0, scale=scale, head_live=live)
+        torch.cuda.synchronize()
+        res[live] = (o1, lse, dQ, dK, dV)
+    o64 = res[64][0].view(B * Lq, H, 128)
+    assert bool((o64[..., 64:] == 0).all()) and torch.isfinite(o64.float()).all()
+    assert torch.equal(res[64][0], res[128][0]) and torch.equal(res[64][1], res[128][1])
+    for i, name in ((2, "dQ"), (3, "dK"), (4, "dV")):
+        g64, g128 = res[64][i], res[128][i]
+        assert bool((g64[..., 64:] == 0).all()), name
+        assert torch.equal(g64[..., :64], g128[..., :64]), name
+    # against the fp32 reference of the un-padded op
+    q, k, v = (t[..., :d].float() for t in (Q, K, V))
+    q.requires_grad_(True); k.requires_grad_(True); v.requires_grad_(True)
+    o_ref = torch.nn.functional.scaled_dot_product_attention(q, k, v, scale=scale)
+    o_ref.backward(dO.view(B, Lq, H, 128)[..., :d].transpose(1, 2).float())
+    assert _rel(o64[..., :d].reshape(B, Lq, H, d).transpose(1, 2), o_ref) < 1e-2
+    for g, r, name in ((res[64][2], q.grad, "dQ"), (res[64][3], k.grad, "dK"), (res[64][4], v.grad, "dV")):
+        assert _rel(g[..., :d], r) < 1.5e-2, name
