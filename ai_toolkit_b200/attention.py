@@ -47,3 +47,24 @@ def bwd(Q, K, V, o0, o1, do0, do1, lse, split, scale=None, head_live=128):
               _p(delta), _p(dOh), _p(dQ), _p(dK), _p(dV), int(B), int(H), int(L), int(K.shape[2]), int(split),
               float(1.0 / math.sqrt(Dh) if scale is None else scale), int(head_live), device=Q.device.index)
     return dQ, dK, dV
+
+
+def small_fwd(q, k, v, B, H, L, Lk, head_dim, scale=None):
+    """Head dims 160 / 192 / 256 (csrc/small_attn.cu): token-major q [B*L, >= H*d], k / v [B*Lk, >= H*d] views -> (o [B*L, H*d],
+    lse [B, H, L])."""
+    o = torch.empty((B * L, H * head_dim), device=q.device, dtype=torch.bfloat16)
+    lse = torch.empty((B, H, L), device=q.device, dtype=torch.float32)
+    cabi.call("b200_attn_small_fwd", _p(q), int(q.stride(0)), _p(k), int(k.stride(0)), _p(v), int(v.stride(0)), _p(o),
+              int(o.stride(0)), _p(lse), int(B), int(H), int(L), int(Lk), int(head_dim),
+              float(1.0 / math.sqrt(head_dim) if scale is None else scale), device=q.device.index)
+    return o, lse
+
+
+def small_bwd(q, k, v, o, dO, lse, dq, dk, dv, B, H, L, Lk, head_dim, scale=None):
+    """Gradients into the (possibly column-sliced) token-major views dq [B*L, .], dk / dv [B*Lk, .]."""
+    delta = torch.empty((B, H, L), device=q.device, dtype=torch.float32)
+    cabi.call("b200_attn_small_bwd", _p(q), int(q.stride(0)), _p(k), int(k.stride(0)), _p(v), int(v.stride(0)), _p(o),
+              int(o.stride(0)), _p(dO), int(dO.stride(0)), _p(lse), _p(delta), _p(dq), int(dq.stride(0)), _p(dk),
+              int(dk.stride(0)), _p(dv), int(dv.stride(0)), int(B), int(H), int(L), int(Lk), int(head_dim),
+              float(1.0 / math.sqrt(head_dim) if scale is None else scale), device=q.device.index)
+    return dq, dk, dv

@@ -93,6 +93,8 @@ SIGNATURES = {
     "b200_attn_bwd": (c_int, [_V, _V, _V, _V, _V, _I, _V, _I, _V, _I, _V, _I, _V, _V, _V, _V, _V, _V, _I, _I, _I, _I, _F, _V]),
     "b200_attn_fwd_x": (c_int, [_V, _V, _V, _V, _V, _I, _V, _I, _V, _I, _I, _I, _I, _I, _F, _V]),
     "b200_attn_bwd_x": (c_int, [_V, _V, _V, _V, _V, _I, _V, _I, _V, _I, _V, _I, _V, _V, _V, _V, _V, _V, _I, _I, _I, _I, _I, _F, _V]),
+    "b200_attn_small_fwd": (c_int, [_V, _V, _I, _V, _I, _V, _I, _V, _I, _V, _I, _I, _I, _I, _I, _F, _V]),
+    "b200_attn_small_bwd": (c_int, [_V, _V, _I, _V, _I, _V, _I, _V, _I, _V, _I, _V, _V, _V, _I, _V, _I, _V, _I, _I, _I, _I, _I, _I, _F, _V]),
     "b200_attn_fwd_xd": (c_int, [_V, _V, _V, _V, _V, _I, _V, _I, _V, _I, _I, _I, _I, _I, _F, _I, _V]),
     "b200_attn_bwd_xd": (c_int, [_V, _V, _V, _V, _V, _I, _V, _I, _V, _I, _V, _I, _V, _V, _V, _V, _V, _V, _I, _I, _I, _I, _I, _F, _I, _V]),
     "b200_rms_rope_fwd": (c_int, [_V, _V, _I, _V, _V, _V, _V, _V, _I, _I, _I, _I, _I, _F, _I, _V]),

@@ -50,7 +50,8 @@ def sdxl_config() -> UNetConfig:
 
 
 def sd15_config() -> UNetConfig:
-    """SD1.5: head dims 40 / 80 / 160 / 160 -- the 160-wide heads of the two deepest levels are NOT supported by the engine."""
+    """SD1.5: 8 heads per level -> head dims 40 / 80 (tcgen05 kernels, zero-padded to 128) and 160 at the 1280-channel levels
+    (CUDA-core kernel csrc/small_attn.cu: 256 / 64 tokens at 512^2)."""
     return UNetConfig()
 
 
@@ -217,6 +218,8 @@ class UNet2DConditionModel(nn.Module):
 # checkpointing)".  Counted on the meta device over oracle/unet_ref.py at C2 (bs=2, 128x128 latents, 77 text tokens): forward
 # 13.522 TF, forward + backward (dX through the frozen layers) 28.443 TF -> per sample; tests/test_unet_blocks.py recounts it.
 SDXL_STEP_FLOPS_PER_SAMPLE = 28.4431220736e12 / 2
+# the same count for SD1.5 at C1 (bs=1, 64x64 latents = 512^2, 77 text tokens of width 768): forward 0.8033 TF, fwd + bwd 1.7260 TF
+SD15_STEP_FLOPS_PER_SAMPLE = 1.72603375616e12
 
 
 def unet_flops(cfg: UNetConfig, B, H, W, Lc=77):

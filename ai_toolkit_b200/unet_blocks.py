@@ -73,9 +73,10 @@ class Transformer2DModel(nn.Module):
     def __init__(self, heads, dim_head, in_channels, num_layers=1, cross_dim=768, use_linear_projection=False, groups=32,
                  device=None, dtype=torch.bfloat16):
         super().__init__()
-        if dim_head > 128 or dim_head % 4:
+        if (dim_head > 128 and dim_head not in (160, 192, 256)) or dim_head % 4:
             raise NotImplementedError(f"attention head dim {dim_head}: the tcgen05 attention kernels are built for 128 and serve "
-                                      "smaller heads by zero padding (SD1.5's 160-wide heads are not supported)")
+                                      "smaller heads by zero padding; 160 / 192 / 256 (SD1.5's deepest levels) run on the CUDA-core "
+                                      "kernel (csrc/small_attn.cu)")
         inner = heads * dim_head
         self.heads, self.dim_head, self.inner, self.in_channels = heads, dim_head, inner, in_channels
         self.use_linear_projection = use_linear_projection
@@ -163,23 +164,30 @@ class Transformer2DEngine:
             kv = _empty((B * Lc, 2 * inner), x)
             z_qkv = shared_input_fwd((a.to_k, a.to_v), ctx, kv)
             k, v = kv[:, :inner], kv[:, inner:]
-        Q = _empty((B, H, L, 128), x)
-        K = _empty((B, H, Lc, 128), x)
-        V = _empty((B, H, Lc, 128), x)
-        ops.heads_pad(q, Q, B, L, d)
-        ops.heads_pad(k, K, B, Lc, d)
-        ops.heads_pad(v, V, B, Lc, d)
-        o_pad = _empty((B * L, H * 128), x)  # the attention kernels write 128 columns per head, token-major
         scale = 1.0 / math.sqrt(d)
-        live = 64 if d <= 64 else 128  # zero-padded half heads: the kernels skip the padding
-        lse = attention.fwd(Q, K, V, None, o_pad, 0, scale=scale, head_live=live)
-        if d == 128:
-            o = o_pad
-        else:  # drop the zero columns: [B L, H, 128] -> [B L, H d]
-            o = o_pad.view(B * L, H, 128)[:, :, :d].reshape(B * L, inner)
+        if d > 128:  # SD1.5's 160-wide heads (deepest levels, <= 1024 tokens): CUDA-core kernel on the token-major projections
+            o, lse = attention.small_fwd(q, k, v, B, H, L, Lc, d, scale=scale)
+            Q = K = V = o_pad = None
+            live = d
+            small = (q, k, v)
+        else:
+            Q = _empty((B, H, L, 128), x)
+            K = _empty((B, H, Lc, 128), x)
+            V = _empty((B, H, Lc, 128), x)
+            ops.heads_pad(q, Q, B, L, d)
+            ops.heads_pad(k, K, B, Lc, d)
+            ops.heads_pad(v, V, B, Lc, d)
+            o_pad = _empty((B * L, H * 128), x)  # the attention kernels write 128 columns per head, token-major
+            live = 64 if d <= 64 else 128  # zero-padded half heads: the kernels skip the padding
+            lse = attention.fwd(Q, K, V, None, o_pad, 0, scale=scale, head_live=live)
+            if d == 128:
+                o = o_pad
+            else:  # drop the zero columns: [B L, H, 128] -> [B L, H d]
+                o = o_pad.view(B * L, H, 128)[:, :, :d].reshape(B * L, inner)
+            small = None
         out = _empty(res.shape, x)
         z_o = linear_fwd(a.to_out[0], o, out, lora=live_lora(a.to_out[0]), res=res)
-        return out, dict(x=x, ctx=ctx, z_q=z_q, z_qkv=z_qkv, Q=Q, K=K, V=V, o_pad=o_pad, o=o, lse=lse, z_o=z_o, scale=scale, live=live)
+        return out, dict(x=x, ctx=ctx, z_q=z_q, z_qkv=z_qkv, Q=Q, K=K, V=V, o_pad=o_pad, o=o, lse=lse, z_o=z_o, scale=scale, live=live, small=small)
 
     @staticmethod
     def _attn_bwd(a, s, dout, B, L, Lc, self_attn):
@@ -188,25 +196,31 @@ class Transformer2DEngine:
         inner = H * d
         do = _empty((B * L, inner), dout)
         linear_bwd(a.to_out[0], dout, s["o"], s["z_o"], do, lora=live_lora(a.to_out[0]))
-        if d == 128:
-            do_pad = do
-        else:
-            do_pad = torch.zeros((B * L, H * 128), device=dout.device, dtype=torch.bfloat16)
-            do_pad.view(B * L, H, 128)[:, :, :d].copy_(do.view(B * L, H, d))
-        dQ, dK, dV = attention.bwd(s["Q"], s["K"], s["V"], None, s["o_pad"], None, do_pad, s["lse"], 0, scale=s["scale"], head_live=s["live"])
         dx = _empty(s["x"].shape, dout)
         if self_attn:  # keys / values come from the same x: one dgrad GEMM over the concatenated [dq | dk | dv]
             dqkv = _empty((B * L, 3 * inner), dout)
-            ops.heads_unpad(dQ, dqkv[:, :inner], B, L, d)
-            ops.heads_unpad(dK, dqkv[:, inner:2 * inner], B, L, d)
-            ops.heads_unpad(dV, dqkv[:, 2 * inner:], B, L, d)
-            shared_input_bwd((a.to_q, a.to_k, a.to_v), dqkv, s["x"], s["z_qkv"], dx)
+            dq, dk, dv = dqkv[:, :inner], dqkv[:, inner:2 * inner], dqkv[:, 2 * inner:]
         else:  # cross-attention: the text embeddings are data -> adapters only on the key / value side
             dq = _empty((B * L, inner), dout)
             dkv = _empty((B * Lc, 2 * inner), dout)
+            dk, dv = dkv[:, :inner], dkv[:, inner:]
+        if s["small"] is not None:
+            q, k, v = s["small"]
+            attention.small_bwd(q, k, v, s["o"], do, s["lse"], dq, dk, dv, B, H, L, Lc, d, scale=s["scale"])
+        else:
+            if d == 128:
+                do_pad = do
+            else:
+                do_pad = torch.zeros((B * L, H * 128), device=dout.device, dtype=torch.bfloat16)
+                do_pad.view(B * L, H, 128)[:, :, :d].copy_(do.view(B * L, H, d))
+            dQ, dK, dV = attention.bwd(s["Q"], s["K"], s["V"], None, s["o_pad"], None, do_pad, s["lse"], 0, scale=s["scale"],
+                                       head_live=s["live"])
             ops.heads_unpad(dQ, dq, B, L, d)
-            ops.heads_unpad(dK, dkv[:, :inner], B, Lc, d)
-            ops.heads_unpad(dV, dkv[:, inner:], B, Lc, d)
+            ops.heads_unpad(dK, dk, B, Lc, d)
+            ops.heads_unpad(dV, dv, B, Lc, d)
+        if self_attn:
+            shared_input_bwd((a.to_q, a.to_k, a.to_v), dqkv, s["x"], s["z_qkv"], dx)
+        else:
             linear_bwd(a.to_q, dq, s["x"], s["z_q"], dx, lora=live_lora(a.to_q))
             shared_input_bwd((a.to_k, a.to_v), dkv, s["ctx"], s["z_qkv"], None)
         return dx

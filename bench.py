@@ -600,12 +600,14 @@ def run_b200_sdxl(args):
     from ai_toolkit_b200.optimizer import B200AdamW
 
     ctx = cabi.Context.get(0)
-    BS = args.batch if args.batch != 1 else 2
-    R = args.rank if args.rank != RANK else 8
-    H = W = 128
-    cfg = host_unet.sdxl_config()
+    SD15 = args.model == "sd15"  # configs[0]: SD1.5 r=4, 512x512, bs=1 (the reference's CPU-runnable case, here on the GPU)
+    BS = args.batch if (args.batch != 1 or SD15) else 2
+    R = args.rank if args.rank != RANK else (4 if SD15 else 8)
+    H = W = 64 if SD15 else 128
+    cfg = host_unet.sd15_config() if SD15 else host_unet.sdxl_config()
+    TD = cfg.cross_attention_dim
     model = host_unet.UNet2DConditionModel(cfg, device=dev).init_synthetic_(seed=0)
-    net = LoRASpecialNetwork(text_encoder=None, unet=model, lora_dim=R, alpha=R, train_unet=True, train_text_encoder=False, is_sdxl=True)
+    net = LoRASpecialNetwork(text_encoder=None, unet=model, lora_dim=R, alpha=R, train_unet=True, train_text_encoder=False, is_sdxl=not SD15)
     net.force_to(dev, torch.float32)
     net._update_torch_multiplier()
     net.apply_to(None, model, False, True)
@@ -621,12 +623,13 @@ def run_b200_sdxl(args):
         "latents": (torch.randn(BS, 4, H, W, generator=hg) * 0.18215 * 5).bfloat16().pin_memory(),
         "noise": torch.randn(BS, 4, H, W, generator=hg).bfloat16().pin_memory(),
         "timesteps": torch.randint(1, 999, (BS,), generator=hg).pin_memory(),
-        "text_embeds": torch.randn(BS, 77, 2048, generator=hg).bfloat16().pin_memory(),
-        "pooled_embeds": torch.randn(BS, 1280, generator=hg).bfloat16().pin_memory(),
+        "text_embeds": torch.randn(BS, 77, TD, generator=hg).bfloat16().pin_memory(),
     }
+    if not SD15:
+        host["pooled_embeds"] = torch.randn(BS, 1280, generator=hg).bfloat16().pin_memory()
     h2d = sum(v.numel() * v.element_size() for v in host.values())
     d = {k: v.to(dev) for k, v in host.items()}
-    step.load_batch(host["latents"], host["noise"], host["timesteps"], host["text_embeds"], host["pooled_embeds"])
+    step.load_batch(host["latents"], host["noise"], host["timesteps"], host["text_embeds"], host.get("pooled_embeds"))
 
     def run_dev():  # the resident batch (static device buffers), as the FLUX arm does
         return step.run()
@@ -656,17 +659,20 @@ def run_b200_sdxl(args):
     ms_e2e = (time.perf_counter() - t0) * 1e3 / args.steps
     sampler.stop_flag = True
     peaks, peak_kind = measured_peaks()
-    f_step = host_unet.SDXL_STEP_FLOPS_PER_SAMPLE * BS
+    f_step = (host_unet.SD15_STEP_FLOPS_PER_SAMPLE if SD15 else host_unet.SDXL_STEP_FLOPS_PER_SAMPLE) * BS
     out = {
-        "metric": f"train-steps/sec SDXL-base LoRA r={R} bs={BS} 1024^2", "value": 1e3 / ms, "unit": "steps/s", "n_gpus": 1,
+        "metric": (f"train-steps/sec SD1.5 LoRA r={R} bs={BS} 512^2" if SD15 else f"train-steps/sec SDXL-base LoRA r={R} bs={BS} 1024^2"),
+        "value": 1e3 / ms, "unit": "steps/s", "n_gpus": 1,
         "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": "BASELINE.json configs[1]: SDXL-base LoRA r=8 bs=2 1024x1024 (latents 2x4x128x128, text 2x77x2048)",
+        "config": {"workload": ("BASELINE.json configs[0]: SD1.5 LoRA r=4 bs=1 512x512 (latents 1x4x64x64, text 1x77x768), bf16 on the GPU"
+                                if SD15 else
+                                "BASELINE.json configs[1]: SDXL-base LoRA r=8 bs=2 1024x1024 (latents 2x4x128x128, text 2x77x2048)"),
                    "global_batch": BS, "img_per_s": BS * 1e3 / ms, "rank": R, "lora_modules": len(net.get_all_modules()),
                    "lora_params": int(net.n_params), "parallelism": "dp1", "cuda_graph": not args.no_graph,
-                   "body": "HYBRID: Transformer2DModel stacks (adapter-bearing; 70 blocks) on this repo's kernels; frozen ResnetBlock2D / "
+                   "body": "HYBRID: Transformer2DModel stacks (adapter-bearing) on this repo's kernels; frozen ResnetBlock2D / "
                            "Down/Upsample2D / conv_in/out / time embeddings = eager PyTorch (cuDNN / cuBLAS) under autograd",
-                   "l2": "per-step working set (5.1 GB weights + activations) >> 126 MB L2; no explicit flush"},
+                   "l2": "per-step working set (1.7 GB (SD1.5) / 5.1 GB (SDXL) of weights + activations) >> 126 MB L2; no explicit flush"},
         "impl": "b200",
         "step_roofline": {"bound": "tensor", "f_step_tflop": f_step / 1e12, "achieved": f_step / (ms * 1e-3) / 1e12,
                           "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
@@ -683,17 +689,17 @@ def run_b200_sdxl(args):
 
         gc.collect()
         torch.cuda.empty_cache()
-        out["gpu_reference"] = gpu_reference_leg_sdxl(dev, d, R, ms)
+        out["gpu_reference"] = gpu_reference_leg_sdxl(dev, d, R, ms, sd15=SD15)
     print(json.dumps(out), flush=True)
 
 
-def gpu_reference_leg_sdxl(dev, d, R, ms_ours, steps=3, warmup=2):
+def gpu_reference_leg_sdxl(dev, d, R, ms_ours, steps=3, warmup=2, sd15=False):
     import torch
     import torch.nn.functional as F
 
     from oracle import unet_ref
 
-    cfg = unet_ref.sdxl_config()
+    cfg = unet_ref.sd15_config() if sd15 else unet_ref.sdxl_config()
     torch.manual_seed(0)
     with torch.device(dev):
         om = unet_ref.UNet2DConditionModel(cfg).to(torch.bfloat16)
@@ -718,6 +724,8 @@ def gpu_reference_leg_sdxl(dev, d, R, ms_ours, steps=3, warmup=2):
 
         def hook(m, inp, out, A=A, Bw=Bw):  # the reference's LoRAModule.forward under bf16 autocast: org + up(down(x)) * scale
             x = inp[0]
+            if x.dim() == 4:  # 1x1-conv projection (SD1.5)
+                return out + F.conv2d(F.conv2d(x, A.to(x.dtype)[:, :, None, None]), Bw.to(x.dtype)[:, :, None, None])
             return out + F.linear(F.linear(x, A.to(x.dtype)), Bw.to(x.dtype))
 
         mod.register_forward_hook(hook)
@@ -731,7 +739,8 @@ def gpu_reference_leg_sdxl(dev, d, R, ms_ours, steps=3, warmup=2):
         opt.zero_grad(set_to_none=True)
         a = ac[d["timesteps"]]
         noisy = (a.sqrt()[:, None, None, None] * d["latents"].float() + (1 - a).sqrt()[:, None, None, None] * d["noise"].float()).bfloat16()
-        pred = om(noisy, d["timesteps"].float(), d["text_embeds"], added_cond_kwargs={"text_embeds": d["pooled_embeds"], "time_ids": tid})[0]
+        pred = om(noisy, d["timesteps"].float(), d["text_embeds"],
+                  added_cond_kwargs=None if sd15 else {"text_embeds": d["pooled_embeds"], "time_ids": tid})[0]
         loss = ((pred.float() - d["noise"].float()) ** 2).mean()
         loss.backward()
         torch.nn.utils.clip_grad_norm_(params, 1.0)
@@ -766,16 +775,16 @@ def main():
     ap.add_argument("--skip-cpu-baseline", action="store_true")
     ap.add_argument("--skip-gpu-reference", action="store_true",
                     help="do not time the eager reference-style PyTorch step on the same GPU after the main measurement")
-    ap.add_argument("--model", default="flux", choices=["flux", "wan", "sdxl"],
+    ap.add_argument("--model", default="flux", choices=["flux", "wan", "sdxl", "sd15"],
                     help="flux = BASELINE.json configs[2] (the headline metric); wan = configs[3] (Wan2.1-T2V-1.3B, 49x512x512); "
-                         "sdxl = configs[1] (hybrid: engine blocks + eager frozen body, one GPU)")
+                         "sdxl = configs[1], sd15 = configs[0] (hybrid: engine blocks + eager frozen body, one GPU)")
     ap.add_argument("--batch", type=int, default=1, help="samples per GPU (BASELINE.json configs[4] uses 4)")
     ap.add_argument("--rank", type=int, default=RANK, help="LoRA rank (configs[4] sweeps 4, 8, 16, 32, 64)")
     ap.add_argument("--layers", type=int, nargs=2, default=None, help="debug: override (double, single) block counts")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
-    elif args.model == "sdxl":
+    elif args.model in ("sdxl", "sd15"):
         run_b200_sdxl(args)
     else:
         run_b200(args)

@@ -199,6 +199,18 @@ int b200_attn_bwd_xd(b200_ctx* ctx, const void* Q, const void* K, const void* V,
                      int ld1, const void* do0, int ldd0, const void* do1, int ldd1, const void* lse, void* delta, void* dOh,
                      void* dQ, void* dK, void* dV, int B, int H, int L, int Lk, int split, float scale, int head_live, void* stream);
 
+/* Attention for head dims the tcgen05 kernels do not cover (head_dim 160, 192 or 256; SD1.5's 1280-channel levels: 8 heads of
+ * 160 at 64..1024 tokens), on the CUDA cores (csrc/small_attn.cu).  TOKEN-major operands as the projections write them:
+ * q / out / dO / dq [B*L, ld] and k / v / dk / dv [B*Lk, ld], head h in columns [h*head_dim, (h+1)*head_dim); lse / delta [B,H,L]
+ * fp32 (natural log).  softmax(scale q k^T) v and its gradients, fp32 statistics; L != Lk allowed (cross attention).
+ * Other head dims: B200_ERR_INVALID (<= 128 belongs to b200_attn_fwd_xd).  Replaces F.scaled_dot_product_attention as called by
+ * diffusers' AttnProcessor2_0 for the UNet (the reference's own call of it: toolkit/models/wan21/wan_attn.py:70-76). */
+int b200_attn_small_fwd(b200_ctx* ctx, const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, void* out, int ldo,
+                        void* lse, int B, int H, int L, int Lk, int head_dim, float scale, void* stream);
+int b200_attn_small_bwd(b200_ctx* ctx, const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, const void* o,
+                        int ldo, const void* dO, int lddo, const void* lse, void* delta, void* dq, int lddq, void* dk, int lddk,
+                        void* dv, int lddv, int B, int H, int L, int Lk, int head_dim, float scale, void* stream);
+
 /* Wan2.1 attention pre-processing (toolkit/models/wan21/wan_attn.py:34-61): RMSNorm ACROSS heads (one RMS over the whole
  * inner dimension H*128, diffusers qk_norm="rms_norm_across_heads") + RoPE on interleaved pairs (cos/sin [Ltot,128] fp32, NULL:
  * no rotation = the cross-attention) + re-layout of ONE tensor x [B*Lseg, ld] to head-major out [B,H,Ltot,128].

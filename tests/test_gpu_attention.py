@@ -196,3 +196,37 @@ def test_attention_zero_padded_half_heads_skip_the_padding(B, H, Lq, Lk, d):
     assert _rel(o64[..., :d].reshape(B, Lq, H, d).transpose(1, 2), o_ref) < 1e-2
     for g, r, name in ((res[64][2], q.grad, "dQ"), (res[64][3], k.grad, "dK"), (res[64][4], v.grad, "dV")):
         assert _rel(g[..., :d], r) < 1.5e-2, name
+
+
+@pytest.mark.parametrize("B,H,Lq,Lk,d", [(2, 8, 256, 256, 160), (1, 8, 64, 64, 160), (2, 2, 1000, 77, 160), (1, 3, 37, 300, 192),
+                                          (1, 2, 100, 100, 256)])
+def test_small_attention_head_dims_above_128(B, H, Lq, Lk, d):
+    """`b200_attn_small_fwd / _bwd` (CUDA-core kernel for SD1.5's 160-wide heads): token-major strided views in, vs the fp32
+    reference of softmax(q k^T / sqrt(d)) v and its gradients; ragged tiles on both sides; cross attention."""
+    from ai_toolkit_b200 import attention
+    torch.manual_seed(Lq + Lk + d)
+    inner = H * d
+    qkv = torch.randn(B * Lq, 3 * inner + 8, device=DEV).bfloat16()      # q is a column slice of a wider buffer
+    kv = torch.randn(B * Lk, 2 * inner, device=DEV).bfloat16()
+    q, k, v = qkv[:, 8:8 + inner], kv[:, :inner], kv[:, inner:]
+    o, lse = attention.small_fwd(q, k, v, B, H, Lq, Lk, d)
+    dO = torch.randn(B * Lq, inner, device=DEV).bfloat16()
+    dq = torch.full((B * Lq, inner), float("nan"), device=DEV, dtype=torch.bfloat16)
+    dkv = torch.full((B * Lk, 2 * inner), float("nan"), device=DEV, dtype=torch.bfloat16)
+    attention.small_bwd(q, k, v, o, dO, lse, dq, dkv[:, :inner], dkv[:, inner:], B, H, Lq, Lk, d)
+    torch.cuda.synchronize()
+
+    def heads(t, L):
+        return t.float().reshape(B, L, H, d).transpose(1, 2).detach().clone().requires_grad_(True)
+    qr, kr, vr = heads(q, Lq), heads(k, Lk), heads(v, Lk)
+    s = (qr @ kr.transpose(-1, -2)) * d ** -0.5
+    o_ref = torch.softmax(s, -1) @ vr
+    o_ref.backward(heads(dO, Lq).detach())
+    back = lambda t, L: t.transpose(1, 2).reshape(B * L, inner)  # noqa: E731
+    assert _rel(o, back(o_ref, Lq)) < 6e-3
+    assert (lse - torch.logsumexp(s, -1)).abs().max().item() < 2e-3
+    assert torch.isfinite(dq.float()).all() and torch.isfinite(dkv.float()).all()
+    assert _rel(dq, back(qr.grad, Lq)) < 1e-2 and _rel(dkv[:, :inner], back(kr.grad, Lk)) < 1e-2
+    assert _rel(dkv[:, inner:], back(vr.grad, Lk)) < 1e-2
+    with pytest.raises(Exception):
+        attention.small_fwd(q[:, :H * 128], k[:, :H * 128], v[:, :H * 128], B, H, Lq, Lk, 128)

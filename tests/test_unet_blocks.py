@@ -28,8 +28,9 @@ def test_container_matches_oracle_parameter_names():
         assert list(so.keys()) == list(sm.keys())
         assert all(so[k].shape == sm[k].shape for k in so)
         m.load_state_dict(so, strict=True)
+    Transformer2DModel(8, 160, 1280, device="meta")  # SD1.5's deepest level: CUDA-core attention kernel
     with pytest.raises(NotImplementedError):
-        Transformer2DModel(8, 160, 1280)  # SD1.5's deepest level
+        Transformer2DModel(8, 136, 1088)
 
 
 def _unet_with(t2d_cls, **kw):
@@ -169,6 +170,8 @@ def _attach_eager_adapters(om, net):
     (False, 4, 40, 1, 96, 2, 16, 12, 77, 4),    # SD1.5 form: 1x1-conv projections, head dim 40 (320 / 8)
     (False, 2, 80, 1, 96, 1, 8, 8, 77, 8),      # SD1.5 second level: head dim 80
     (True, 5, 64, 2, 256, 2, 16, 16, 77, 8),    # SDXL form: Linear projections, head dim 64, depth 2
+    (False, 2, 160, 1, 96, 2, 16, 16, 77, 4),   # SD1.5 deepest levels: head dim 160 -> CUDA-core attention kernel (256 tokens)
+    (False, 2, 160, 1, 96, 1, 6, 6, 77, 8),     # ... 36 tokens: ragged tiles
 ])
 def test_transformer2d_engine_matches_oracle(linear, heads, dim_head, layers, cross_dim, B, H, W, Lc, rank):
     model, net, refs, C = _setup(linear, heads, dim_head, layers, cross_dim, rank, rank / 2)
@@ -203,17 +206,20 @@ def test_transformer2d_engine_matches_oracle(linear, heads, dim_head, layers, cr
 
 
 # ------------------------------------------------------------------------------------- the UNet host (ai_toolkit_b200/unet.py)
-def _tiny_cfgs():
+def _tiny_cfgs(form="sdxl"):
     from ai_toolkit_b200 import unet as host
-    kw = dict(block_out_channels=(64, 128), attn_layers=(1, 2), heads=(1, 2), cross_attention_dim=96, use_linear_projection=True,
-              addition_embed=True, addition_time_embed_dim=16, projection_class_embeddings_input_dim=32 + 6 * 16)
+    if form == "sd15":  # 1x1-conv projections, no text-time embedding, head dims 64 and 160 (the CUDA-core attention kernel)
+        kw = dict(block_out_channels=(64, 320), attn_layers=(1, 1), heads=(1, 2), cross_attention_dim=96, use_linear_projection=False)
+    else:
+        kw = dict(block_out_channels=(64, 128), attn_layers=(1, 2), heads=(1, 2), cross_attention_dim=96, use_linear_projection=True,
+                  addition_embed=True, addition_time_embed_dim=16, projection_class_embeddings_input_dim=32 + 6 * 16)
     return host.UNetConfig(**kw), unet_ref.UNetConfig(**kw)
 
 
 def test_unet_host_matches_oracle_parameter_names():
     from ai_toolkit_b200 import unet as host
     hc, oc = _tiny_cfgs()
-    for a, b in ((hc, oc), (host.sdxl_config(), unet_ref.sdxl_config())):
+    for a, b in ((hc, oc), (host.sd15_config(), unet_ref.sd15_config()), (host.sdxl_config(), unet_ref.sdxl_config())):
         with torch.device("meta"):
             so = unet_ref.UNet2DConditionModel(b).state_dict()
         sm = host.UNet2DConditionModel(a, device="meta").state_dict()
@@ -221,8 +227,8 @@ def test_unet_host_matches_oracle_parameter_names():
         assert all(so[k].shape == sm[k].shape for k in so)
     n_sdxl = sum(v.numel() for v in sm.values())
     assert abs(n_sdxl - 2.567e9) < 0.01e9  # SDXL-base UNet: 2.57 B parameters
-    with pytest.raises(NotImplementedError):
-        host.UNet2DConditionModel(host.sd15_config(), device="meta")  # 160-wide heads of SD1.5's deepest levels
+    n_sd15 = sum(v.numel() for v in host.UNet2DConditionModel(host.sd15_config(), device="meta").state_dict().values())
+    assert abs(n_sd15 - 859.5e6) < 1e6  # SD1.5 UNet: 860 M parameters
     # the FLOP figure bench.py reports against (FlopCounterMode over the oracle forward + backward)
     from torch.utils.flop_counter import FlopCounterMode
     with torch.device("meta"):
@@ -240,12 +246,13 @@ def test_unet_host_matches_oracle_parameter_names():
 
 
 @pytest.mark.gpu
-def test_unet_host_step_matches_oracle():
-    """Tiny SDXL-form UNet: prediction, loss and every LoRA gradient of `UNetLoRATrainStep` vs the fp32 oracle UNet with eager
+@pytest.mark.parametrize("form", ["sdxl", "sd15"])
+def test_unet_host_step_matches_oracle(form):
+    """Tiny SDXL-form / SD1.5-form UNet: prediction, loss and every LoRA gradient of `UNetLoRATrainStep` vs the fp32 oracle UNet with eager
     adapters and the oracle's `calculate_loss`; then one optimizer step moves the flat parameters."""
     from ai_toolkit_b200.optimizer import B200AdamW
     from ai_toolkit_b200 import unet as host
-    hc, oc = _tiny_cfgs()
+    hc, oc = _tiny_cfgs(form)
     o = unet_ref.init_synthetic_(unet_ref.UNet2DConditionModel(oc), seed=3, std=0.05)
     o.requires_grad_(False)
     m = host.UNet2DConditionModel(hc, device=DEV)
@@ -260,8 +267,9 @@ def test_unet_host_step_matches_oracle():
         for lora in net.unet_loras:
             lora.lora_up.weight.copy_(torch.randn(lora.lora_up.weight.shape, generator=g) * 0.05)
     net.mark_params_changed()
-    # 11 Transformer2DModels (2 + 2 down, 1 mid, 3 + 3 up) x proj_in/out + 17 BasicTransformerBlocks x 10 Linears
-    assert len(net.unet_loras) == 2 * 11 + 10 * (2 * 1 + 2 * 2 + 1 * 2 + 3 * 2 + 3 * 1)
+    # 11 Transformer2DModels (2 + 2 down, 1 mid, 3 + 3 up) x proj_in/out + their BasicTransformerBlocks x 10 Linears
+    n_blocks = (2 * 1 + 2 * 2 + 1 * 2 + 3 * 2 + 3 * 1) if form == "sdxl" else 11
+    assert len(net.unet_loras) == 2 * 11 + 10 * n_blocks
     B, H, W = 2, 16, 16
     lat = torch.randn(B, 4, H, W, generator=g).bfloat16().to(DEV)
     noise = torch.randn(B, 4, H, W, generator=g).bfloat16().to(DEV)
@@ -284,7 +292,9 @@ def test_unet_host_step_matches_oracle():
             leaves.append((A, Bw))
 
             def hook(mm, inp, out, A=A, Bw=Bw, s=lora.scale):
-                return out + (F.linear(F.linear(inp[0].float(), A), Bw) * s).to(out.dtype)
+                x_in = inp[0].float()
+                lx = F.conv2d(F.conv2d(x_in, A), Bw) if isinstance(mm, torch.nn.Conv2d) else F.linear(F.linear(x_in, A), Bw)
+                return out + (lx * s).to(out.dtype)
 
             mod.register_forward_hook(hook)
         noisy = step.table.add_noise_ref(lat.float(), noise.float(), ts).to(dt) if hasattr(step.table, "add_noise_ref") else None
@@ -292,20 +302,24 @@ def test_unet_host_step_matches_oracle():
             ac = step.table.alphas_cumprod.to(DEV)[ts].float()
             noisy = (ac.sqrt()[:, None, None, None] * lat.float() + (1 - ac).sqrt()[:, None, None, None] * noise.float())
             noisy = noisy.to(torch.bfloat16).to(dt)  # the kernel rounds the noisy latents to bf16 (the reference's train dtype)
-        pred = om(noisy, ts.float(), text.to(dt), added_cond_kwargs={"text_embeds": pooled.to(dt), "time_ids": step.time_ids(B, H, W)})[0]
+        pred = om(noisy, ts.float(), text.to(dt), added_cond_kwargs={"text_embeds": pooled.to(dt), "time_ids": step.time_ids(B, H, W)}
+                  if form == "sdxl" else None)[0]
         loss = ((pred.float() - noise.float()) ** 2).mean()
         loss.backward()
         res[name] = (loss.detach(), torch.cat([p.grad.reshape(-1) for ab in leaves for p in ab]))
-    tot = step.run(lat, noise, ts, text, pooled)
+    tot = step.run(lat, noise, ts, text, pooled if form == "sdxl" else None)
     gm = net.flat_grads[:res["fp32"][1].numel()]
     # (run() already stepped the optimizer; the gradients are still in the flat buffer until the next zero_grad)
     e_l = abs(tot.item() - res["fp32"][0].item()) / res["fp32"][0].item()
     fl_l = abs(res["bf16"][0].item() - res["fp32"][0].item()) / res["fp32"][0].item()
     e_g, fl_g = _rel(gm, res["fp32"][1]), _rel(res["bf16"][1], res["fp32"][1])
-    print(f"[unet host] loss {tot.item():.6f} vs {res['fp32'][0].item():.6f} rel {e_l:.3e} (floor {fl_l:.3e}); dA/dB {e_g:.3e} (floor {fl_g:.3e})")
+    print(f"[unet host {form}] loss {tot.item():.6f} vs {res['fp32'][0].item():.6f} rel {e_l:.3e} (floor {fl_l:.3e}); dA/dB {e_g:.3e} (floor {fl_g:.3e})")
     assert e_l < max(2e-3, 1.5 * fl_l) and e_g < max(2e-3, 1.5 * fl_g)
     assert not torch.equal(net.flat_params, p0)
-    out = step.hook_train_loop(dict(latents=lat, noise=noise, timesteps=ts.cpu(), text_embeds=text, pooled_embeds=pooled))
+    batch = dict(latents=lat, noise=noise, timesteps=ts.cpu(), text_embeds=text)
+    if form == "sdxl":
+        batch["pooled_embeds"] = pooled
+    out = step.hook_train_loop(batch)
     assert out["loss"] > 0 and out["loss"] == out["loss"]
 
 
