@@ -116,6 +116,7 @@ SIGNATURES = {
     "b200_geglu_fwd": (c_int, [_V, _V, _I, _V, _I, _L, _I, _V]),
     "b200_geglu_bwd": (c_int, [_V, _V, _I, _V, _I, _V, _I, _L, _I, _V]),
     "b200_heads_pad": (c_int, [_V, _V, _V, _I, _I, _I, _I, _I, _I, _V]),
+    "b200_heads_pad3": (c_int, [_V, _V, _V, _I, _I, _V, _V, _I, _I, _V, _V, _I, _I, _I, _I, _I, _I, _I, _V]),
     "b200_flow_add_noise": (c_int, [_V, _V, _V, _V, _V, _I, _I, _I, _I, _I, _V]),
     "b200_flow_loss": (c_int, [_V, _V, _V, _V, _V, _V, _V, _I, _I, _I, _I, _I, _F, _V]),
     "b200_grad_sumsq": (c_int, [_V, _V, _L, _V, _V]),

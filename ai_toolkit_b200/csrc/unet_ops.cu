@@ -256,18 +256,31 @@ __global__ void __launch_bounds__(256) geglu_bwd_kernel(const bf16* __restrict__
 
 // x [B L, ld] (H heads of d <= 128 columns) <-> head-major [B, H, L, 128] with zero padding; to_heads = 0: the inverse
 // (the padded columns of the head-major tensor are dropped).  One warp per token, lane owns 4 of the 128 columns of a head.
-__global__ void __launch_bounds__(256) heads_pad_kernel(const bf16* __restrict__ src, bf16* __restrict__ dst, int ld, int B, int L,
-                                                        int H, int d, int to_heads) {
+struct HeadsPadSeg {
+  const bf16* src;
+  bf16* dst;
+  int ld, L;
+};
+struct HeadsPadArgs {
+  HeadsPadSeg seg[3];  // blockIdx.y selects the tensor: q / k / v (or dQ / dK / dV) of one attention in ONE launch
+  int B, H, d, to_heads;
+};
+
+__global__ void __launch_bounds__(256) heads_pad_kernel(const HeadsPadArgs g) {
   pdl_grid_sync();
+  const HeadsPadSeg sg = g.seg[blockIdx.y];
+  const bf16* __restrict__ src = sg.src;
+  bf16* __restrict__ dst = sg.dst;
+  const int L = sg.L, ld = sg.ld, H = g.H, d = g.d;
   const long long tok = static_cast<long long>(blockIdx.x) * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
-  if (tok >= static_cast<long long>(B) * L) return;
+  if (tok >= static_cast<long long>(g.B) * L) return;
   const int l = static_cast<int>(tok % L), b = static_cast<int>(tok / L);
   const bool mine = lane * 4 < d;
   for (int h = 0; h < H; ++h) {
     const size_t hm = ((static_cast<size_t>(b) * H + h) * L + l) * 128 + lane * 4;
     const size_t tm = static_cast<size_t>(tok) * ld + h * d + lane * 4;
-    if (to_heads) {
+    if (g.to_heads) {
       uint2 v = make_uint2(0u, 0u);
       if (mine) v = *reinterpret_cast<const uint2*>(src + tm);
       *reinterpret_cast<uint2*>(dst + hm) = v;
@@ -362,16 +375,32 @@ extern "C" int b200_geglu_bwd(b200_ctx* ctx, const void* dy, int lddy, const voi
   return B200_OK;
 }
 
-extern "C" int b200_heads_pad(b200_ctx* ctx, const void* src, void* dst, int ld, int B, int L, int H, int head_dim, int to_heads,
-                              void* stream) {
+extern "C" int b200_heads_pad3(b200_ctx* ctx, const void* src0, void* dst0, int ld0, int L0, const void* src1, void* dst1, int ld1,
+                               int L1, const void* src2, void* dst2, int ld2, int L2, int n, int B, int H, int head_dim,
+                               int to_heads, void* stream) {
   int rc = check_ctx(ctx);
   if (rc) return rc;
-  B200_REQUIRE(src && dst && B > 0 && L > 0 && H > 0 && head_dim > 0 && head_dim <= 128 && head_dim % 4 == 0 && ld % 4 == 0,
-               "b200_heads_pad: bad args head_dim=%d (<= 128, multiple of 4)", head_dim);
-  const long long rows = static_cast<long long>(B) * L;
-  B200_KLAUNCH(heads_pad_kernel, static_cast<unsigned>((rows + 7) / 8), 256, 0, reinterpret_cast<cudaStream_t>(stream),
-               (const bf16*)src, (bf16*)dst, ld, B, L, H, head_dim, to_heads);
+  B200_REQUIRE(n >= 1 && n <= 3 && B > 0 && H > 0 && head_dim > 0 && head_dim <= 128 && head_dim % 4 == 0,
+               "b200_heads_pad3: bad args n=%d head_dim=%d (<= 128, multiple of 4)", n, head_dim);
+  HeadsPadArgs a = {};
+  const void* srcs[3] = {src0, src1, src2};
+  void* dsts[3] = {dst0, dst1, dst2};
+  const int lds[3] = {ld0, ld1, ld2}, Ls[3] = {L0, L1, L2};
+  long long rows = 0;
+  for (int i = 0; i < n; ++i) {
+    B200_REQUIRE(srcs[i] && dsts[i] && Ls[i] > 0 && lds[i] % 4 == 0, "b200_heads_pad3: tensor %d: null pointer, L <= 0 or ld %% 4", i);
+    a.seg[i] = HeadsPadSeg{(const bf16*)srcs[i], (bf16*)dsts[i], lds[i], Ls[i]};
+    rows = max(rows, static_cast<long long>(B) * Ls[i]);
+  }
+  a.B = B; a.H = H; a.d = head_dim; a.to_heads = to_heads;
+  dim3 grid(static_cast<unsigned>((rows + 7) / 8), n);
+  B200_KLAUNCH(heads_pad_kernel, grid, 256, 0, reinterpret_cast<cudaStream_t>(stream), a);
   B200_CUDA_CHECK(cudaGetLastError());
   ctx->launches.fetch_add(1);
   return B200_OK;
+}
+
+extern "C" int b200_heads_pad(b200_ctx* ctx, const void* src, void* dst, int ld, int B, int L, int H, int head_dim, int to_heads,
+                              void* stream) {
+  return b200_heads_pad3(ctx, src, dst, ld, L, nullptr, nullptr, 0, 0, nullptr, nullptr, 0, 0, 1, B, H, head_dim, to_heads, stream);
 }

@@ -158,6 +158,21 @@ def heads_pad(x, out, B, L, head_dim):
     return out
 
 
+def heads_pad_multi(pairs, B, head_dim, to_heads=True):
+    """Up to three (token-major view [B*L_i, >= H*head_dim], head-major [B, H, L_i, 128]) pairs of ONE attention in one launch
+    (q / k / v, or with to_heads=False the gradients dQ / dK / dV back into token-major views)."""
+    assert 1 <= len(pairs) <= 3
+    args = []
+    H = None
+    for tm, hm in pairs:
+        H = int(hm.shape[1])
+        src, dst = (tm, hm) if to_heads else (hm, tm)
+        args += [_p(src), _p(dst), int(tm.stride(0)), int(hm.shape[2])]
+    for _ in range(3 - len(pairs)):
+        args += [None, None, 0, 0]
+    cabi.call("b200_heads_pad3", *args, len(pairs), int(B), H, int(head_dim), int(bool(to_heads)), device=_dev(pairs[0][0]))
+
+
 def heads_unpad(hm, out, B, L, head_dim):
     """head-major [B, H, L, 128] -> out [B*L, >= H*head_dim] view (first head_dim columns of every head)."""
     cabi.call("b200_heads_pad", _p(hm), _p(out), int(out.stride(0)), int(B), int(L), int(hm.shape[1]), int(head_dim), 0,

@@ -174,9 +174,7 @@ class Transformer2DEngine:
             Q = _empty((B, H, L, 128), x)
             K = _empty((B, H, Lc, 128), x)
             V = _empty((B, H, Lc, 128), x)
-            ops.heads_pad(q, Q, B, L, d)
-            ops.heads_pad(k, K, B, Lc, d)
-            ops.heads_pad(v, V, B, Lc, d)
+            ops.heads_pad_multi([(q, Q), (k, K), (v, V)], B, d)
             o_pad = _empty((B * L, H * 128), x)  # the attention kernels write 128 columns per head, token-major
             live = 64 if d <= 64 else 128  # zero-padded half heads: the kernels skip the padding
             lse = attention.fwd(Q, K, V, None, o_pad, 0, scale=scale, head_live=live)
@@ -215,9 +213,7 @@ class Transformer2DEngine:
                 do_pad.view(B * L, H, 128)[:, :, :d].copy_(do.view(B * L, H, d))
             dQ, dK, dV = attention.bwd(s["Q"], s["K"], s["V"], None, s["o_pad"], None, do_pad, s["lse"], 0, scale=s["scale"],
                                        head_live=s["live"])
-            ops.heads_unpad(dQ, dq, B, L, d)
-            ops.heads_unpad(dK, dk, B, Lc, d)
-            ops.heads_unpad(dV, dv, B, Lc, d)
+            ops.heads_pad_multi([(dq, dQ), (dk, dK), (dv, dV)], B, d, to_heads=False)
         if self_attn:
             shared_input_bwd((a.to_q, a.to_k, a.to_v), dqkv, s["x"], s["z_qkv"], dx)
         else:

@@ -323,6 +323,10 @@ int b200_geglu_bwd(b200_ctx* ctx, const void* dy, int lddy, const void* proj, in
                    void* stream);
 int b200_heads_pad(b200_ctx* ctx, const void* src, void* dst, int ld, int B, int L, int H, int head_dim, int to_heads,
                    void* stream);
+/* the same for up to three tensors of one attention (q / k / v, or dQ / dK / dV) in ONE launch; tensor i has L_i tokens per sample
+ * (cross attention: q has L, k / v have Lk) */
+int b200_heads_pad3(b200_ctx* ctx, const void* src0, void* dst0, int ld0, int L0, const void* src1, void* dst1, int ld1, int L1,
+                    const void* src2, void* dst2, int ld2, int L2, int n, int B, int H, int head_dim, int to_heads, void* stream);
 
 /* -------------------------------------------------------------------------------------------------
  * Optimizer over the flat fp32 LoRA parameter buffer.

@@ -120,6 +120,20 @@ def test_row_kernels_vs_torch():
     back = torch.zeros(B * L, H * d, device=DEV, dtype=torch.bfloat16)
     ops.heads_unpad(hm, back, B, L, d)
     assert torch.equal(back, x[:, :H * d])
+    # three tensors of one (cross) attention in one launch: q has L tokens, k / v have Lk
+    Lk = 11
+    qkv = torch.randn(B * L, 3 * H * d, device=DEV).bfloat16()
+    kv = torch.randn(B * Lk, 2 * H * d, device=DEV).bfloat16()
+    Q = torch.full((B, H, L, 128), float("nan"), device=DEV, dtype=torch.bfloat16)
+    K = torch.full((B, H, Lk, 128), float("nan"), device=DEV, dtype=torch.bfloat16)
+    V = torch.full((B, H, Lk, 128), float("nan"), device=DEV, dtype=torch.bfloat16)
+    ops.heads_pad_multi([(qkv[:, H * d:2 * H * d], Q), (kv[:, :H * d], K), (kv[:, H * d:], V)], B, d)
+    for hm_, tm_, L_ in ((Q, qkv[:, H * d:2 * H * d], L), (K, kv[:, :H * d], Lk), (V, kv[:, H * d:], Lk)):
+        assert torch.equal(hm_[..., :d], tm_.reshape(B, L_, H, d).transpose(1, 2)) and float(hm_[..., d:].abs().sum()) == 0.0
+    dq = torch.zeros(B * L, H * d, device=DEV, dtype=torch.bfloat16)
+    dkv = torch.zeros(B * Lk, 2 * H * d, device=DEV, dtype=torch.bfloat16)
+    ops.heads_pad_multi([(dq, Q), (dkv[:, :H * d], K), (dkv[:, H * d:], V)], B, d, to_heads=False)
+    assert torch.equal(dq, qkv[:, H * d:2 * H * d]) and torch.equal(dkv, kv)
 
 
 def _setup(linear, heads, dim_head, layers, cross_dim, rank, alpha, seed=0):
