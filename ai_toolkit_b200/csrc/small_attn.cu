@@ -53,15 +53,15 @@ __device__ __forceinline__ void sa_store_row(bf16* p, const float (&v)[DPT], flo
 // dot of my DPT channels with the same channels of a bf16 row in shared memory
 template <int DPT>
 __device__ __forceinline__ float sa_dot(const float (&a)[DPT], const bf16* srow) {
-  float s = 0.f;
+  float s0 = 0.f, s1 = 0.f;  // two chains
 #pragma unroll
   for (int c = 0; c < DPT / 8; ++c) {
     const uint4 u = *reinterpret_cast<const uint4*>(srow + c * 8);
     const float2 x0 = unpack_bf16x2(u.x), x1 = unpack_bf16x2(u.y), x2 = unpack_bf16x2(u.z), x3 = unpack_bf16x2(u.w);
-    s += a[c * 8 + 0] * x0.x + a[c * 8 + 1] * x0.y + a[c * 8 + 2] * x1.x + a[c * 8 + 3] * x1.y + a[c * 8 + 4] * x2.x +
-         a[c * 8 + 5] * x2.y + a[c * 8 + 6] * x3.x + a[c * 8 + 7] * x3.y;
+    s0 += a[c * 8 + 0] * x0.x + a[c * 8 + 2] * x1.x + a[c * 8 + 4] * x2.x + a[c * 8 + 6] * x3.x;
+    s1 += a[c * 8 + 1] * x0.y + a[c * 8 + 3] * x1.y + a[c * 8 + 5] * x2.y + a[c * 8 + 7] * x3.y;
   }
-  return s;
+  return s0 + s1;
 }
 // acc += w * (bf16 row in shared memory)
 template <int DPT>
@@ -118,10 +118,16 @@ __global__ void __launch_bounds__(128) small_attn_fwd_kernel(const SmallAttnArgs
     float s[kSaTile];
     float mt = m;
 #pragma unroll
-    for (int j = 0; j < kSaTile; ++j) {
-      const float dot = sa_quad_sum(sa_dot<DPT>(q, sK + j * D + sub * DPT));
-      s[j] = (j0 + j < g.Lk) ? dot * c2 : -INFINITY;
-      mt = fmaxf(mt, s[j]);
+    for (int jb = 0; jb < kSaTile; jb += 4) {  // 4 independent dot chains in flight (one chain is 40 dependent FMAs)
+      float part[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) part[u] = sa_dot<DPT>(q, sK + (jb + u) * D + sub * DPT);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const float dot = sa_quad_sum(part[u]);
+        s[jb + u] = (j0 + jb + u < g.Lk) ? dot * c2 : -INFINITY;
+        mt = fmaxf(mt, s[jb + u]);
+      }
     }
     const float corr = (m == -INFINITY) ? 0.f : exp2f(m - mt);  // (mt is finite: every tile has at least one live key)
     l *= corr;
@@ -178,12 +184,20 @@ __global__ void __launch_bounds__(128) small_attn_bwd_q_kernel(const SmallAttnAr
     sa_stage(sK, g.k + h * D, g.ldk, kv_base, j0, g.Lk, D);
     sa_stage(sV, g.v + h * D, g.ldv, kv_base, j0, g.Lk, D);
     __syncthreads();
-#pragma unroll 4
-    for (int j = 0; j < kSaTile; ++j) {
-      const float dot = sa_quad_sum(sa_dot<DPT>(q, sK + j * D + sub * DPT));
-      const float dp = sa_quad_sum(sa_dot<DPT>(dO, sV + j * D + sub * DPT));
-      const float p = (j0 + j < g.Lk) ? exp2f(dot * c2 - lse2) : 0.f;
-      sa_axpy<DPT>(dq, p * (dp - delta) * g.scale, sK + j * D + sub * DPT);
+#pragma unroll 2
+    for (int jb = 0; jb < kSaTile; jb += 2) {  // 4 x 2 independent dot chains, then the shuffles, then the updates
+      float pd[2], pp[2];
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        pd[u] = sa_dot<DPT>(q, sK + (jb + u) * D + sub * DPT);
+        pp[u] = sa_dot<DPT>(dO, sV + (jb + u) * D + sub * DPT);
+      }
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const float dot = sa_quad_sum(pd[u]), dp = sa_quad_sum(pp[u]);
+        const float p = (j0 + jb + u < g.Lk) ? exp2f(dot * c2 - lse2) : 0.f;
+        sa_axpy<DPT>(dq, p * (dp - delta) * g.scale, sK + (jb + u) * D + sub * DPT);
+      }
     }
   }
   if (live) sa_store_row<DPT>(g.dq + qrow * g.lddq + hc, dq, 1.0f);
@@ -221,13 +235,22 @@ __global__ void __launch_bounds__(128) small_attn_bwd_kv_kernel(const SmallAttnA
       sL[kSaTile + threadIdx.x] = ok ? g.delta[static_cast<long long>(bh) * g.L + i0 + threadIdx.x] : 0.f;
     }
     __syncthreads();
-#pragma unroll 4
-    for (int i = 0; i < kSaTile; ++i) {
-      const float dot = sa_quad_sum(sa_dot<DPT>(k, sQ + i * D + sub * DPT));
-      const float dp = sa_quad_sum(sa_dot<DPT>(v, sD + i * D + sub * DPT));
-      const float p = exp2f(dot * c2 - sL[i]);  // dead query rows: exp2(-inf) = 0
-      sa_axpy<DPT>(dv, p, sD + i * D + sub * DPT);
-      sa_axpy<DPT>(dk, p * (dp - sL[kSaTile + i]) * g.scale, sQ + i * D + sub * DPT);
+#pragma unroll 2
+    for (int ib = 0; ib < kSaTile; ib += 2) {
+      float pd[2], pp[2];
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        pd[u] = sa_dot<DPT>(k, sQ + (ib + u) * D + sub * DPT);
+        pp[u] = sa_dot<DPT>(v, sD + (ib + u) * D + sub * DPT);
+      }
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int i = ib + u;
+        const float dot = sa_quad_sum(pd[u]), dp = sa_quad_sum(pp[u]);
+        const float p = exp2f(dot * c2 - sL[i]);  // dead query rows: exp2(-inf) = 0
+        sa_axpy<DPT>(dv, p, sD + i * D + sub * DPT);
+        sa_axpy<DPT>(dk, p * (dp - sL[kSaTile + i]) * g.scale, sQ + i * D + sub * DPT);
+      }
     }
   }
   if (live) {

@@ -6,6 +6,14 @@ timeout 1800 python -m pytest tests -m gpu -q -p no:cacheprovider -rs -s > gpuru
 grep -E "passed|failed|FLUX dims|100-step|\[wan\]|wan loss|SKIP" gpurun_out/r2_final_gputests.log | tail -12
 timeout 900 python bench.py --steps 10 --warmup 3 > gpurun_out/r2_final_bench.log 2>&1; echo "bench exit $?"
 grep "^{" gpurun_out/r2_final_bench.log | tail -1 | cut -c1-400
+for m in sdxl sd15 wan; do
+  timeout 900 python bench.py --model $m --steps 10 --warmup 3 > gpurun_out/r2_final_bench_$m.log 2>&1; echo "bench $m exit $?"
+  grep "^{" gpurun_out/r2_final_bench_$m.log | tail -1 | python -c "
+import sys, json
+for l in sys.stdin:
+    d = json.loads(l); print(d['metric'], '| ms/step', round(d['ms_per_step'], 2), '| e2e', round(d['e2e']['ms_per_step'], 2), '| frac', round(d['step_roofline']['frac'], 3), '| ref', {k: (round(v.get('ms_per_step', 0), 1) if isinstance(v, dict) else v) for k, v in d.get('gpu_reference', {}).items() if k in ('ms_per_step', 'checkpointing', 'no_checkpointing')})
+"
+done
 timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/r2_final_ref.log 2>&1; echo "reference arm exit $?"
 grep "^{" gpurun_out/r2_final_ref.log | tail -1 | cut -c1-300
 timeout 900 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --cache-control none --csv \
