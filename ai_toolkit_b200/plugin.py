@@ -93,6 +93,10 @@ def adopt_flux_transformer(src):
     return dst
 
 
+def _is_unet(model) -> bool:
+    return model is not None and type(model).__name__ == "UNet2DConditionModel"
+
+
 def make_trainer_class(SDTrainerBase, get_lr_scheduler=None):
     """-> `SDTrainerB200(SDTrainerBase)`.  `SDTrainerBase` is the reference's
     `extensions_built_in.sd_trainer.SDTrainer.SDTrainer`; `get_lr_scheduler` its `toolkit.scheduler.get_lr_scheduler`."""
@@ -119,6 +123,12 @@ def make_trainer_class(SDTrainerBase, get_lr_scheduler=None):
                 sd.unet = adopt_flux_transformer(sd.unet)
                 if getattr(sd, "pipeline", None) is not None and hasattr(sd.pipeline, "transformer"):
                     sd.pipeline.transformer = sd.unet
+            elif _is_unet(getattr(sd, "unet", None)):
+                # SD1.5 / SDXL: the adapter-bearing Transformer2DModel stacks move onto the engine (same tensors, same names);
+                # the frozen ResNet / sampler body stays diffusers' eager model
+                from .unet_blocks import adopt_unet_transformers
+
+                adopt_unet_transformers(sd.unet)
 
         def hook_before_train_loop(self):
             super().hook_before_train_loop()
@@ -167,9 +177,10 @@ def make_trainer_class(SDTrainerBase, get_lr_scheduler=None):
 
         def _b200_check_supported(self, batch):
             tc = self.train_config
-            if not getattr(self.sd, "is_flux", False):
-                raise NotImplementedError("sd_trainer_b200: the fused engine covers FLUX (BASELINE.json configs[2]); other "
-                                          "architectures run their adapters through LoRAModule.forward under the stock trainer")
+            if not getattr(self.sd, "is_flux", False) and not _is_unet(getattr(self.sd, "unet", None)):
+                raise NotImplementedError("sd_trainer_b200: the fused step covers FLUX and the SD1.5 / SDXL UNet (BASELINE.json "
+                                          "configs[0..2]); other architectures run their adapters through LoRAModule.forward "
+                                          "under the stock trainer")
             for flag in ("do_prior_divergence", "train_turbo", "do_guided_loss", "diff_output_preservation",
                          "blank_prompt_preservation", "inverted_mask_prior", "do_signal_amplification"):
                 if getattr(tc, flag, False):
@@ -184,6 +195,15 @@ def make_trainer_class(SDTrainerBase, get_lr_scheduler=None):
 
             key = (tuple(latents.shape), int(text_embeds.shape[1]))
             step = self._b200_steps.get(key)
+            if step is None and not getattr(self.sd, "is_flux", False):
+                from .unet import UNetLoRATrainStep
+
+                tc = self.train_config
+                step = UNetLoRATrainStep(self.sd.unet, self.network, self.optimizer,
+                                         prediction_type=str(getattr(self.sd, "prediction_type", "epsilon")),
+                                         min_snr_gamma=getattr(tc, "min_snr_gamma", None), snr_gamma=getattr(tc, "snr_gamma", None),
+                                         use_cuda_graph=True)
+                self._b200_steps[key] = step
             if step is None:
                 tc = self.train_config
                 step = FluxLoRATrainStep(self.sd.unet, self.network, self.optimizer, batch_size=latents.shape[0],
@@ -213,7 +233,7 @@ def make_trainer_class(SDTrainerBase, get_lr_scheduler=None):
                     self.network.multiplier = nw()
                 step = self._b200_step_for(b.latents, text)
                 step.load_batch(b.latents.to(device), noise.to(device), timesteps.to(device).float(), text.to(device),
-                                pooled.to(device))
+                                pooled.to(device) if pooled is not None else None)
                 first = (i == 0) and not self._b200_mid_accumulation
                 last = (i == n - 1) and not getattr(self, "is_grad_accumulation_step", False)
                 loss = step.run(first_micro_batch=first, last_micro_batch=last)

@@ -291,7 +291,10 @@ class UNetLoRATrainStep:
     def __init__(self, unet, network, optimizer, *, prediction_type="epsilon", min_snr_gamma=None, snr_gamma=None,
                  use_cuda_graph=False):
         self.unet, self.network, self.optimizer = unet, network, optimizer
-        self.dev = unet.device
+        self.dev = getattr(unet, "device", None) or next(unet.parameters()).device
+        cfg = getattr(unet, "cfg", None)  # this package's host; a diffusers UNet (adopt_unet_transformers) carries `.config`
+        self.addition_embed = bool(cfg.addition_embed) if cfg is not None else \
+            getattr(getattr(unet, "config", None), "addition_embed_type", None) == "text_time"
         self.table = DDPMTable(prediction_type=prediction_type, device=self.dev)
         self.min_snr_gamma, self.snr_gamma = min_snr_gamma, snr_gamma
         self.use_cuda_graph = use_cuda_graph
@@ -328,6 +331,8 @@ class UNetLoRATrainStep:
             raise ValueError(f"batch shape {tuple(latents.shape)} differs from the step's static buffers {tuple(b['latents'].shape)}")
         b["latents"].copy_(latents, non_blocking=True)
         b["noise"].copy_(noise, non_blocking=True)
+        if timesteps.is_floating_point():  # the trainer hands the scheduler's float timesteps over (integers for DDPM)
+            timesteps = timesteps.round().to(torch.int64)
         b["timesteps"].copy_(timesteps, non_blocking=True)
         b["text"].copy_(text_embeds, non_blocking=True)
         if pooled_embeds is not None:
@@ -342,12 +347,13 @@ class UNetLoRATrainStep:
                 src = v[k].pin_memory() if torch.device(self.dev).type == "cuda" else v[k]
                 b[k].copy_(src, non_blocking=True)
 
-    def _step(self):
+    def _step(self, zero=True, step=True):
         net, opt, b = self.network, self.optimizer, self.buf
-        opt.zero_grad()
+        if zero:
+            opt.zero_grad()
         noisy = ops.ddpm_add_noise(b["latents"], b["noise"], b["timesteps"], self.table.device_table)
         added = None
-        if self.unet.cfg.addition_embed:
+        if self.addition_embed:
             added = {"text_embeds": b["pooled"], "time_ids": b["time_ids"]}
         net.is_active = True
         try:
@@ -358,18 +364,23 @@ class UNetLoRATrainStep:
             pred.backward(dpred)
         finally:
             net.is_active = False
-        opt.step()
+        if step:
+            opt.step()
 
-    def run(self, latents=None, noise=None, timesteps=None, text_embeds=None, pooled_embeds=None, loss_multiplier=None):
+    def run(self, latents=None, noise=None, timesteps=None, text_embeds=None, pooled_embeds=None, loss_multiplier=None, *,
+            first_micro_batch=True, last_micro_batch=True):
         """latents / noise [B, 4, H, W] bf16, timesteps int64 [B], text_embeds [B, 77, Dc] bf16 (+ pooled [B, 1280] for SDXL);
-        with no arguments the resident batch is stepped again.  Returns the device loss scalar (no host sync)."""
+        with no arguments the resident batch is stepped again.  Returns the device loss scalar (no host sync).
+        Gradient accumulation as in `FluxLoRATrainStep.run`: gradients of the micro-batches are summed, the optimizer runs after
+        the last one (those partial steps are launched eagerly; the CUDA graph holds the whole single-batch step)."""
         if latents is not None:
             self.load_batch(latents, noise, timesteps, text_embeds, pooled_embeds, loss_multiplier)
         B = self.buf["latents"].shape[0]
         self.optimizer.sync_hyper()
-        if not self.use_cuda_graph or self._warm < 2:
-            self._step()
-            self._warm += 1
+        whole = first_micro_batch and last_micro_batch
+        if not self.use_cuda_graph or self._warm < 2 or not whole:
+            self._step(zero=first_micro_batch, step=last_micro_batch)
+            self._warm += 1 if whole else 0
             return self.buf["loss_ws"][B:B + 1]
         if self._graph is None:
             torch.cuda.synchronize()

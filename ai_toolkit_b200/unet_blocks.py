@@ -103,6 +103,34 @@ class Transformer2DModel(nn.Module):
         return (out,) if kwargs.get("return_dict") is False else out
 
 
+def adopt_unet_transformers(unet: nn.Module) -> int:
+    """Replace every diffusers-style `Transformer2DModel` of a LOADED UNet (any module whose class has that name and the
+    diffusers attribute layout: norm / proj_in / transformer_blocks[i].{norm1, attn1, norm2, attn2, norm3, ff.net} / proj_out) by
+    this package's container over the SAME tensors (`load_state_dict(assign=True)`: no second copy).  The rest of the UNet stays
+    the caller's eager model; kohya adapter names do not change (same class name, same attribute paths).  Returns the count."""
+    count = 0
+    for parent in list(unet.modules()):
+        for name, child in list(parent.named_children()):
+            if type(child).__name__ != "Transformer2DModel" or isinstance(child, Transformer2DModel):
+                continue
+            blk0 = child.transformer_blocks[0]
+            heads = int(blk0.attn1.heads)
+            inner = int(blk0.attn1.to_q.weight.shape[0])
+            w = child.proj_in.weight
+            with torch.device("meta"):
+                new = Transformer2DModel(heads, inner // heads, int(child.norm.num_channels), len(child.transformer_blocks),
+                                         cross_dim=int(blk0.attn2.to_k.weight.shape[1]),
+                                         use_linear_projection=isinstance(child.proj_in, nn.Linear), groups=int(child.norm.num_groups),
+                                         dtype=w.dtype)
+            if abs(float(child.norm.eps) - 1e-6) > 1e-12:
+                raise NotImplementedError(f"Transformer2DModel GroupNorm eps {child.norm.eps}: the engine's container assumes 1e-6")
+            new.load_state_dict(child.state_dict(), assign=True)
+            new.requires_grad_(False)
+            setattr(parent, name, new)
+            count += 1
+    return count
+
+
 def _anchor(model):
     """A leaf that requires grad (any live adapter weight), so that autograd calls the backward even when the input of the
     first Transformer2DModel of a UNet carries no gradient; None when no adapter is live."""

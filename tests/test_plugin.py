@@ -221,3 +221,34 @@ def test_adopt_flux_transformer_shares_storage():
     a, b = dict(src.named_parameters()), dict(dst.named_parameters())
     assert a.keys() == b.keys()
     assert all(a[k].data_ptr() == b[k].data_ptr() for k in a) and not any(p.requires_grad for p in dst.parameters())
+
+
+def test_unet_route_adopts_the_transformers_and_builds_the_unet_step(monkeypatch):
+    """SD1.5 / SDXL under `sd_trainer_b200`: `hook_after_model_load` moves the Transformer2DModels of the loaded UNet onto the
+    engine (same tensors), the supported-configuration check lets the UNet through, and the step class is `UNetLoRATrainStep`
+    with the model's prediction type and the configured min-SNR gamma."""
+    from ai_toolkit_b200.unet import UNetLoRATrainStep
+    from ai_toolkit_b200.unet_blocks import Transformer2DModel
+    from oracle import unet_ref
+
+    cls, _ = _trainer_class()
+    tr = object.__new__(cls)
+    cfg = unet_ref.UNetConfig(block_out_channels=(64, 128), attn_layers=(1, 1), heads=(1, 2), cross_attention_dim=96)
+    unet = unet_ref.init_synthetic_(unet_ref.UNet2DConditionModel(cfg), seed=2)
+    tr.sd = types.SimpleNamespace(is_flux=False, unet=unet, pipeline=None, prediction_type="v_prediction")
+    monkeypatch.setattr(type(tr).__mro__[1], "hook_after_model_load", lambda self: None, raising=False)
+    tr.hook_after_model_load()
+    assert sum(isinstance(m, Transformer2DModel) for m in unet.modules()) == 2 + 2 + 1 + 3 + 3
+    net = LoRASpecialNetwork(None, unet, lora_dim=4, alpha=4, train_text_encoder=False)
+    net.force_to("cpu", torch.float32)
+    net._update_torch_multiplier()
+    net.apply_to(None, unet, False, True)
+    tr.network = net
+    tr.optimizer = types.SimpleNamespace()
+    tr.train_config = types.SimpleNamespace(loss_type="mse", min_snr_gamma=5.0, snr_gamma=None, cfg_scale=1.0)
+    tr.adapter = tr.embedding = None
+    tr._b200_steps = {}
+    tr._b200_check_supported(None)  # does not raise for the UNet
+    step = tr._b200_step_for(torch.zeros(1, 4, 8, 8), torch.zeros(1, 77, 96))
+    assert isinstance(step, UNetLoRATrainStep) and step.table.prediction_type == "v_prediction" and step.min_snr_gamma == 5.0
+    assert tr._b200_step_for(torch.zeros(1, 4, 8, 8), torch.zeros(1, 77, 96)) is step

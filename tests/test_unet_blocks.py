@@ -67,6 +67,23 @@ def test_kohya_names_under_a_unet_identical_to_live_reference():
     assert list(sr.keys()) == list(sn.keys()) and all(torch.equal(sr[k], sn[k]) for k in sr)
 
 
+def test_adopt_unet_transformers_shares_storage_and_keeps_names():
+    """A loaded eager UNet (here the oracle's, with diffusers' attribute layout) gets its Transformer2DModels replaced by the
+    engine's containers over the SAME tensors; state-dict keys and the kohya adapter names under it do not change."""
+    from ai_toolkit_b200.unet_blocks import adopt_unet_transformers
+    _, oc = _tiny_cfgs("sdxl")
+    u = unet_ref.init_synthetic_(unet_ref.UNet2DConditionModel(oc), seed=1)
+    kw = dict(text_encoder=None, lora_dim=4, alpha=2, train_unet=True, train_text_encoder=False)
+    names_before = [l.lora_name for l in LoRASpecialNetwork(unet=u, **kw).unet_loras]
+    before = {k: v.data_ptr() for k, v in u.state_dict().items()}
+    assert adopt_unet_transformers(u) == 11 and adopt_unet_transformers(u) == 0
+    after = {k: v.data_ptr() for k, v in u.state_dict().items()}
+    assert list(before) == list(after) and all(before[k] == after[k] for k in before)
+    assert sum(isinstance(m, Transformer2DModel) for m in u.modules()) == 11
+    assert [l.lora_name for l in LoRASpecialNetwork(unet=u, **kw).unet_loras] == names_before
+    assert not any(p.requires_grad for m in u.modules() if isinstance(m, Transformer2DModel) for p in m.parameters())
+
+
 # ------------------------------------------------------------------------------------------------------------- GPU
 @pytest.mark.gpu
 def test_row_kernels_vs_torch():
@@ -373,3 +390,48 @@ def test_unet_host_step_cuda_graph_equals_eager():
     print("[unet graph] eager", le, "graph", lg)
     assert all(abs(a - b) / abs(a) < 2e-3 for a, b in zip(le, lg))
     assert _rel(runs[True][1], runs[False][1]) < 2e-3
+
+
+@pytest.mark.gpu
+def test_adopted_eager_unet_trains_like_the_host_unet():
+    """The plugin's route for SD1.5 / SDXL (`hook_after_model_load` -> `adopt_unet_transformers`): a loaded eager UNet whose
+    Transformer2DModels were adopted, stepped by `UNetLoRATrainStep` (gradient accumulation over two micro-batches, then one
+    whole step), against this package's host UNet with the same weights and adapters."""
+    from ai_toolkit_b200 import unet as host
+    from ai_toolkit_b200.optimizer import B200AdamW
+    from ai_toolkit_b200.unet_blocks import adopt_unet_transformers
+    hc, oc = _tiny_cfgs("sdxl")
+    o = unet_ref.init_synthetic_(unet_ref.UNet2DConditionModel(oc), seed=3, std=0.05).requires_grad_(False)
+    runs = {}
+    for kind in ("host", "adopted"):
+        if kind == "host":
+            m = host.UNet2DConditionModel(hc, device=DEV)
+            m.load_state_dict(o.state_dict(), strict=True)
+        else:
+            m = copy.deepcopy(o).to(DEV, torch.bfloat16)
+            assert adopt_unet_transformers(m) == 11
+        net = LoRASpecialNetwork(None, m, lora_dim=8, alpha=4, train_text_encoder=False)
+        net.force_to(DEV, torch.float32)
+        net._update_torch_multiplier()
+        net.apply_to(None, m, False, True)
+        g = torch.Generator().manual_seed(4)
+        with torch.no_grad():
+            for lora in net.unet_loras:
+                lora.lora_down.weight.copy_(torch.randn(lora.lora_down.weight.shape, generator=g) * 0.05)
+                lora.lora_up.weight.copy_(torch.randn(lora.lora_up.weight.shape, generator=g) * 0.05)
+        net.mark_params_changed()
+        opt = B200AdamW(net, lr=1e-3, max_grad_norm=1.0)
+        step = host.UNetLoRATrainStep(m, net, opt, prediction_type="epsilon", use_cuda_graph=False)
+        losses = []
+        for i in range(3):
+            lat = torch.randn(2, 4, 16, 16, generator=g).bfloat16()
+            noise = torch.randn(2, 4, 16, 16, generator=g).bfloat16()
+            text = torch.randn(2, 77, 96, generator=g).bfloat16()
+            pooled = torch.randn(2, 32, generator=g).bfloat16()
+            ts = torch.randint(1, 999, (2,), generator=g).float()  # the trainer passes float timesteps
+            first, last = (i != 1), (i != 0)                      # micro-batches 0 + 1 accumulate, batch 2 is a whole step
+            losses.append(float(step.run(lat, noise, ts, text, pooled, first_micro_batch=first, last_micro_batch=last).item()))
+        runs[kind] = (losses, net.flat_params.clone())
+    print("[adopted unet] host", runs["host"][0], "adopted", runs["adopted"][0])
+    assert all(abs(a - b) / abs(a) < 2e-3 for a, b in zip(runs["host"][0], runs["adopted"][0]))
+    assert _rel(runs["adopted"][1], runs["host"][1]) < 2e-3
