@@ -328,11 +328,10 @@ def test_unet_host_step_matches_oracle(form):
                 return out + (lx * s).to(out.dtype)
 
             mod.register_forward_hook(hook)
-        noisy = step.table.add_noise_ref(lat.float(), noise.float(), ts).to(dt) if hasattr(step.table, "add_noise_ref") else None
-        if noisy is None:
-            ac = step.table.alphas_cumprod.to(DEV)[ts].float()
-            noisy = (ac.sqrt()[:, None, None, None] * lat.float() + (1 - ac).sqrt()[:, None, None, None] * noise.float())
-            noisy = noisy.to(torch.bfloat16).to(dt)  # the kernel rounds the noisy latents to bf16 (the reference's train dtype)
+        # DDPMScheduler.add_noise on the table of the reference's training scheduler; the noisy latents are bf16 (the train dtype)
+        ac = step.table.alphas_cumprod.to(DEV)[ts].float()
+        noisy = (ac.sqrt()[:, None, None, None] * lat.float() + (1 - ac).sqrt()[:, None, None, None] * noise.float())
+        noisy = noisy.to(torch.bfloat16).to(dt)
         pred = om(noisy, ts.float(), text.to(dt), added_cond_kwargs={"text_embeds": pooled.to(dt), "time_ids": step.time_ids(B, H, W)}
                   if form == "sdxl" else None)[0]
         loss = ((pred.float() - noise.float()) ** 2).mean()
