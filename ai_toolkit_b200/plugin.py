@@ -181,20 +181,63 @@ def make_trainer_class(SDTrainerBase, get_lr_scheduler=None):
                 raise NotImplementedError("sd_trainer_b200: the fused step covers FLUX and the SD1.5 / SDXL UNet (BASELINE.json "
                                           "configs[0..2]); other architectures run their adapters through LoRAModule.forward "
                                           "under the stock trainer")
-            for flag in ("do_prior_divergence", "train_turbo", "do_guided_loss", "diff_output_preservation",
-                         "blank_prompt_preservation", "inverted_mask_prior", "do_signal_amplification"):
+            for flag in ("do_prior_divergence", "train_turbo", "do_guided_loss", "inverted_mask_prior", "do_signal_amplification"):
                 if getattr(tc, flag, False):
                     raise NotImplementedError(f"sd_trainer_b200: train.{flag} is outside the fused default path")
+            if self._b200_preserving() and not getattr(self.sd, "is_flux", False):
+                raise NotImplementedError("sd_trainer_b200: diff_output_preservation / blank_prompt_preservation are built for the "
+                                          "FLUX step (prior-prediction target); not for the UNet step")
             if getattr(self, "adapter", None) is not None or getattr(self, "embedding", None) is not None:
                 raise NotImplementedError("sd_trainer_b200: adapters / textual inversion are outside the fused default path")
             if str(getattr(tc, "loss_type", "mse")) != "mse":
                 raise NotImplementedError(f"sd_trainer_b200: loss_type {tc.loss_type!r} (the fused loss kernel is 'mse')")
 
-        def _b200_step_for(self, latents, text_embeds):
+        def _b200_preserving(self):
+            tc = self.train_config
+            return bool(getattr(tc, "diff_output_preservation", False) or getattr(tc, "blank_prompt_preservation", False))
+
+        def _b200_preservation_embeds(self, batch, conditioned_prompts, n):
+            """The embeddings of the preservation pass (SDTrainer.py:1697-1705, 1772-1790, 2184-2193): the class prompt (trigger
+            word replaced, per item) for diff_output_preservation, the blank prompt for blank_prompt_preservation."""
+            tc = self.train_config
+            if getattr(tc, "diff_output_preservation", False):
+                pe = getattr(batch, "dop_prompt_embeds", None)  # cached to disk with the trigger word replaced per dataset
+                if pe is None and getattr(self, "cached_dop_class_embeds", None) is not None:
+                    pe = self.cached_dop_class_embeds           # no per-item cache: the class-only embeds
+                if pe is None:
+                    items = getattr(batch, "file_items", None) or [None] * len(conditioned_prompts)
+
+                    def swap(prompt, item):
+                        trig = getattr(item, "trigger_word", None) or getattr(self, "trigger_word", None)
+                        return prompt if trig is None else prompt.replace(trig, tc.diff_output_preservation_class)
+
+                    with torch.no_grad():
+                        pe = self.sd.encode_prompt([swap(p, it) for p, it in zip(conditioned_prompts, items)],
+                                                   long_prompts=getattr(self, "do_long_prompts", False))
+                return pe.expand_to_batch(n) if hasattr(pe, "expand_to_batch") else pe
+            blank = getattr(self, "cached_blank_embeds", None)
+            if blank is None:
+                with torch.no_grad():
+                    blank = self.sd.encode_prompt("")
+                self.cached_blank_embeds = blank
+            return blank.expand_to_batch(n) if hasattr(blank, "expand_to_batch") else blank
+
+        def _b200_step_for(self, latents, text_embeds, preservation=False):
             from .train_step import FluxLoRATrainStep
 
-            key = (tuple(latents.shape), int(text_embeds.shape[1]))
+            key = (tuple(latents.shape), int(text_embeds.shape[1]), bool(preservation))
             step = self._b200_steps.get(key)
+            if step is None and preservation:
+                # the preservation term (SDTrainer.py:2182-2219): MSE(active prediction, inactive-network prediction) on the
+                # preservation embeddings x multiplier = the step's prior-prediction target mode, as a further micro-batch
+                tc = self.train_config
+                mult = tc.diff_output_preservation_multiplier if getattr(tc, "diff_output_preservation", False) \
+                    else tc.blank_prompt_preservation_multiplier
+                step = FluxLoRATrainStep(self.sd.unet, self.network, self.optimizer, batch_size=latents.shape[0],
+                                         latent_shape=tuple(latents.shape[1:]), text_len=int(text_embeds.shape[1]),
+                                         guidance_scale=float(getattr(tc, "cfg_scale", 1.0)), use_cuda_graph=True,
+                                         prior_target=True, loss_multiplier=float(mult))
+                self._b200_steps[key] = step
             if step is None and not getattr(self.sd, "is_flux", False):
                 from .unet import UNetLoRATrainStep
 
@@ -232,14 +275,28 @@ def make_trainer_class(SDTrainerBase, get_lr_scheduler=None):
                 if nw is not None:  # per-sample adapter strength (SDTrainer.py:1558)
                     self.network.multiplier = nw()
                 step = self._b200_step_for(b.latents, text)
-                step.load_batch(b.latents.to(device), noise.to(device), timesteps.to(device).float(), text.to(device),
-                                pooled.to(device) if pooled is not None else None)
+                lat_d, noise_d, ts_d = b.latents.to(device), noise.to(device), timesteps.to(device).float()
+                step.load_batch(lat_d, noise_d, ts_d, text.to(device), pooled.to(device) if pooled is not None else None)
                 first = (i == 0) and not self._b200_mid_accumulation
                 last = (i == n - 1) and not getattr(self, "is_grad_accumulation_step", False)
-                loss = step.run(first_micro_batch=first, last_micro_batch=last)
+                preserving = self._b200_preserving()
+                loss = step.run(first_micro_batch=first, last_micro_batch=last and not preserving)
                 step.loss_host.copy_(loss, non_blocking=True)
                 torch.cuda.current_stream().synchronize()
-                total += float(step.loss_host[0])
+                normal = float(step.loss_host[0])
+                total += normal
+                if preserving:  # second micro-batch of the same step: gradients add up, one optimizer step (loss = normal + preservation)
+                    ppe = self._b200_preservation_embeds(b, conditioned_prompts, lat_d.shape[0])
+                    pstep = self._b200_step_for(b.latents, ppe.text_embeds, preservation=True)
+                    pstep.load_batch(lat_d, noise_d, ts_d, ppe.text_embeds.to(device), ppe.pooled_embeds.to(device))
+                    ploss = pstep.run(first_micro_batch=False, last_micro_batch=last)
+                    pstep.loss_host.copy_(ploss, non_blocking=True)
+                    torch.cuda.current_stream().synchronize()
+                    pres = float(pstep.loss_host[0]) * float(getattr(pstep, "loss_multiplier", 1.0))  # (the kernel scales dpred only)
+                    total += pres
+                    logs = getattr(self, "additional_logs", None)
+                    if isinstance(logs, dict):
+                        logs["loss/normal"], logs["loss/preservation"] = normal, pres
             self._b200_mid_accumulation = bool(getattr(self, "is_grad_accumulation_step", False))
             # clip_grad_norm_, optimizer.step and ema.update already happened inside step.run (one fused launch sequence)
             self.lr_scheduler.step()

@@ -510,3 +510,42 @@ def test_prior_prediction_as_target():
     want = torch.nn.functional.mse_loss(active.float(), prior.float()).item()
     assert want > 0 and abs(out["loss"] - want) < 1e-5 * want + 1e-9
     assert float(net.flat_grads.abs().sum()) > 0
+
+
+def test_preservation_micro_batch_adds_to_the_normal_step():
+    """diff_output_preservation as the plugin runs it (SDTrainer.py:2182-2219): a normal micro-batch, then a prior-target
+    micro-batch on the class embeddings with the multiplier, ONE optimizer step.  The accumulated LoRA gradient must be
+    grad(normal) + multiplier * grad(preservation), where both are measured by separate single-pass steps."""
+    from ai_toolkit_b200.optimizer import B200AdamW
+    from ai_toolkit_b200.train_step import FluxLoRATrainStep
+    B, hl, wl, Lt = 2, 16, 16, 24
+    model, net, onets, batch = _setup(1, 1, 2, B, hl, wl, Lt, 8, seed=41, precisions=("bf16",))
+    lat, noise, t, text, pooled = batch
+    g = torch.Generator().manual_seed(5)
+    text2 = (torch.randn(text.shape, generator=g) * 0.1).bfloat16().to(DEV)       # the class-prompt embeddings
+    pooled2 = torch.randn(pooled.shape, generator=g).bfloat16().to(DEV)
+    mult = 0.5
+    opt = B200AdamW(net, lr=0.0, weight_decay=0.0, max_grad_norm=0.0)
+    kw = dict(batch_size=B, latent_shape=(16, hl, wl), text_len=Lt, use_cuda_graph=False)
+    main = FluxLoRATrainStep(model, net, opt, **kw)
+    pres = FluxLoRATrainStep(model, net, opt, prior_target=True, loss_multiplier=mult, **kw)
+    b_main = dict(latents=lat, noise=noise, timesteps=t, text_embeds=text, pooled_embeds=pooled)
+    b_pres = dict(latents=lat, noise=noise, timesteps=t, text_embeds=text2, pooled_embeds=pooled2)
+    main._load_dict(b_main)
+    l_main = float(main.run(True, True).item())
+    g_main = net.flat_grads.clone()
+    pres._load_dict(b_pres)
+    l_pres = float(pres.run(True, True).item())
+    g_pres = net.flat_grads.clone()                  # already x multiplier (gscale)
+    assert l_pres > 0 and float(g_pres.abs().sum()) > 0
+    main._load_dict(b_main)
+    la = float(main.run(first_micro_batch=True, last_micro_batch=False).item())
+    pres._load_dict(b_pres)
+    lb = float(pres.run(first_micro_batch=False, last_micro_batch=True).item())
+    assert la == pytest.approx(l_main, rel=1e-5) and lb == pytest.approx(l_pres, rel=1e-5)
+    assert _rel(net.flat_grads, g_main + g_pres) < 1e-3
+    # the gradient of the preservation pass scales with the multiplier (the reported loss does not: the plugin multiplies it)
+    pres1 = FluxLoRATrainStep(model, net, opt, prior_target=True, loss_multiplier=1.0, **kw)
+    pres1._load_dict(b_pres)
+    pres1.run(True, True)
+    assert _rel(g_pres, mult * net.flat_grads) < 2e-2   # (dpred is rounded to bf16 after the scaling)

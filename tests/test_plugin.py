@@ -252,3 +252,39 @@ def test_unet_route_adopts_the_transformers_and_builds_the_unet_step(monkeypatch
     step = tr._b200_step_for(torch.zeros(1, 4, 8, 8), torch.zeros(1, 77, 96))
     assert isinstance(step, UNetLoRATrainStep) and step.table.prediction_type == "v_prediction" and step.min_snr_gamma == 5.0
     assert tr._b200_step_for(torch.zeros(1, 4, 8, 8), torch.zeros(1, 77, 96)) is step
+
+
+def test_preservation_runs_as_a_second_micro_batch_of_the_same_step(monkeypatch):
+    """diff_output_preservation / blank_prompt_preservation (SDTrainer.py:2182-2219): normal pass, then the preservation pass
+    (prior-prediction target on the class / blank embeddings, x multiplier) with gradients summed and ONE optimizer step; the
+    loss is normal + preservation and both are logged."""
+    tr, net, log, _ = _instance(monkeypatch)
+    tr.b200_setup()
+    tr.lr_scheduler = types.SimpleNamespace(step=lambda: None)
+    tr.train_config.diff_output_preservation = True
+    tr.train_config.diff_output_preservation_multiplier = 0.5
+    tr.train_config.diff_output_preservation_class = "person"
+    tr.train_config.blank_prompt_preservation = False
+    tr.additional_logs = {}
+    class_pe = types.SimpleNamespace(text_embeds=torch.ones(1, 8, 64), pooled_embeds=torch.ones(1, 32))
+    class_pe.expand_to_batch = lambda n: class_pe
+    tr.cached_dop_class_embeds = class_pe
+    calls = []
+    fake_main, fake_pres = _FakeStep(log), _FakeStep(log)
+    fake_pres.loss_multiplier = 0.5
+
+    def step_for(latents, text, preservation=False):
+        calls.append((preservation, float(text.flatten()[0])))
+        return fake_pres if preservation else fake_main
+
+    monkeypatch.setattr(tr, "_b200_step_for", step_for, raising=False)
+    out = tr.hook_train_loop(_batch(t=250.0))
+    assert calls == [(False, 0.0), (True, 1.0)]                       # second pass on the class embeddings
+    runs = [e for e in log if e[0] == "run"]
+    assert runs == [("run", True, False), ("run", False, True)]         # zero once, optimizer once
+    assert out["loss"] == pytest.approx(1.0 + 0.5 * 1.0)               # normal + multiplier x preservation
+    assert tr.additional_logs == {"loss/normal": 1.0, "loss/preservation": 0.5}
+    # the UNet step has no prior-target mode: fail loudly
+    tr.sd.is_flux = False
+    with pytest.raises(NotImplementedError):
+        tr.hook_train_loop(_batch())
