@@ -390,6 +390,25 @@ class UNetLoRATrainStep:
         self._graph.replay()
         return self.buf["loss_ws"][B:B + 1]
 
+    # -- save / resume from the device flat buffers (BaseSDTrainProcess.save :505-721, run :2046-2060, :2189-2222) ----
+    def save(self, save_root, name, step, epoch=0, dtype=torch.float16, **kw):
+        """`{name}_{step:09d}.safetensors` with the kohya keys (`lora_unet_*.lora_down/.lora_up/.alpha`) + `optimizer.pt`."""
+        from . import checkpoint
+
+        if torch.device(self.dev).type == "cuda":
+            torch.cuda.synchronize()
+        return checkpoint.save_checkpoint(self.network, self.optimizer, save_root, name, step=step, epoch=epoch, dtype=dtype, **kw)
+
+    def resume(self, save_root, name, **kw):
+        """-> (path, step, epoch); the captured graph stays valid (same flat buffers), the operand packs are refreshed."""
+        from . import checkpoint
+
+        out = checkpoint.resume(self.network, self.optimizer, save_root, name, **kw)
+        self.network.mark_params_changed()
+        if torch.device(self.dev).type == "cuda":
+            self.network.refresh_packs(force=True)
+        return out
+
     def hook_train_loop(self, batch) -> OrderedDict:
         loss = self.run(batch["latents"], batch["noise"], batch["timesteps"], batch["text_embeds"], batch.get("pooled_embeds"))
         self.loss_host.copy_(loss, non_blocking=True)

@@ -84,6 +84,42 @@ def test_adopt_unet_transformers_shares_storage_and_keeps_names():
     assert not any(p.requires_grad for m in u.modules() if isinstance(m, Transformer2DModel) for p in m.parameters())
 
 
+def test_unet_step_save_resume_round_trip_with_kohya_keys(tmp_path):
+    """`UNetLoRATrainStep.save / resume`: the reference's file layout with kohya keys for a UNet (host logic; runs on the CPU)."""
+    from safetensors.torch import load_file
+
+    from ai_toolkit_b200 import unet as host
+    from ai_toolkit_b200.optimizer import B200AdamW
+    from ai_toolkit_b200.unet_blocks import adopt_unet_transformers
+    _, oc = _tiny_cfgs("sd15")
+
+    def build(seed):
+        u = unet_ref.init_synthetic_(unet_ref.UNet2DConditionModel(oc), seed=1)
+        adopt_unet_transformers(u)
+        torch.manual_seed(seed)
+        net = LoRASpecialNetwork(None, u, lora_dim=4, alpha=2, train_text_encoder=False)
+        net.force_to("cpu", torch.float32)
+        net._update_torch_multiplier()
+        net.apply_to(None, u, False, True)
+        with torch.no_grad():
+            for lora in net.unet_loras:
+                lora.lora_up.weight.normal_(0, 0.02)
+        opt = B200AdamW(net, lr=1e-4)
+        return host.UNetLoRATrainStep(u, net, opt, prediction_type="epsilon"), net
+
+    step, net = build(0)
+    path = step.save(str(tmp_path), "unet_lora", step=7)
+    keys = load_file(path)
+    assert "lora_unet_down_blocks_1_attentions_0_proj_in.lora_down.weight" in keys
+    assert "lora_unet_mid_block_attentions_0_transformer_blocks_0_attn2_to_k.alpha" in keys
+    step2, net2 = build(1)
+    assert not torch.equal(net2.flat_params, net.flat_params)
+    out = step2.resume(str(tmp_path), "unet_lora")
+    assert out[1] == 7
+    # saved in fp16 (save.dtype default of the reference): equal after the same rounding
+    assert torch.equal(net2.flat_params.half(), net.flat_params.half())
+
+
 # ------------------------------------------------------------------------------------------------------------- GPU
 @pytest.mark.gpu
 def test_row_kernels_vs_torch():
