@@ -216,6 +216,10 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    if getattr(args, "model", "flux") != "flux":  # the CPU arm times the headline workload; the other models carry `gpu_reference`
+        print(json.dumps({"impl": "reference", "unavailable": f"the CPU reference arm covers --model flux (BASELINE.json's metric); "
+                                                              f"--model {args.model} reports the eager reference-style step as gpu_reference"}))
+        return
     sec, times, f_sample, desc, threads = cpu_reference_sample(steps=max(3, min(args.steps, 5)), warmup=max(1, min(args.warmup, 2)),
                                                                rank=args.rank)
     f_step = flux_flops(args.batch, args.rank)[0]
