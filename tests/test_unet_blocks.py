@@ -84,6 +84,19 @@ def test_adopt_unet_transformers_shares_storage_and_keeps_names():
     assert not any(p.requires_grad for m in u.modules() if isinstance(m, Transformer2DModel) for p in m.parameters())
 
 
+def test_adopt_unet_transformers_fails_loudly_on_what_the_engine_does_not_cover():
+    from ai_toolkit_b200.unet_blocks import adopt_unet_transformers
+    u = unet_ref.UNet2DConditionModel(unet_ref.UNetConfig(block_out_channels=(64, 136 * 2), attn_layers=(1, 1), heads=(1, 2),
+                                                          cross_attention_dim=96, norm_groups=8))
+    with pytest.raises(NotImplementedError):  # head dim 136: neither <= 128 nor one of the CUDA-core kernel's 160 / 192 / 256
+        adopt_unet_transformers(u)
+    _, oc = _tiny_cfgs("sdxl")
+    u = unet_ref.UNet2DConditionModel(oc)
+    u.mid_block.attentions[0].norm.eps = 1e-5
+    with pytest.raises(NotImplementedError):  # the container's GroupNorm eps is diffusers' 1e-6
+        adopt_unet_transformers(u)
+
+
 def test_unet_step_save_resume_round_trip_with_kohya_keys(tmp_path):
     """`UNetLoRATrainStep.save / resume`: the reference's file layout with kohya keys for a UNet (host logic; runs on the CPU)."""
     from safetensors.torch import load_file
